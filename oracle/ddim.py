@@ -1,0 +1,94 @@
+"""LDM DDIM sampler math, restated on CPU (TEST INFRASTRUCTURE).
+
+Restated reference code (paths relative to /root/reference/latentdiffusion):
+  ldm/modules/diffusionmodules/util.py:21-43   make_beta_schedule ("linear": f64 linspace of sqrt)
+  ldm/models/diffusion/ddpm.py:118-127         register_schedule: alphas_cumprod (f64 cumprod -> f32)
+  ldm/modules/diffusionmodules/util.py:46-74   make_ddim_timesteps / make_ddim_sampling_parameters
+  ldm/models/diffusion/ddim.py:24-53           DDIMSampler.make_schedule
+  ldm/models/diffusion/ddim.py:115-164         ddim_sampling loop
+  ldm/models/diffusion/ddim.py:167-205         p_sample_ddim update
+
+dtype notes that matter for bit parity: alphas_cumprod is rounded to f32 when registered;
+ddim_alphas is that f32 tensor indexed; ddim_alphas_prev and ddim_sigmas are float64 numpy
+arrays built FROM the f32 values; every per-step coefficient then passes through
+``torch.full(..., fill)`` and is rounded to f32 again before the fp32 tensor arithmetic.
+"""
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+Tensor = torch.Tensor
+f32 = np.float32
+
+
+def make_beta_schedule_linear(n_timestep: int, linear_start: float, linear_end: float) -> np.ndarray:
+    """util.py:22-25."""
+    return (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2).numpy()
+
+
+def alphas_cumprod_f32(betas: np.ndarray) -> np.ndarray:
+    """ddpm.py:125-138: f64 cumprod, stored as an f32 buffer."""
+    return np.cumprod(1.0 - betas, axis=0).astype(f32)
+
+
+def make_ddim_timesteps(num_ddim: int, num_ddpm: int) -> np.ndarray:
+    """util.py:46-60, 'uniform': range(0, T, T // S) + 1."""
+    c = num_ddpm // num_ddim
+    return np.asarray(list(range(0, num_ddpm, c))) + 1
+
+
+def ddim_tables(acp_f32: np.ndarray, ddim_timesteps: np.ndarray, eta: float):
+    """util.py:63-74 + ddim.py:44-47 -> dict of float64 arrays whose f32 rounding is what
+    p_sample_ddim feeds to torch.full."""
+    a = acp_f32[ddim_timesteps].astype(f32)                           # torch f32 tensor in the reference
+    a_prev = np.asarray([float(acp_f32[0])] + [float(v) for v in acp_f32[ddim_timesteps[:-1]]])  # f64 of f32 values
+    a64 = a.astype(np.float64)
+    one_minus_a = (f32(1.0) - a).astype(f32).astype(np.float64)       # `1 - alphas` is an f32 tensor op, then widened
+    sig = eta * np.sqrt((1 - a_prev) / one_minus_a * (1 - a64 / a_prev))
+    # 1 - ddim_alphas is an f32 tensor op, np.sqrt of it stays f32
+    s1m = np.sqrt((f32(1.0) - a).astype(f32)).astype(f32)
+    return {"alphas": a.astype(np.float64), "alphas_prev": a_prev, "sigmas": sig,
+            "sqrt_one_minus_alphas": s1m.astype(np.float64)}
+
+
+def ddim_update(x: np.ndarray, e_t: np.ndarray, a_t, a_prev, sigma_t, sqrt_one_minus_at, noise: Optional[np.ndarray],
+                temperature: float = 1.0):
+    """ddim.py:190-205 in float32, one op per line (no FMA):
+        pred_x0 = (x - s1m * e) / sqrt(a_t)
+        dir_xt  = sqrt(1 - a_prev - sigma^2) * e
+        x_prev  = sqrt(a_prev) * pred_x0 + dir_xt + sigma * noise * temperature
+    """
+    a_t, a_prev, sigma_t, s1m = f32(a_t), f32(a_prev), f32(sigma_t), f32(sqrt_one_minus_at)
+    x = x.astype(f32)
+    e = e_t.astype(f32)
+    pred_x0 = ((x - (s1m * e).astype(f32)).astype(f32) / np.sqrt(a_t)).astype(f32)
+    c2 = np.sqrt(f32(f32(f32(1.0) - a_prev) - f32(sigma_t * sigma_t)))
+    dir_xt = (c2 * e).astype(f32)
+    n = np.zeros_like(x) if noise is None else noise.astype(f32)
+    nz = ((sigma_t * n).astype(f32) * f32(temperature)).astype(f32)
+    x_prev = (((np.sqrt(a_prev) * pred_x0).astype(f32) + dir_xt).astype(f32) + nz).astype(f32)
+    return x_prev, pred_x0
+
+
+@torch.no_grad()
+def ddim_sample(eps_fn: Callable[[Tensor, Tensor], Tensor], acp_f32: np.ndarray, x_T: Tensor, S: int, eta: float = 0.0,
+                noises: Optional[List[Tensor]] = None, temperature: float = 1.0, record=None) -> Tensor:
+    """ddim.py:115-164 with injected per-step noise.  eps_fn(x, t_long[B]) -> e_t."""
+    T = acp_f32.shape[0]
+    ts = make_ddim_timesteps(S, T)
+    tab = ddim_tables(acp_f32, ts, eta)
+    img = x_T.clone()
+    b = img.shape[0]
+    total = ts.shape[0]
+    for i, step in enumerate(np.flip(ts)):
+        index = total - i - 1
+        t = torch.full((b,), int(step), dtype=torch.long)
+        e_t = eps_fn(img, t).float()
+        nz = None if noises is None else noises[i].numpy()
+        x_prev, pred_x0 = ddim_update(img.numpy(), e_t.numpy(), tab["alphas"][index], tab["alphas_prev"][index],
+                                      tab["sigmas"][index], tab["sqrt_one_minus_alphas"][index], nz, temperature)
+        img = torch.from_numpy(x_prev)
+        if record is not None:
+            record.append((img.clone(), torch.from_numpy(pred_x0)))
+    return img

@@ -1,0 +1,57 @@
+"""Deterministic synthetic weights (TEST INFRASTRUCTURE).
+
+The reference zero-initialises the last conv of every ResBlock, every attention proj_out and
+the output conv (unet.py:216-218,300,719), so a random-init network returns a
+constant; parity on it would test nothing.  Instead every tensor of a ``state_dict`` is
+filled from a numpy ``RandomState`` keyed on (seed, parameter name): stable across machines
+and independent of module construction order, so the build container (which loads the tensors
+into the *reference* modules to make tests/golden) and the GPU box (which loads them into
+the CUDA modules and into oracle.nets) see identical weights without shipping them.
+"""
+import zlib
+from typing import Dict, Sequence
+
+import numpy as np
+import torch
+
+
+def synth_tensor(name: str, shape: Sequence[int], seed: int) -> torch.Tensor:
+    rs = np.random.RandomState((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+    shape = tuple(int(s) for s in shape)
+    if len(shape) <= 1:
+        v = rs.standard_normal(shape).astype(np.float32)
+        if name.endswith(".weight"):          # GroupNorm / LayerNorm scale
+            v = 1.0 + 0.1 * v
+        else:                                 # any bias
+            v = 0.05 * v
+    else:
+        fan_in = int(np.prod(shape[1:]))
+        v = (rs.standard_normal(shape) / np.sqrt(fan_in)).astype(np.float32)
+    return torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+
+
+def synth_state_dict(shapes: Dict[str, Sequence[int]], seed: int) -> Dict[str, torch.Tensor]:
+    return {k: synth_tensor(k, s, seed) for k, s in shapes.items()}
+
+
+def shapes_of(module_or_sd) -> Dict[str, tuple]:
+    sd = module_or_sd.state_dict() if hasattr(module_or_sd, "state_dict") else module_or_sd
+    return {k: tuple(v.shape) for k, v in sd.items() if v.dtype.is_floating_point}
+
+
+def exp_noise(seed: int, shape) -> np.ndarray:
+    """Exp(1) noise block for the categorical draw, float32, strictly positive."""
+    rs = np.random.RandomState(seed)
+    q = rs.standard_exponential(shape).astype(np.float32)
+    return np.maximum(q, np.float32(1e-30))
+
+
+def uniform_one_hot(seed: int, B: int, C: int, spatial) -> torch.Tensor:
+    """x_T ~ Uniform over classes, one-hot float32 [B, C, *spatial] (evaluator.py:135-136)."""
+    rs = np.random.RandomState(seed)
+    idx = rs.randint(0, C, size=(B,) + tuple(spatial))
+    return torch.from_numpy(np.moveaxis(np.eye(C, dtype=np.float32)[idx], -1, 1).copy())
+
+
+def normal(seed: int, shape) -> torch.Tensor:
+    return torch.from_numpy(np.random.RandomState(seed).standard_normal(shape).astype(np.float32))
