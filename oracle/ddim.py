@@ -44,8 +44,11 @@ def ddim_tables(acp_f32: np.ndarray, ddim_timesteps: np.ndarray, eta: float):
     a = acp_f32[ddim_timesteps].astype(f32)                           # torch f32 tensor in the reference
     a_prev = np.asarray([float(acp_f32[0])] + [float(v) for v in acp_f32[ddim_timesteps[:-1]]])  # f64 of f32 values
     a64 = a.astype(np.float64)
-    one_minus_a = (f32(1.0) - a).astype(f32).astype(np.float64)       # `1 - alphas` is an f32 tensor op, then widened
-    sig = eta * np.sqrt((1 - a_prev) / one_minus_a * (1 - a64 / a_prev))
+    # `(1 - alphas_prev) / (1 - alphas)` is ndarray(f64) / Tensor(f32): numpy defers to
+    # Tensor.__rtruediv__, which evaluates `(1 - alphas).reciprocal() * other` -- the subtraction and
+    # the reciprocal are f32 tensor ops, only the product is f64 (probe-verified, bit-exact).
+    recip = (f32(1.0) / (f32(1.0) - a).astype(f32)).astype(f32).astype(np.float64)
+    sig = eta * np.sqrt(recip * (1 - a_prev) * (1 - a64 / a_prev))
     # 1 - ddim_alphas is an f32 tensor op, np.sqrt of it stays f32
     s1m = np.sqrt((f32(1.0) - a).astype(f32)).astype(f32)
     return {"alphas": a.astype(np.float64), "alphas_prev": a_prev, "sigmas": sig,
