@@ -1,0 +1,255 @@
+/*
+ * guidegen_sm100.h -- C ABI of libguidegen_sm100.so
+ *
+ * B200 (sm_100a) kernels for the reverse-diffusion denoising step of GuideGen
+ * (OvO1111/JointImageGeneration).  The reference has no FFI/plugin layer: its "backend"
+ * is the set of torch library calls made by the Python classes on the sampling path
+ * (SURVEY.md section 2.3, K1..K16).  Each entry point below replaces one of those call
+ * sites; the reference file:line it stands in for is cited on the declaration
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ *   - the library never allocates, frees or retains device memory;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t); no host sync, no
+ *     allocation -> all calls are legal inside CUDA-graph stream capture;
+ *   - return value: 0 = ok, <0 = gg_status (bad argument / unsupported shape / alignment),
+ *     >0 = a cudaError_t raised by the launch.  There is NO fallback path of any kind.
+ *   - "CL" = channels-last bf16 activation [N, D, H, W, C] (2-D data: D = 1), C % 8 == 0.
+ */
+#ifndef GUIDEGEN_SM100_H
+#define GUIDEGEN_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gg_stream_t; /* cudaStream_t */
+
+enum gg_status {
+    GG_OK = 0,
+    GG_ERR_BAD_ARG = -1,
+    GG_ERR_UNSUPPORTED = -2,
+    GG_ERR_ALIGNMENT = -3,
+    GG_ERR_NO_DEVICE = -4,
+    GG_ERR_DRIVER = -5
+};
+
+/* library version (major*100+minor) and a static description of status codes */
+int gg_version(void);
+const char* gg_status_string(int status);
+/* 0 when the current device is compute capability 10.x, GG_ERR_NO_DEVICE otherwise */
+int gg_device_check(void);
+/* number of kernels launched by this library since load / since last reset (host counter) */
+uint64_t gg_launch_count(void);
+void gg_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K11-K13  categorical posterior + clamp + categorical draw
+ *   ccdm/ddpm/models/diffusion_denoising.py:105-139  DiffusionModel.theta_post_prob
+ *   ccdm/ddpm/models/diffusion_denoising.py:216-224  clamp(1e-12), sample / max_prob / prob
+ *   ccdm/ddpm/models/one_hot_categorical.py:25-54    OneHotCategoricalBCHW
+ * Layout is the reference's: fp32 [B, C, V] (V = D*H*W, class axis second).
+ * ---------------------------------------------------------------------------------------- */
+enum gg_cat_mode {
+    GG_CAT_POSTERIOR = 0,   /* out = theta_post_prob(xt, x0, t)                       (fp32 probs) */
+    GG_CAT_SAMPLE = 1,      /* posterior -> clamp -> normalise -> argmax(p/q) -> one-hot fp32     */
+    GG_CAT_ARGMAX = 2,      /* posterior -> clamp -> normalise -> argmax -> one-hot (fp32|int64)  */
+    GG_CAT_PROBS = 3,       /* posterior -> clamp -> normalise -> probs                            */
+    GG_CAT_SAMPLE_GIVEN = 4,/* x0 IS the distribution: normalise -> argmax(p/q) -> one-hot
+                               (OneHotCategoricalBCHW(probs).sample(), one_hot_categorical.py:30) */
+    GG_CAT_ARGMAX_GIVEN = 5 /* x0 IS the distribution: normalise -> argmax -> one-hot             */
+};
+
+typedef struct {
+    const float* x0;        /* [B, C, V] predicted x0 probabilities (or the distribution itself) */
+    const float* xt;        /* [B, C, V] current state (one-hot or soft); unused for *_GIVEN      */
+    const float* q;         /* [B*V, C]  Exp(1) noise rows (channels-last, the block
+                               torch.multinomial draws); NULL -> in-kernel Philox(seed, offset)   */
+    const float* coef;      /* [B, 2]    (alpha_t, cumalpha_{t-1}) per sample; unused for *_GIVEN */
+    float* out;             /* [B, C, V] fp32 result, may be NULL when only labels are wanted     */
+    int64_t* out_i64;       /* [B, C, V] int64 one-hot (F.one_hot dtype) or NULL                  */
+    uint8_t* labels;        /* [B, V]    drawn class index or NULL                                */
+    int32_t B, C;           /* 2 <= C <= 32                                                        */
+    int64_t V;
+    float clamp_min;        /* 1e-12 in the reference; <= 0 disables                               */
+    int32_t mode;           /* gg_cat_mode                                                         */
+    uint64_t seed, offset;  /* Philox key / counter base when q == NULL                            */
+} gg_cat_args;
+
+int gg_cat_posterior_sample(const gg_cat_args* a, gg_stream_t stream);
+
+/* Fused sampler-loop form of the same step (channels-last, stays on the device between steps):
+ * reads the head conv's fp32 logits [V_total, Cpad] (softmax fused, unet.py:720), the current
+ * labels uint8 [V_total], draws the next labels and writes the next UNet input: CL bf16
+ * [V_total, Cin_pad] = one-hot(C) | condition channel(s) | zero padding  (unet.py:775). */
+typedef struct {
+    const float* logits;    /* [Vt, Cpad] fp32 */
+    const uint8_t* labels_in;   /* [Vt] */
+    const float* q;         /* [Vt, C] Exp(1) or NULL -> Philox */
+    const float* coef;      /* [B, 2] */
+    const void* cond;       /* bf16 [Vt, n_cond] condition channels or NULL (zeros)               */
+    uint8_t* labels_out;    /* [Vt] */
+    void* next_x;           /* bf16 [Vt, Cin_pad] or NULL */
+    float* probs_out;       /* optional fp32 [B, C, V] posterior probabilities (debug/confidence) */
+    int32_t B, C, Cpad, n_cond, Cin_pad;
+    int64_t V;              /* voxels per sample; Vt = B*V */
+    float clamp_min;
+    int32_t mode;           /* GG_CAT_SAMPLE or GG_CAT_ARGMAX */
+    uint64_t seed, offset;
+} gg_cat_step_cl_args;
+
+int gg_cat_step_cl(const gg_cat_step_cl_args* a, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K14  DDIM update        latentdiffusion/ldm/models/diffusion/ddim.py:190-205 (p_sample_ddim)
+ *   pred_x0 = (x - sqrt(1-a_t) e) / sqrt(a_t);  x_prev = sqrt(a_prev) pred_x0
+ *             + sqrt(1 - a_prev - sigma^2) e + sigma * noise * temperature      (fp32, no FMA)
+ * coef (device) = [a_t, a_prev, sigma_t, sqrt_one_minus_a_t] as the f32 values torch.full makes.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* x;
+    const float* e_t;
+    const float* noise;     /* NULL: term omitted (sigma == 0, value identical to the reference) */
+    const float* coef;      /* [4] device */
+    float* x_prev;
+    float* pred_x0;         /* may be NULL */
+    int64_t n;              /* elements */
+    float temperature;
+} gg_ddim_args;
+
+int gg_ddim_update(const gg_ddim_args* a, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout bridges at the drop-in boundary (fp32 NC* <-> CL bf16)
+ *   unet.py:775 th.cat([x, input_condition], 1); ddpm.py:1419 torch.cat([x] + c_concat, 1)
+ * ---------------------------------------------------------------------------------------- */
+/* y[n, v, 0:C1+C2] = cat(x1[n, :, v], x2[n, :, v]); channels [C1+C2, Cpad) zero-filled */
+int gg_nchw_to_cl(const float* x1, int32_t C1, const float* x2, int32_t C2, void* y_cl, int32_t Cpad,
+                  int32_t N, int64_t V, gg_stream_t stream);
+/* y[n, c, v] = x_cl[n, v, c] for c < C  (bf16 or fp32 source selected by src_is_f32) */
+int gg_cl_to_nchw(const void* x_cl, int32_t Cstride, int32_t src_is_f32, float* y, int32_t C, int32_t N, int64_t V,
+                  int32_t softmax, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  GroupNorm32(32, C) (+SiLU)       ccdm .../unet_openai/nn.py:17-19,100; unet.py:189-190
+ *     fp32 statistics, eps given by caller (1e-5; SpatialTransformer's Normalize uses 1e-6).
+ *     Two-source form covers GroupNorm over th.cat([h, skip], 1) (unet.py:812 + :189).
+ * Step 1: per-(n, channel) partial sums over spatial chunks (deterministic, no atomics)
+ * Step 2: finalize -> per-(n, channel) scale/shift          (the slab all-reduce plugs in here)
+ * Step 3: y = act(x * scale + shift) written as ONE CL tensor with C1+C2 channels
+ * ---------------------------------------------------------------------------------------- */
+/* number of spatial chunks gg_gn_partial will use for S positions of C channels */
+int32_t gg_gn_num_chunks(int64_t S, int32_t C);
+/* partial: fp32 [N, nchunks, C, 2] (sum, sum of squares) */
+int gg_gn_partial(const void* x_cl, int32_t N, int64_t S, int32_t C, float* partial, gg_stream_t stream);
+typedef struct {
+    const float* partial1; int32_t C1; int32_t nchunks1;
+    const float* partial2; int32_t C2; int32_t nchunks2;   /* NULL / 0 when single source */
+    const float* gamma; const float* beta;                 /* [C1+C2] */
+    float* scale_shift;                                    /* out fp32 [N, C1+C2, 2]       */
+    int32_t N; int32_t groups; int64_t S; float eps;
+} gg_gn_finalize_args;
+int gg_gn_finalize(const gg_gn_finalize_args* a, gg_stream_t stream);
+int gg_gn_apply(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* scale_shift,
+                void* y_cl, int32_t N, int64_t S, int32_t silu, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1-K5,K15  implicit-GEMM convolution on tcgen05 tensor cores (bf16 x bf16 -> fp32 in TMEM)
+ *   nn.Conv3d / nn.Conv2d / nn.Conv1d / nn.Linear call sites:
+ *   unet.py:191,217 (ResBlock 3^d), :135-139 (Downsample stride 2), :104 (Upsample conv),
+ *   :228 (1x1 skip), :292,300 (qkv / proj_out 1x1), :522 (input conv), :719 (output conv);
+ *   openaimodel.py:207,233,107,154,244,522,688; ldm/modules/attention.py:162-169,239-259
+ * A operand = CL activations read by TMA, one 5-D box per (filter tap, 64-channel chunk): no
+ * im2col buffer; zero padding and channel padding = TMA out-of-bounds fill.  Up to 4 sources
+ * are summed into one accumulator: sources with centre_only = 0 see the full kd x kh x kw
+ * filter (two of them = conv over th.cat([h, skip], 1), K15), sources with centre_only = 1
+ * contribute a 1x1 term (the ResBlock's skip_connection fused into its second conv).
+ * Tap (a, b, c) reads input position  stride * o + (od + a, oh + b, ow + c).
+ * Packed weight matrix: bf16 [Cout, Ktot] row-major, Ktot = gg_conv_packed_k(); columns are
+ * ordered  source -> tap (a, b, c row-major) -> 64-channel chunk -> channel, channels of the
+ * last chunk of a source zero-padded to 64.
+ * Epilogue: + bias[c] + emb[n, c] + residual[n, pos, c]; bf16 or fp32 CL output through
+ * explicit element strides (so a strided view, e.g. one parity class of an upsampled
+ * grid, can be written).  bias / emb rows must be readable up to Cout rounded up to 8, and
+ * the output row must hold that many channels (padding channels receive bias only).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* x;          /* CL bf16 [N, D, H, W, C] */
+    int32_t C;              /* multiple of 8 */
+    int32_t centre_only;    /* 1: contributes only a 1x1 (centre) term */
+} gg_conv_src;
+
+typedef struct {
+    gg_conv_src src[4];
+    int32_t nsrc;
+    int32_t N, D, H, W;               /* input extents (D = 1 for 2-D data, D = H = 1 for tokens)   */
+    int32_t dims;                     /* 1, 2 or 3: spatial dims that are strided when stride = 2   */
+    int32_t kd, kh, kw;               /* taps per dim (1..3)                                         */
+    int32_t od, oh, ow;               /* input offset of tap 0 (-1 for a padded 3-tap filter)        */
+    int32_t stride;                   /* 1 or 2 (stride 2 needs 3 taps, offset -1 in strided dims)   */
+    int32_t Do, Ho, Wo;               /* output extents                                              */
+    const void* w_packed;             /* bf16 [Cout, Ktot]                                           */
+    const float* bias;                /* [>= Cout8] or NULL                                          */
+    const float* emb;                 /* fp32 [N, emb_stride] per-sample additive term or NULL       */
+    int32_t emb_stride;
+    const void* residual;             /* CL bf16 [N, Do, Ho, Wo, res_stride] or NULL                 */
+    int32_t res_stride;
+    void* y;                          /* output                                                      */
+    int64_t y_sn, y_sd, y_sh, y_sw;   /* element strides of y for n, d, h, w (multiples of 8)        */
+    int32_t y_is_f32;                 /* 0: bf16, 1: fp32                                            */
+    int32_t Cout;
+    int32_t block_n;                  /* 0 = gg_conv_pick_block_n(Cout); else multiple of 16 <= 256  */
+    int32_t brick[4];                 /* 0s = auto; else (bn, bd, bh, bw) with product 128           */
+} gg_conv_args;
+
+/* N tile (accumulator columns) the kernel uses for a given Cout */
+int32_t gg_conv_pick_block_n(int32_t Cout);
+/* K extent (columns) of the packed weight matrix for the sources / taps in `a` */
+int64_t gg_conv_packed_k(const gg_conv_args* a);
+int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream);
+
+/* K5  nearest x2 upsample in every spatial dim (unet.py:108-113), CL bf16 */
+int gg_upsample2x(const void* x_cl, void* y_cl, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t dims,
+                  gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K8/K9  attention, flash style (no T x T buffer), head dim 32 or 64, fp32 softmax
+ *   unet.py:343-360 QKVAttentionLegacy (scale ch^-1/4 on q and on k)
+ *   ldm/modules/attention.py:170-193 CrossAttention (scale d^-1/2 on the product)
+ * Generic strided heads: element (b, t, h, i) of q is q[b*q_bs + t*q_rs + h*q_hs + i].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* q; const void* k; const void* v; void* o;      /* bf16 */
+    int64_t q_bs, k_bs, v_bs, o_bs;                            /* batch strides (elements)  */
+    int32_t q_rs, k_rs, v_rs, o_rs;                            /* row (token) strides       */
+    int32_t q_hs, k_hs, v_hs, o_hs;                            /* head strides              */
+    int32_t B, H, Tq, Tk, d;
+    float scale;                                               /* applied to q.k before softmax */
+} gg_attn_args;
+int gg_attention_fwd(const gg_attn_args* a, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7/K10  small dense pieces
+ *   nn.py:103-121 timestep_embedding; unet.py:511-515 time_embed; unet.py:205-211 emb_layers
+ *   ldm/modules/attention.py:37-46 GEGLU; :204-206 nn.LayerNorm
+ * ---------------------------------------------------------------------------------------- */
+/* emb[b, :] = [cos(t_b f_i) | sin(t_b f_i)], f_i = exp(-ln(max_period) i / half); t on device */
+int gg_timestep_embedding(const float* t, float* emb, int32_t B, int32_t dim, float max_period, gg_stream_t stream);
+/* y[m, n] = sum_k act(x[m, k]) * w[n, k] + b[n]   fp32, M small (<= 64); act_in: 0 none, 1 SiLU;
+ * act_out: 0 none, 1 SiLU */
+int gg_small_linear(const float* x, const float* w, const float* b, float* y, int32_t M, int32_t N, int32_t K,
+                    int32_t act_in, int32_t act_out, gg_stream_t stream);
+/* LayerNorm over the last axis, bf16 in/out, fp32 statistics */
+int gg_layernorm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int32_t C, float eps,
+                 gg_stream_t stream);
+/* y[r, j] = x[r, j] * gelu(x[r, inner + j])  (exact erf GELU), bf16 */
+int gg_geglu(const void* x, void* y, int64_t rows, int32_t inner, gg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUIDEGEN_SM100_H */

@@ -1,0 +1,540 @@
+// conv_tcgen05.cu -- implicit-GEMM convolution / linear layer on the 5th-gen tensor cores
+//
+//   D[pos, co] = sum over (source, tap, ci)  A_src[pos + tap, ci] * W[co, (source, tap, ci)]
+//
+// * activations are channels-last bf16 [N, D, H, W, C]; a tile of BM = 128 output positions is
+//   a 4-D brick (bn, bd, bh, bw) so that ONE 5-D TMA box per (tap, 64-channel chunk) lands in
+//   shared memory already in the K-major SWIZZLE_128B layout tcgen05.mma reads: no im2col
+//   buffer, zero padding = TMA out-of-bounds fill (also pads C up to the 64-channel chunk);
+// * channel concat (th.cat skip connections), the fused 1x1 skip convolution of a ResBlock
+//   and stride-2 convolutions are just more K blocks read through other tensor maps
+//   (stride 2: one strided map per input parity class, tap -> (parity map, offset));
+// * accumulators live in TMEM (2 x 256 columns, double buffered), fp32;
+// * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+//   lane), warps 2..5 = epilogue (tcgen05.ld -> +bias +emb +residual -> bf16/fp32 stores),
+//   which overlaps the next tile's main loop.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_MAPS = 8;
+constexpr int MAX_SEGS = 4;
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int NUM_THREADS = 192;
+constexpr int ACC_COLS = 256;  // TMEM columns per accumulator buffer
+
+struct ConvSeg {
+    int map0;      // first tensor map of this segment
+    int nchunks;   // 64-channel chunks
+    int kd, kh, kw;  // tap counts
+    int od, oh, ow;  // offset of tap 0 (input coordinate = output coordinate + o + tap)
+    int stride2;   // 1: tap -> parity map (map0 + parity code) and offset {-1, 0, 0}
+    int s2d, s2h, s2w;  // which dims are strided (dims < 3 leave d (and h) unstrided)
+};
+
+struct alignas(64) ConvParams {
+    CUtensorMap amap[MAX_MAPS];
+    CUtensorMap wmap;
+    ConvSeg seg[MAX_SEGS];
+    int nseg, num_kb, stages, BN;
+    int No, Do, Ho, Wo;
+    int bn, bd, bh, bw;
+    int tn, td, th, tw;
+    int n_tiles_n, total_tiles;
+    int Cout8;
+    const float* bias;
+    const float* emb;
+    int emb_stride;
+    const __nv_bfloat16* residual;
+    int res_stride;
+    void* y;
+    long long y_sn, y_sd, y_sh, y_sw;
+    int y_is_f32;
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0, 14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset [32, 46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const int stages = p.stages;
+    const int BN = p.BN;
+    const uint32_t stage_bytes = A_BYTES + (uint32_t)BN * 128u;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tfull = empty + MAX_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < MAX_MAPS; ++i) prefetch_tmap(&p.amap[i]);
+        prefetch_tmap(&p.wmap);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_n = p.td * p.th * p.tw;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles_n;
+                int mt = tile / p.n_tiles_n;
+                const int iw = mt % p.tw; mt /= p.tw;
+                const int ih = mt % p.th; mt /= p.th;
+                const int id = mt % p.td; mt /= p.td;
+                const int n0 = mt * p.bn, d0 = id * p.bd, h0 = ih * p.bh, w0 = iw * p.bw;
+                int kb = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const ConvSeg sg = p.seg[s];
+                    for (int a = 0; a < sg.kd; ++a)
+                        for (int b = 0; b < sg.kh; ++b)
+                            for (int c = 0; c < sg.kw; ++c) {
+                                int mi = sg.map0, od, oh, ow;
+                                if (sg.stride2) {
+                                    // input = 2*o + k - 1: k=0 -> odd grid at o-1, k=1 -> even grid at o, k=2 -> odd grid at o
+                                    const int pd = sg.s2d ? ((a + 1) & 1) : 0, ph = sg.s2h ? ((b + 1) & 1) : 0,
+                                              pw = sg.s2w ? ((c + 1) & 1) : 0;
+                                    mi += pd * 4 + ph * 2 + pw;
+                                    od = sg.s2d ? (a == 0 ? -1 : 0) : sg.od + a;
+                                    oh = sg.s2h ? (b == 0 ? -1 : 0) : sg.oh + b;
+                                    ow = sg.s2w ? (c == 0 ? -1 : 0) : sg.ow + c;
+                                } else {
+                                    od = sg.od + a; oh = sg.oh + b; ow = sg.ow + c;
+                                }
+                                for (int j = 0; j < sg.nchunks; ++j) {
+                                    mbar_wait(&empty[stage], phase ^ 1u);
+                                    mbar_expect_tx(&full[stage], stage_bytes);
+                                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                                    tma_load_5d(sa, &p.amap[mi], &full[stage], j * BK, w0 + ow, h0 + oh, d0 + od, n0);
+                                    tma_load_2d(sa + A_BYTES, &p.wmap, &full[stage], kb * BK, nt * BN);
+                                    ++kb;
+                                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                                }
+                            }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 bytes per K=16 step inside the 128-byte swizzle atom (encoded >> 4)
+                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);
+                acc ^= 1u;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ================================================================ epilogue (warps 2..5)
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        uint32_t acc = 0, acc_phase = 0;
+        const int bvol = p.bd * p.bh * p.bw, bhw = p.bh * p.bw;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles_n;
+            int mt = tile / p.n_tiles_n;
+            const int iw = mt % p.tw; mt /= p.tw;
+            const int ih = mt % p.th; mt /= p.th;
+            const int id = mt % p.td; mt /= p.td;
+            const int rn = row / bvol, r1 = row - rn * bvol;
+            const int rd = r1 / bhw, r2 = r1 - rd * bhw;
+            const int rh = r2 / p.bw, rw = r2 - rh * p.bw;
+            const int n = mt * p.bn + rn, d = id * p.bd + rd, h = ih * p.bh + rh, w = iw * p.bw + rw;
+            const bool valid = n < p.No && d < p.Do && h < p.Ho && w < p.Wo;
+            const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw;
+            const long long lin = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
+            const float* embp = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
+
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(t_addr + c0, r);
+                tmem_ld_wait();
+                const int ch = nt * BN + c0;
+                if (valid && ch < p.Cout8) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int cg = ch + 8 * g;
+                        if (cg >= p.Cout8) break;
+                        float* vv = v + 8 * g;
+                        if (p.bias) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cg + 4));
+                            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+                            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+                        }
+                        if (embp) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(embp + cg));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(embp + cg + 4));
+                            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+                            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+                        }
+                        if (p.residual) {
+                            const uint4 rr = ldg_nc_u4(p.residual + lin * p.res_stride + cg);
+                            vv[0] += bf16_lo(rr.x); vv[1] += bf16_hi(rr.x); vv[2] += bf16_lo(rr.y); vv[3] += bf16_hi(rr.y);
+                            vv[4] += bf16_lo(rr.z); vv[5] += bf16_hi(rr.z); vv[6] += bf16_lo(rr.w); vv[7] += bf16_hi(rr.w);
+                        }
+                        if (p.y_is_f32) {
+                            float* yp = reinterpret_cast<float*>(p.y) + yoff + cg;
+                            *reinterpret_cast<float4*>(yp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                            *reinterpret_cast<float4*>(yp + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+                        } else {
+                            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + cg;
+                            *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16(vv[0], vv[1]), pack_bf16(vv[2], vv[3]),
+                                                                       pack_bf16(vv[4], vv[5]), pack_bf16(vv[6], vv[7]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// -------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// 5-D activation map over a (possibly strided) sub-grid of a CL tensor
+static bool encode_act_map(CUtensorMap* m, const void* base, int C, const int64_t dim[4] /*W,H,D,N extents*/,
+                           const int64_t stride_el[4] /*element strides of W,H,D,N*/, const int box[4] /*bw,bh,bd,bn*/) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)dim[0], (cuuint64_t)dim[1], (cuuint64_t)dim[2], (cuuint64_t)dim[3]};
+    cuuint64_t gstr[4] = {(cuuint64_t)stride_el[0] * 2, (cuuint64_t)stride_el[1] * 2, (cuuint64_t)stride_el[2] * 2,
+                          (cuuint64_t)stride_el[3] * 2};
+    cuuint32_t bx[5] = {(cuuint32_t)BK, (cuuint32_t)box[0], (cuuint32_t)box[1], (cuuint32_t)box[2], (cuuint32_t)box[3]};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static bool encode_w_map(CUtensorMap* m, const void* base, int64_t Ktot, int rows, int BN) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t bx[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
+static int pow2_ceil(int v) { int r = 1; while (r < v) r *= 2; return r; }
+
+// brick of 128 output positions: as much W as possible, then H, D, N (powers of two)
+static void pick_brick(int No, int Do, int Ho, int Wo, int out[4] /*bn,bd,bh,bw*/) {
+    int rem = BM;
+    int bw = std::min(rem, pow2_ceil(Wo)); rem /= bw;
+    int bh = std::min(rem, pow2_ceil(Ho)); rem /= bh;
+    int bd = std::min(rem, pow2_ceil(Do)); rem /= bd;
+    int bn = rem;  // may exceed No: rows beyond are masked
+    (void)No;
+    out[0] = bn; out[1] = bd; out[2] = bh; out[3] = bw;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" int32_t gg_conv_pick_block_n(int32_t Cout) {
+    if (Cout <= 0) return 0;
+    const int c16 = (Cout + 15) / 16 * 16;
+    if (c16 <= 256) return c16;
+    // largest multiple of 16 (<= 256) whose tiling wastes <= 6 % of the columns; else the least waste
+    int best = 256, best_waste = 1 << 30;
+    for (int bn = 256; bn >= 64; bn -= 16) {
+        const int tiles = (Cout + bn - 1) / bn;
+        const int waste = tiles * bn - Cout;
+        if (waste * 100 <= 6 * Cout) return bn;
+        if (waste < best_waste) { best_waste = waste; best = bn; }
+    }
+    return best;
+}
+
+extern "C" int64_t gg_conv_packed_k(const gg_conv_args* a) {
+    if (!a || a->nsrc < 1 || a->nsrc > 4) return -1;
+    int64_t kb = 0;
+    for (int s = 0; s < a->nsrc; ++s) {
+        const int nch = (a->src[s].C + BK - 1) / BK;
+        const int taps = a->src[s].centre_only ? 1 : a->kd * a->kh * a->kw;
+        kb += (int64_t)taps * nch;
+    }
+    return kb * BK;
+}
+
+extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
+    GG_REQUIRE(a != nullptr && a->nsrc >= 1 && a->nsrc <= MAX_SEGS, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->N > 0 && a->D > 0 && a->H > 0 && a->W > 0 && a->Cout > 0 && a->y && a->w_packed, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->kd >= 1 && a->kh >= 1 && a->kw >= 1 && a->kd <= 3 && a->kh <= 3 && a->kw <= 3, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(a->stride == 1 || a->stride == 2, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(a->Do > 0 && a->Ho > 0 && a->Wo > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE(aligned(a->y, 16) && aligned(a->w_packed, 16), GG_ERR_ALIGNMENT);
+    GG_REQUIRE(a->y_sw % 8 == 0 && a->y_sh % 8 == 0 && a->y_sd % 8 == 0 && a->y_sn % 8 == 0, GG_ERR_ALIGNMENT);
+    if (a->residual) GG_REQUIRE(aligned(a->residual, 16) && a->res_stride % 8 == 0, GG_ERR_ALIGNMENT);
+    if (a->bias) GG_REQUIRE(aligned(a->bias, 16), GG_ERR_ALIGNMENT);
+    if (a->emb) GG_REQUIRE(aligned(a->emb, 16) && a->emb_stride % 4 == 0, GG_ERR_ALIGNMENT);
+    if (!encode_fn()) return GG_ERR_DRIVER;
+
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = a->block_n > 0 ? a->block_n : gg_conv_pick_block_n(a->Cout);
+    GG_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, GG_ERR_UNSUPPORTED);
+    p.BN = BN;
+    int brick[4];
+    if (a->brick[0] > 0) {
+        for (int i = 0; i < 4; ++i) brick[i] = a->brick[i];
+        GG_REQUIRE(brick[0] * brick[1] * brick[2] * brick[3] == BM, GG_ERR_BAD_ARG);
+    } else {
+        pick_brick(a->N, a->Do, a->Ho, a->Wo, brick);
+    }
+    for (int i = 0; i < 4; ++i) GG_REQUIRE(brick[i] >= 1 && brick[i] <= 256, GG_ERR_BAD_ARG);
+    p.bn = brick[0]; p.bd = brick[1]; p.bh = brick[2]; p.bw = brick[3];
+    p.No = a->N; p.Do = a->Do; p.Ho = a->Ho; p.Wo = a->Wo;
+    p.tn = (a->N + p.bn - 1) / p.bn; p.td = (a->Do + p.bd - 1) / p.bd;
+    p.th = (a->Ho + p.bh - 1) / p.bh; p.tw = (a->Wo + p.bw - 1) / p.bw;
+    p.n_tiles_n = (a->Cout + BN - 1) / BN;
+    const int64_t total = (int64_t)p.tn * p.td * p.th * p.tw * p.n_tiles_n;
+    GG_REQUIRE(total < (1ll << 31), GG_ERR_UNSUPPORTED);
+    p.total_tiles = (int)total;
+    p.Cout8 = (a->Cout + 7) / 8 * 8;
+
+    // segments and tensor maps
+    const int box[4] = {p.bw, p.bh, p.bd, p.bn};
+    int nmaps = 0, num_kb = 0;
+    const int64_t W = a->W, H = a->H, D = a->D, N = a->N;
+    for (int s = 0; s < a->nsrc; ++s) {
+        const gg_conv_src& src = a->src[s];
+        GG_REQUIRE(src.x != nullptr && src.C > 0 && src.C % 8 == 0, GG_ERR_BAD_ARG);
+        GG_REQUIRE(aligned(src.x, 16), GG_ERR_ALIGNMENT);
+        ConvSeg& sg = p.seg[s];
+        sg.map0 = nmaps;
+        sg.nchunks = (src.C + BK - 1) / BK;
+        const int64_t C = src.C;
+        if (src.centre_only || a->stride == 1) {
+            GG_REQUIRE(nmaps + 1 <= MAX_MAPS, GG_ERR_UNSUPPORTED);
+            if (src.centre_only) {
+                sg.kd = sg.kh = sg.kw = 1;
+                sg.od = sg.oh = sg.ow = 0;
+                // centre tap of a strided conv reads the even sub-grid; of a stride-1 conv the tensor itself
+                const int64_t st = a->stride;
+                const int64_t dim[4] = {(W + st - 1) / st, a->dims >= 2 ? (H + st - 1) / st : H, a->dims >= 3 ? (D + st - 1) / st : D, N};
+                const int64_t str[4] = {C * st, W * C * (a->dims >= 2 ? st : 1), H * W * C * (a->dims >= 3 ? st : 1), D * H * W * C};
+                if (!encode_act_map(&p.amap[nmaps], src.x, src.C, dim, str, box)) return GG_ERR_DRIVER;
+            } else {
+                sg.kd = a->kd; sg.kh = a->kh; sg.kw = a->kw;
+                sg.od = a->od; sg.oh = a->oh; sg.ow = a->ow;
+                const int64_t dim[4] = {W, H, D, N};
+                const int64_t str[4] = {C, W * C, H * W * C, D * H * W * C};
+                if (!encode_act_map(&p.amap[nmaps], src.x, src.C, dim, str, box)) return GG_ERR_DRIVER;
+            }
+            nmaps += 1;
+        } else {
+            // stride 2, 3-tap (pad 1) in every strided dim: 8 parity sub-grids
+            GG_REQUIRE(nmaps + 8 <= MAX_MAPS, GG_ERR_UNSUPPORTED);
+            sg.stride2 = 1;
+            sg.s2w = 1; sg.s2h = a->dims >= 2; sg.s2d = a->dims >= 3;
+            GG_REQUIRE(a->kw == 3 && a->ow == -1, GG_ERR_UNSUPPORTED);
+            if (sg.s2h) GG_REQUIRE(a->kh == 3 && a->oh == -1, GG_ERR_UNSUPPORTED);
+            if (sg.s2d) GG_REQUIRE(a->kd == 3 && a->od == -1, GG_ERR_UNSUPPORTED);
+            sg.kd = a->kd; sg.kh = a->kh; sg.kw = a->kw;
+            sg.od = a->od; sg.oh = a->oh; sg.ow = a->ow;
+            for (int code = 0; code < 8; ++code) {
+                const int pd = (code >> 2) & 1, ph = (code >> 1) & 1, pw = code & 1;
+                const bool used = (sg.s2d || pd == 0) && (sg.s2h || ph == 0);
+                const int64_t sd = sg.s2d ? 2 : 1, sh = sg.s2h ? 2 : 1;
+                int64_t dim[4] = {(W - pw + 1) / 2, sg.s2h ? (H - ph + 1) / 2 : H, sg.s2d ? (D - pd + 1) / 2 : D, N};
+                const int64_t str[4] = {2 * C, sh * W * C, sd * H * W * C, D * H * W * C};
+                const char* base = reinterpret_cast<const char*>(src.x) + 2 * (((int64_t)pd * H + ph) * W + pw) * C;
+                if (!used || dim[0] <= 0 || dim[1] <= 0 || dim[2] <= 0) {
+                    // never addressed by the producer (or empty grid: extent-1 dims only read as zero)
+                    base = reinterpret_cast<const char*>(src.x);
+                    for (int i = 0; i < 3; ++i) if (dim[i] <= 0) dim[i] = 1;
+                    if (used) return GG_ERR_UNSUPPORTED;  // odd-parity grid empty => extent 1 in a strided dim
+                }
+                if (!encode_act_map(&p.amap[nmaps + code], base, src.C, dim, str, box)) return GG_ERR_DRIVER;
+            }
+            nmaps += 8;
+        }
+        num_kb += sg.kd * sg.kh * sg.kw * sg.nchunks;
+    }
+    // unused map slots: copy map 0 so that prefetch.tensormap never sees garbage
+    for (int i = nmaps; i < MAX_MAPS; ++i) p.amap[i] = p.amap[0];
+    p.nseg = a->nsrc;
+    p.num_kb = num_kb;
+    const int64_t Ktot = (int64_t)num_kb * BK;
+    if (!encode_w_map(&p.wmap, a->w_packed, Ktot, a->Cout, BN)) return GG_ERR_DRIVER;
+
+    const int stage_bytes = A_BYTES + BN * 128;
+    const int bar_bytes = 256;
+    int stages = (SMEM_BUDGET - 1024 - bar_bytes) / stage_bytes;
+    stages = std::min(stages, MAX_STAGES);
+    GG_REQUIRE(stages >= 2, GG_ERR_UNSUPPORTED);
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + bar_bytes + 1024;
+
+    p.bias = a->bias; p.emb = a->emb; p.emb_stride = a->emb_stride;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.res_stride = a->res_stride;
+    p.y = a->y; p.y_sn = a->y_sn; p.y_sd = a->y_sd; p.y_sh = a->y_sh; p.y_sw = a->y_sw; p.y_is_f32 = a->y_is_f32;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int grid = std::min(p.total_tiles, num_sms());
+    conv_tcgen05_kernel<<<grid, NUM_THREADS, smem, as_stream(stream)>>>(p);
+    return launch_result();
+}

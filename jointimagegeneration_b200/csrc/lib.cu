@@ -1,0 +1,36 @@
+// lib.cu -- library-level entry points of libguidegen_sm100 (version, status, launch counter)
+#include "common.cuh"
+
+namespace gg {
+std::atomic<uint64_t> g_launches{0};
+}
+
+extern "C" {
+
+int gg_version(void) { return 101; }
+
+const char* gg_status_string(int status) {
+    switch (status) {
+        case GG_OK: return "ok";
+        case GG_ERR_BAD_ARG: return "bad argument";
+        case GG_ERR_UNSUPPORTED: return "unsupported shape or configuration (no fallback path exists)";
+        case GG_ERR_ALIGNMENT: return "pointer or stride alignment";
+        case GG_ERR_NO_DEVICE: return "no sm_100 device";
+        case GG_ERR_DRIVER: return "CUDA driver entry point unavailable";
+        default: break;
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "unknown status";
+}
+
+int gg_device_check(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return GG_ERR_NO_DEVICE;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return GG_ERR_NO_DEVICE;
+    return major == 10 ? GG_OK : GG_ERR_NO_DEVICE;
+}
+
+uint64_t gg_launch_count(void) { return gg::g_launches.load(); }
+void gg_launch_count_reset(void) { gg::g_launches.store(0); }
+
+}  // extern "C"

@@ -1,0 +1,369 @@
+// norm_small.cu -- GroupNorm32 (+SiLU), LayerNorm, GEGLU, nearest upsample, timestep embedding,
+// small-M linear.  All HBM- or latency-bound; channels-last bf16 activations, fp32 statistics.
+#include "common.cuh"
+
+namespace gg {
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm step 1: per-(n, chunk, channel) partial (sum, sum of squares); deterministic
+// ------------------------------------------------------------------------------------------
+static inline int64_t gn_chunk_positions(int64_t S, int32_t C) {
+    int64_t cs = (32768 + C - 1) / C;           // ~64 KB of bf16 per block
+    cs = (cs + 7) / 8 * 8;
+    int64_t n = (S + cs - 1) / cs;
+    if (n > 2048) { cs = (S + 2047) / 2048; }
+    return cs;
+}
+
+__global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t S, int C, int64_t cs,
+                                                         int nchunks, float* __restrict__ partial) {
+    extern __shared__ float sm[];  // [R][2*C]
+    const int P8 = C >> 3;
+    const int R = 256 / P8;
+    const int oct = threadIdx.x % P8, row = threadIdx.x / P8;
+    const int chunk = blockIdx.x, n = blockIdx.y;
+    const int64_t p0 = (int64_t)chunk * cs, p1 = min(S, p0 + cs);
+    float s[8], ss[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.f; ss[e] = 0.f; }
+    if (row < R) {
+        const __nv_bfloat16* base = x + ((int64_t)n * S) * C + oct * 8;
+        int64_t p = p0 + row;
+        // two loads in flight per thread
+        for (; p + R < p1; p += 2 * R) {
+            uint4 a = ldg_nc_u4(base + p * C);
+            uint4 b = ldg_nc_u4(base + (p + R) * C);
+            const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float f0 = bf16_lo(wa[e]), f1 = bf16_hi(wa[e]), g0 = bf16_lo(wb[e]), g1 = bf16_hi(wb[e]);
+                s[2 * e] += f0 + g0; s[2 * e + 1] += f1 + g1;
+                ss[2 * e] += f0 * f0 + g0 * g0; ss[2 * e + 1] += f1 * f1 + g1 * g1;
+            }
+        }
+        for (; p < p1; p += R) {
+            uint4 a = ldg_nc_u4(base + p * C);
+            const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float f0 = bf16_lo(wa[e]), f1 = bf16_hi(wa[e]);
+                s[2 * e] += f0; s[2 * e + 1] += f1;
+                ss[2 * e] += f0 * f0; ss[2 * e + 1] += f1 * f1;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            sm[row * 2 * C + 2 * (oct * 8 + e)] = s[e];
+            sm[row * 2 * C + 2 * (oct * 8 + e) + 1] = ss[e];
+        }
+    }
+    __syncthreads();
+    float* out = partial + ((int64_t)n * nchunks + chunk) * 2 * C;
+    for (int j = threadIdx.x; j < 2 * C; j += 256) {
+        float acc = 0.f;
+        for (int r = 0; r < R; ++r) acc += sm[r * 2 * C + j];
+        out[j] = acc;
+    }
+}
+
+// step 2: group statistics in fp64 from the fp32 partials -> per-(n, channel) scale / shift
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const gg_gn_finalize_args a) {
+    const int C = a.C1 + a.C2;
+    const int cpg = C / a.groups;
+    const int g = blockIdx.x, n = blockIdx.y;
+    double s = 0.0, ss = 0.0;
+    // channels of this group may live in either source
+    for (int cc = 0; cc < cpg; ++cc) {
+        const int c = g * cpg + cc;
+        const float* part; int Cs, nch, cl;
+        if (c < a.C1) { part = a.partial1; Cs = a.C1; nch = a.nchunks1; cl = c; }
+        else { part = a.partial2; Cs = a.C2; nch = a.nchunks2; cl = c - a.C1; }
+        const float* p = part + ((int64_t)n * nch) * 2 * Cs + 2 * cl;
+        for (int k = threadIdx.x; k < nch; k += 128) {
+            s += (double)p[(int64_t)k * 2 * Cs];
+            ss += (double)p[(int64_t)k * 2 * Cs + 1];
+        }
+    }
+    __shared__ double sh[2][4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+    __syncthreads();
+    s = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+    ss = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+    const double cnt = (double)a.S * cpg;
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    for (int cc = threadIdx.x; cc < cpg; cc += 128) {
+        const int c = g * cpg + cc;
+        const float ga = a.gamma ? a.gamma[c] : 1.0f, be = a.beta ? a.beta[c] : 0.0f;
+        const float sc = ga * rstd;
+        a.scale_shift[((int64_t)n * C + c) * 2] = sc;
+        a.scale_shift[((int64_t)n * C + c) * 2 + 1] = be - (float)mean * sc;
+    }
+}
+
+// step 3: y = act(x * scale + shift), concat of two sources written as one CL tensor
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
+                                                       const __nv_bfloat16* __restrict__ x2, int C2,
+                                                       const float* __restrict__ ss, __nv_bfloat16* __restrict__ y,
+                                                       int64_t S, int64_t total, int silu) {
+    const int C = C1 + C2, P8 = C >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pos = i / P8;              // n * S + s
+        const int oct = (int)(i - pos * P8);
+        const int n = (int)(pos / S);
+        const int c0 = oct * 8;
+        uint4 v = (c0 < C1) ? ldg_nc_u4(x1 + pos * C1 + c0) : ldg_nc_u4(x2 + pos * C2 + (c0 - C1));
+        const float4* sp = reinterpret_cast<const float4*>(ss + ((int64_t)n * C + c0) * 2);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float4 k = __ldg(sp + e);      // (scale, shift) of channels c0+2e, c0+2e+1
+            float f0 = bf16_lo(w[e]) * k.x + k.y, f1 = bf16_hi(w[e]) * k.z + k.w;
+            if (silu) { f0 = silu_f(f0); f1 = silu_f(f1); }
+            o[e] = pack_bf16(f0, f1);
+        }
+        stg_na_u4(y + pos * C + c0, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (one warp per row), GEGLU, nearest x2 upsample
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                        int64_t rows, int C, float eps) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __nv_bfloat16* xr = x + row * C;
+    float s = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s += bf16_lo(w[e]) + bf16_hi(w[e]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = bf16_lo(w[e]) - mean, b = bf16_hi(w[e]) - mean;
+            q += a * a + b * b;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    __nv_bfloat16* yr = y + row * C;
+    for (int c = lane * 8; c < C; c += 256) {
+        uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int cc = c + 2 * e;
+            const float a = (bf16_lo(w[e]) - mean) * rstd * gamma[cc] + beta[cc];
+            const float b = (bf16_hi(w[e]) - mean) * rstd * gamma[cc + 1] + beta[cc + 1];
+            o[e] = pack_bf16(a, b);
+        }
+        *reinterpret_cast<uint4*>(yr + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                    int64_t rows, int inner) {
+    const int P8 = inner >> 3;
+    const int64_t total = rows * P8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / P8;
+        const int c0 = (int)(i - r * P8) * 8;
+        uint4 a = ldg_nc_u4(x + r * 2 * inner + c0), g = ldg_nc_u4(x + r * 2 * inner + inner + c0);
+        const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wg[4] = {g.x, g.y, g.z, g.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            o[e] = pack_bf16(bf16_lo(wa[e]) * gelu_erf(bf16_lo(wg[e])), bf16_hi(wa[e]) * gelu_erf(bf16_hi(wg[e])));
+        stg_na_u4(y + r * inner + c0, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                         int N, int D, int H, int W, int C, int fd, int fh, int fw) {
+    const int P8 = C >> 3;
+    const int Do = D * fd, Ho = H * fh, Wo = W * fw;
+    const int64_t total = (int64_t)N * Do * Ho * Wo * P8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t t = i;
+        const int oct = (int)(t % P8); t /= P8;
+        const int w = (int)(t % Wo); t /= Wo;
+        const int h = (int)(t % Ho); t /= Ho;
+        const int d = (int)(t % Do); t /= Do;
+        const int64_t src = ((((int64_t)t * D + d / fd) * H + h / fh) * W + w / fw) * C + oct * 8;
+        stg_na_u4(y + (i / P8) * C + oct * 8, __ldg(reinterpret_cast<const uint4*>(x + src)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// timestep embedding + small-M linear (fp32; accurate sinf/cosf/expf -- no fast-math here)
+// ------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ emb, int B, int dim, float max_period) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, j = i - b * half;
+    const float freq = expf(-logf(max_period) * (float)j / (float)half);
+    const float arg = t[b] * freq;
+    emb[(int64_t)b * dim + j] = cosf(arg);
+    emb[(int64_t)b * dim + half + j] = sinf(arg);
+    if ((dim & 1) && j == 0) emb[(int64_t)b * dim + dim - 1] = 0.f;
+}
+
+template <int MT>
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ y, int M, int N,
+                                                           int K, int act_in, int act_out) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    for (int m0 = 0; m0 < M; m0 += MT) {
+        float acc[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            const float wv = __ldg(w + (int64_t)n * K + k);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                if (m0 + m < M) {
+                    float xv = __ldg(x + (int64_t)(m0 + m) * K + k);
+                    if (act_in) xv = xv / (1.0f + expf(-xv));
+                    acc[m] += xv * wv;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            float v = acc[m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && m0 + m < M) {
+                v += bias ? bias[n] : 0.f;
+                if (act_out) v = v / (1.0f + expf(-v));
+                y[(int64_t)(m0 + m) * N + n] = v;
+            }
+        }
+    }
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" int32_t gg_gn_num_chunks(int64_t S, int32_t C) {
+    if (S <= 0 || C <= 0) return 0;
+    const int64_t cs = gn_chunk_positions(S, C);
+    return (int32_t)((S + cs - 1) / cs);
+}
+
+extern "C" int gg_gn_partial(const void* x_cl, int32_t N, int64_t S, int32_t C, float* partial, gg_stream_t stream) {
+    GG_REQUIRE(x_cl && partial && N > 0 && S > 0 && C > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE(C % 8 == 0 && C <= 2048, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(aligned(x_cl, 16), GG_ERR_ALIGNMENT);
+    const int64_t cs = gn_chunk_positions(S, C);
+    const int nchunks = (int)((S + cs - 1) / cs);
+    const int R = 256 / (C / 8);
+    const size_t smem = (size_t)R * 2 * C * sizeof(float);
+    dim3 grid(nchunks, N);
+    gn_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x_cl), S, C, cs, nchunks,
+                                                            partial);
+    return launch_result();
+}
+
+extern "C" int gg_gn_finalize(const gg_gn_finalize_args* a, gg_stream_t stream) {
+    GG_REQUIRE(a && a->partial1 && a->scale_shift && a->N > 0 && a->groups > 0 && a->S > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->C2 == 0 || a->partial2, GG_ERR_BAD_ARG);
+    GG_REQUIRE((a->C1 + a->C2) % a->groups == 0, GG_ERR_UNSUPPORTED);
+    dim3 grid(a->groups, a->N);
+    gn_finalize_kernel<<<grid, 128, 0, as_stream(stream)>>>(*a);
+    return launch_result();
+}
+
+extern "C" int gg_gn_apply(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* scale_shift, void* y_cl,
+                           int32_t N, int64_t S, int32_t silu, gg_stream_t stream) {
+    GG_REQUIRE(x1_cl && scale_shift && y_cl && N > 0 && S > 0 && C1 > 0 && C2 >= 0 && (C2 == 0 || x2_cl), GG_ERR_BAD_ARG);
+    GG_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(aligned(x1_cl, 16) && aligned(y_cl, 16) && aligned(scale_shift, 16) && (!x2_cl || aligned(x2_cl, 16)),
+               GG_ERR_ALIGNMENT);
+    const int64_t total = (int64_t)N * S * ((C1 + C2) / 8);
+    const int64_t want = (total + 255) / 256;
+    const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)num_sms() * 32);
+    gn_apply_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x1_cl), C1,
+                                                         reinterpret_cast<const __nv_bfloat16*>(x2_cl), C2, scale_shift,
+                                                         reinterpret_cast<__nv_bfloat16*>(y_cl), S, total, silu);
+    return launch_result();
+}
+
+extern "C" int gg_layernorm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int32_t C, float eps,
+                            gg_stream_t stream) {
+    GG_REQUIRE(x && gamma && beta && y && rows > 0 && C > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE(C % 8 == 0, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(aligned(x, 16) && aligned(y, 16), GG_ERR_ALIGNMENT);
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    layernorm_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+                                                          reinterpret_cast<__nv_bfloat16*>(y), rows, C, eps);
+    return launch_result();
+}
+
+extern "C" int gg_geglu(const void* x, void* y, int64_t rows, int32_t inner, gg_stream_t stream) {
+    GG_REQUIRE(x && y && rows > 0 && inner > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE(inner % 8 == 0, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(aligned(x, 16) && aligned(y, 16), GG_ERR_ALIGNMENT);
+    const int64_t total = rows * (inner / 8);
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
+    geglu_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                      reinterpret_cast<__nv_bfloat16*>(y), rows, inner);
+    return launch_result();
+}
+
+extern "C" int gg_upsample2x(const void* x_cl, void* y_cl, int32_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t dims,
+                             gg_stream_t stream) {
+    GG_REQUIRE(x_cl && y_cl && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && dims >= 1 && dims <= 3, GG_ERR_BAD_ARG);
+    GG_REQUIRE(C % 8 == 0, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(aligned(x_cl, 16) && aligned(y_cl, 16), GG_ERR_ALIGNMENT);
+    const int fd = dims >= 3 ? 2 : 1, fh = dims >= 2 ? 2 : 1, fw = 2;
+    const int64_t total = (int64_t)N * D * fd * H * fh * W * fw * (C / 8);
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
+    upsample2x_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x_cl),
+                                                           reinterpret_cast<__nv_bfloat16*>(y_cl), N, D, H, W, C, fd, fh, fw);
+    return launch_result();
+}
+
+extern "C" int gg_timestep_embedding(const float* t, float* emb, int32_t B, int32_t dim, float max_period, gg_stream_t stream) {
+    GG_REQUIRE(t && emb && B > 0 && dim >= 2, GG_ERR_BAD_ARG);
+    const int total = B * (dim / 2);
+    timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(t, emb, B, dim, max_period);
+    return launch_result();
+}
+
+extern "C" int gg_small_linear(const float* x, const float* w, const float* b, float* y, int32_t M, int32_t N, int32_t K,
+                               int32_t act_in, int32_t act_out, gg_stream_t stream) {
+    GG_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0, GG_ERR_BAD_ARG);
+    const unsigned blocks = (unsigned)((N + 7) / 8);
+    if (M <= 4) small_linear_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(x, w, b, y, M, N, K, act_in, act_out);
+    else small_linear_kernel<16><<<blocks, 256, 0, as_stream(stream)>>>(x, w, b, y, M, N, K, act_in, act_out);
+    return launch_result();
+}

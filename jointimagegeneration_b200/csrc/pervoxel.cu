@@ -1,0 +1,558 @@
+// pervoxel.cu -- HBM-bound per-voxel kernels of the two samplers (sm_100a)
+//
+//   gg_cat_posterior_sample : CCDM categorical posterior + clamp + categorical draw at the
+//                             reference's tensor interface (fp32 [B, C, V])
+//   gg_cat_step_cl          : the same step in the device-resident sampler loop (channels-last)
+//   gg_ddim_update          : LDM DDIM update
+//   gg_nchw_to_cl / gg_cl_to_nchw : layout bridges at the drop-in boundary
+//
+// Arithmetic contract (bit-exact with oracle/diffusion.py::theta_post_prob_closed and
+// categorical_sample, oracle/ddim.py::ddim_update): every operation is an explicit
+// round-to-nearest fp32 intrinsic (__fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn), which the
+// compiler never contracts into FMAs; class-axis sums run left to right.
+#include "common.cuh"
+
+namespace gg {
+
+// ------------------------------------------------------------------------------------------
+// K11-K13 at the reference interface
+// ------------------------------------------------------------------------------------------
+template <int VPT> struct VecF;
+template <> struct VecF<4> { using T = float4; };
+template <> struct VecF<2> { using T = float2; };
+template <> struct VecF<1> { using T = float; };
+
+template <int VPT>
+__device__ __forceinline__ void load_plane(const float* p, float (&dst)[VPT]) {
+    if constexpr (VPT == 4) {
+        float4 t = ldg_nc_f4(p);
+        dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+    } else if constexpr (VPT == 2) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        dst[0] = t.x; dst[1] = t.y;
+    } else {
+        dst[0] = __ldg(p);
+    }
+}
+template <int VPT>
+__device__ __forceinline__ void store_plane(float* p, const float (&src)[VPT]) {
+    if constexpr (VPT == 4) {
+        stg_na_f4(p, make_float4(src[0], src[1], src[2], src[3]));
+    } else if constexpr (VPT == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(src[0], src[1]);
+    } else {
+        p[0] = src[0];
+    }
+}
+
+template <int C, int VPT, bool VEC>
+__global__ void __launch_bounds__(256) cat_posterior_kernel(const gg_cat_args a, const int64_t groups_per_sample) {
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= groups_per_sample * a.B) return;
+    const int b = (int)(gi / groups_per_sample);
+    const int64_t v0 = (gi - (int64_t)b * groups_per_sample) * VPT;
+    const int64_t V = a.V;
+    const int mode = a.mode;
+    const bool given = (mode == GG_CAT_SAMPLE_GIVEN || mode == GG_CAT_ARGMAX_GIVEN);
+    const bool draw = (mode == GG_CAT_SAMPLE || mode == GG_CAT_SAMPLE_GIVEN);
+    int nv = VPT;
+    if (!VEC) nv = (int)min((int64_t)VPT, V - v0);
+
+    float p[C][VPT];
+    const float* x0p = a.x0 + ((int64_t)b * C) * V + v0;
+    // ---- load x0 (and xt) planes: 128-bit coalesced along the voxel axis
+    float x0v[C][VPT];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        if (VEC) load_plane<VPT>(x0p + (int64_t)c * V, x0v[c]);
+        else {
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) x0v[c][j] = j < nv ? __ldg(x0p + (int64_t)c * V + j) : 1.0f;
+        }
+    }
+    if (!given) {
+        const float* xtp = a.xt + ((int64_t)b * C) * V + v0;
+        const float al = __ldg(a.coef + 2 * b), g = __ldg(a.coef + 2 * b + 1);
+        const float k = __fdiv_rn(__fsub_rn(1.0f, al), (float)C);
+        const float h = __fdiv_rn(__fsub_rn(1.0f, g), (float)C);
+        float u[C][VPT];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float xt[VPT];
+            if (VEC) load_plane<VPT>(xtp + (int64_t)c * V, xt);
+            else {
+#pragma unroll
+                for (int j = 0; j < VPT; ++j) xt[j] = j < nv ? __ldg(xtp + (int64_t)c * V + j) : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) u[c][j] = __fadd_rn(__fmul_rn(al, xt[j]), k);
+        }
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            float U = u[0][j];
+#pragma unroll
+            for (int c = 1; c < C; ++c) U = __fadd_rn(U, u[c][j]);
+            const float hU = __fmul_rn(h, U);
+            float r[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) r[c] = __fdiv_rn(x0v[c][j], __fadd_rn(__fmul_rn(g, u[c][j]), hU));
+            float R = r[0];
+#pragma unroll
+            for (int c = 1; c < C; ++c) R = __fadd_rn(R, r[c]);
+            const float hR = __fmul_rn(h, R);
+#pragma unroll
+            for (int c = 0; c < C; ++c) p[c][j] = __fmul_rn(u[c][j], __fadd_rn(__fmul_rn(g, r[c]), hR));
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) p[c][j] = x0v[c][j];
+    }
+
+    float* outp = a.out ? a.out + ((int64_t)b * C) * V + v0 : nullptr;
+    if (mode == GG_CAT_POSTERIOR) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (VEC) store_plane<VPT>(outp + (int64_t)c * V, p[c]);
+            else {
+#pragma unroll
+                for (int j = 0; j < VPT; ++j) if (j < nv) outp[(int64_t)c * V + j] = p[c][j];
+            }
+        }
+        return;
+    }
+    // ---- clamp (diffusion_denoising.py:216) and normalise (Categorical.__init__)
+    const float cm = a.clamp_min;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        if (cm > 0.0f) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) p[c][j] = fmaxf(p[c][j], cm);
+        }
+        float P = p[0][j];
+#pragma unroll
+        for (int c = 1; c < C; ++c) P = __fadd_rn(P, p[c][j]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) p[c][j] = __fdiv_rn(p[c][j], P);
+    }
+    if (mode == GG_CAT_PROBS) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (VEC) store_plane<VPT>(outp + (int64_t)c * V, p[c]);
+            else {
+#pragma unroll
+                for (int j = 0; j < VPT; ++j) if (j < nv) outp[(int64_t)c * V + j] = p[c][j];
+            }
+        }
+        return;
+    }
+    // ---- draw: first argmax of p/q (torch.multinomial(.., 1, True)) or plain first argmax
+    int idx[VPT];
+    if (draw) {
+        const int64_t gv0 = (int64_t)b * V + v0;
+        float qv[VPT * C];
+        if (a.q != nullptr) {
+            const float* qp = a.q + gv0 * C;
+            if (VEC && (VPT * C) % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < VPT * C / 4; ++i) {
+                    float4 t = ldg_nc_f4(qp + 4 * i);
+                    qv[4 * i] = t.x; qv[4 * i + 1] = t.y; qv[4 * i + 2] = t.z; qv[4 * i + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < VPT * C; ++i) qv[i] = (i / C) < nv ? __ldg(qp + i) : 1.0f;
+            }
+        } else {
+            constexpr int NB = (C + 3) / 4;
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                const uint64_t ctr = (uint64_t)(gv0 + j) * NB;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const uint64_t cc = ctr + i;
+                    uint4 r = philox4x32_10(make_uint4((uint32_t)cc, (uint32_t)(cc >> 32), (uint32_t)a.offset,
+                                                       (uint32_t)(a.offset >> 32)),
+                                            make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * i + e < C) qv[j * C + 4 * i + e] = exp1_from_bits(rr[e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            float best = __fdiv_rn(p[0][j], qv[j * C]);
+            int bi = 0;
+#pragma unroll
+            for (int c = 1; c < C; ++c) {
+                const float r = __fdiv_rn(p[c][j], qv[j * C + c]);
+                if (r > best) { best = r; bi = c; }
+            }
+            idx[j] = bi;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            float best = p[0][j];
+            int bi = 0;
+#pragma unroll
+            for (int c = 1; c < C; ++c)
+                if (p[c][j] > best) { best = p[c][j]; bi = c; }
+            idx[j] = bi;
+        }
+    }
+    // ---- outputs
+    if (outp != nullptr) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float oh[VPT];
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) oh[j] = idx[j] == c ? 1.0f : 0.0f;
+            if (VEC) store_plane<VPT>(outp + (int64_t)c * V, oh);
+            else {
+#pragma unroll
+                for (int j = 0; j < VPT; ++j) if (j < nv) outp[(int64_t)c * V + j] = oh[j];
+            }
+        }
+    }
+    if (a.out_i64 != nullptr) {
+        int64_t* o64 = a.out_i64 + ((int64_t)b * C) * V + v0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (VEC && VPT % 2 == 0) {
+#pragma unroll
+                for (int j = 0; j < VPT; j += 2) {
+                    longlong2 t = make_longlong2(idx[j] == c, idx[j + 1] == c);
+                    *reinterpret_cast<longlong2*>(o64 + (int64_t)c * V + j) = t;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < VPT; ++j) if (j < nv) o64[(int64_t)c * V + j] = idx[j] == c;
+            }
+        }
+    }
+    if (a.labels != nullptr) {
+        uint8_t* lp = a.labels + (int64_t)b * V + v0;
+        bool done = false;
+        if constexpr (VPT == 4) {
+            if (VEC) {
+                *reinterpret_cast<uchar4*>(lp) = make_uchar4(idx[0], idx[1], idx[2], idx[3]);
+                done = true;
+            }
+        }
+        if (!done) {
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) if (j < nv) lp[j] = (uint8_t)idx[j];
+        }
+    }
+}
+
+template <int C>
+static int launch_cat(const gg_cat_args& a, cudaStream_t s) {
+    constexpr int VPT = C <= 12 ? 4 : (C <= 24 ? 2 : 1);
+    const bool vec = (a.V % VPT == 0) && aligned(a.x0, 16) && (a.xt == nullptr || aligned(a.xt, 16)) &&
+                     (a.out == nullptr || aligned(a.out, 16)) && (a.q == nullptr || aligned(a.q, 16)) &&
+                     (a.out_i64 == nullptr || aligned(a.out_i64, 16)) && (a.labels == nullptr || aligned(a.labels, 4));
+    const int64_t gps = (a.V + VPT - 1) / VPT;
+    const int64_t total = gps * a.B;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (vec) cat_posterior_kernel<C, VPT, true><<<blocks, 256, 0, s>>>(a, gps);
+    else cat_posterior_kernel<C, VPT, false><<<blocks, 256, 0, s>>>(a, gps);
+    return launch_result();
+}
+
+// ------------------------------------------------------------------------------------------
+// channels-last sampler-loop form: 4 lanes per voxel (Cpad = 16 fp32 = one 64-byte row),
+// class-axis reductions by warp shuffles (xor 1, 2)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_args a) {
+    const int64_t Vt = (int64_t)a.B * a.V;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t vox = t >> 2;
+    const int sub = (int)(t & 3);
+    const bool live = vox < Vt;
+    const int64_t vx = live ? vox : Vt - 1;
+    const int C = a.C;
+    const int b = (int)(vx / a.V);
+    // softmax over the head conv's logits (unet.py:720), classes [4*sub, 4*sub+4)
+    float4 lg = ldg_nc_f4(a.logits + vx * a.Cpad + 4 * sub);
+    float l[4] = {lg.x, lg.y, lg.z, lg.w};
+    float m = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (4 * sub + e >= C) l[e] = -INFINITY;
+        m = fmaxf(m, l[e]);
+    }
+    m = quad_max(m);
+    float ex[4], se = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { ex[e] = (4 * sub + e < C) ? expf(l[e] - m) : 0.f; se += ex[e]; }
+    se = quad_sum(se);
+    const float inv = 1.0f / se;
+    // posterior (closed form) with x_t given as a label
+    const int lab = a.labels_in[vx];
+    const float al = __ldg(a.coef + 2 * b), g = __ldg(a.coef + 2 * b + 1);
+    const float k = (1.0f - al) / (float)C, h = (1.0f - g) / (float)C;
+    float u[4], r[4], U = 0.f, R = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = 4 * sub + e;
+        u[e] = c < C ? ((c == lab ? al : 0.f) + k) : 0.f;
+        U += u[e];
+    }
+    U = quad_sum(U);
+    const float hU = h * U;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = 4 * sub + e;
+        r[e] = c < C ? (ex[e] * inv) / (g * u[e] + hU) : 0.f;
+        R += r[e];
+    }
+    R = quad_sum(R);
+    const float hR = h * R;
+    float p[4], P = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = 4 * sub + e;
+        p[e] = c < C ? fmaxf(u[e] * (g * r[e] + hR), a.clamp_min) : 0.f;
+        P += p[e];
+    }
+    P = quad_sum(P);
+    float best = -1.f;
+    int bi = 0;
+    if (a.mode == GG_CAT_SAMPLE) {
+        float q[4] = {1.f, 1.f, 1.f, 1.f};
+        if (a.q != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (4 * sub + e < C) q[e] = __ldg(a.q + vx * C + 4 * sub + e);
+        } else {
+            const uint64_t cc = (uint64_t)vx * 4 + sub;
+            uint4 rr = philox4x32_10(make_uint4((uint32_t)cc, (uint32_t)(cc >> 32), (uint32_t)a.offset,
+                                                (uint32_t)(a.offset >> 32)),
+                                     make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+            q[0] = exp1_from_bits(rr.x); q[1] = exp1_from_bits(rr.y);
+            q[2] = exp1_from_bits(rr.z); q[3] = exp1_from_bits(rr.w);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float v = (4 * sub + e < C) ? __fdiv_rn(__fdiv_rn(p[e], P), q[e]) : -1.f;
+            if (v > best) { best = v; bi = 4 * sub + e; }
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float v = (4 * sub + e < C) ? __fdiv_rn(p[e], P) : -1.f;
+            if (v > best) { best = v; bi = 4 * sub + e; }
+        }
+    }
+    // first-index argmax across the 4 lanes of the voxel
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (!live) return;
+    if (a.probs_out != nullptr) {
+        const int64_t v = vx - (int64_t)b * a.V;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (4 * sub + e < C) a.probs_out[((int64_t)b * C + 4 * sub + e) * a.V + v] = p[e];
+    }
+    if (sub == 0) a.labels_out[vx] = (uint8_t)bi;
+    if (a.next_x != nullptr) {
+        // next UNet input row: one-hot(C) | cond | zero pad, bf16, 8 channels (16 bytes) per lane
+        __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(a.next_x) + vx * a.Cin_pad;
+        const __nv_bfloat16* cond = reinterpret_cast<const __nv_bfloat16*>(a.cond);
+        for (int c0 = 8 * sub; c0 < a.Cin_pad; c0 += 32) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float f[2];
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    const int c = c0 + 2 * e + z;
+                    float v = 0.f;
+                    if (c < C) v = (c == bi) ? 1.f : 0.f;
+                    else if (c < C + a.n_cond && cond != nullptr) v = __bfloat162float(cond[vx * a.n_cond + (c - C)]);
+                    f[z] = v;
+                }
+                w[e] = pack_bf16(f[0], f[1]);
+            }
+            *reinterpret_cast<uint4*>(row + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K14  DDIM update
+// ------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) ddim_kernel(const gg_ddim_args a) {
+    const float a_t = __ldg(a.coef), a_prev = __ldg(a.coef + 1), sigma = __ldg(a.coef + 2), s1m = __ldg(a.coef + 3);
+    const float sq_at = __fsqrt_rn(a_t), sq_ap = __fsqrt_rn(a_prev);
+    const float c2 = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, a_prev), __fmul_rn(sigma, sigma)));
+    const float temp = a.temperature;
+    auto one = [&](float x, float e, float n, float& xp, float& p0) {
+        p0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(s1m, e)), sq_at);
+        const float dir = __fmul_rn(c2, e);
+        const float nz = __fmul_rn(__fmul_rn(sigma, n), temp);
+        xp = __fadd_rn(__fadd_rn(__fmul_rn(sq_ap, p0), dir), nz);
+    };
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (VEC) {
+        const int64_t i4 = i * 4;
+        if (i4 >= a.n) return;
+        float4 x = ldg_nc_f4(a.x + i4), e = ldg_nc_f4(a.e_t + i4);
+        float4 n = a.noise ? ldg_nc_f4(a.noise + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 xp, p0;
+        one(x.x, e.x, n.x, xp.x, p0.x); one(x.y, e.y, n.y, xp.y, p0.y);
+        one(x.z, e.z, n.z, xp.z, p0.z); one(x.w, e.w, n.w, xp.w, p0.w);
+        stg_na_f4(a.x_prev + i4, xp);
+        if (a.pred_x0) stg_na_f4(a.pred_x0 + i4, p0);
+    } else {
+        if (i >= a.n) return;
+        float xp, p0;
+        one(a.x[i], a.e_t[i], a.noise ? a.noise[i] : 0.f, xp, p0);
+        a.x_prev[i] = xp;
+        if (a.pred_x0) a.pred_x0[i] = p0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// layout bridges
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_cl_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
+                                                         int C2, __nv_bfloat16* __restrict__ y, int Cpad, int N, int64_t V) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * V) return;
+    const int n = (int)(i / V);
+    const int64_t v = i - (int64_t)n * V;
+    __nv_bfloat16* row = y + i * Cpad;
+    for (int c0 = 0; c0 < Cpad; c0 += 8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float f[2];
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int c = c0 + 2 * e + z;
+                float t = 0.f;
+                if (c < C1) t = __ldg(x1 + ((int64_t)n * C1 + c) * V + v);
+                else if (c < C1 + C2) t = __ldg(x2 + ((int64_t)n * C2 + (c - C1)) * V + v);
+                f[z] = t;
+            }
+            w[e] = pack_bf16(f[0], f[1]);
+        }
+        *reinterpret_cast<uint4*>(row + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(256) cl_to_nchw_kernel(const void* __restrict__ x, int Cs, float* __restrict__ y, int C,
+                                                         int N, int64_t V, int softmax) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * V) return;
+    const int n = (int)(i / V);
+    const int64_t v = i - (int64_t)n * V;
+    auto ld = [&](int c) -> float {
+        if (F32) return __ldg(reinterpret_cast<const float*>(x) + i * Cs + c);
+        return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i * Cs + c]);
+    };
+    if (softmax) {
+        float m = -INFINITY;
+        for (int c = 0; c < C; ++c) m = fmaxf(m, ld(c));
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s += expf(ld(c) - m);
+        const float inv = 1.0f / s;
+        for (int c = 0; c < C; ++c) y[((int64_t)n * C + c) * V + v] = expf(ld(c) - m) * inv;
+    } else {
+        for (int c = 0; c < C; ++c) y[((int64_t)n * C + c) * V + v] = ld(c);
+    }
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" int gg_cat_posterior_sample(const gg_cat_args* a, gg_stream_t stream) {
+    GG_REQUIRE(a != nullptr && a->x0 != nullptr, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->B > 0 && a->V > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->mode >= GG_CAT_POSTERIOR && a->mode <= GG_CAT_ARGMAX_GIVEN, GG_ERR_BAD_ARG);
+    const bool given = a->mode == GG_CAT_SAMPLE_GIVEN || a->mode == GG_CAT_ARGMAX_GIVEN;
+    if (!given) GG_REQUIRE(a->xt != nullptr && a->coef != nullptr, GG_ERR_BAD_ARG);
+    if (a->mode == GG_CAT_POSTERIOR || a->mode == GG_CAT_PROBS) GG_REQUIRE(a->out != nullptr, GG_ERR_BAD_ARG);
+    else GG_REQUIRE(a->out != nullptr || a->out_i64 != nullptr || a->labels != nullptr, GG_ERR_BAD_ARG);
+    cudaStream_t s = as_stream(stream);
+    switch (a->C) {
+#define GG_CASE(c) case c: return launch_cat<c>(*a, s);
+        GG_CASE(2) GG_CASE(3) GG_CASE(4) GG_CASE(5) GG_CASE(6) GG_CASE(7) GG_CASE(8) GG_CASE(9) GG_CASE(10)
+        GG_CASE(11) GG_CASE(12) GG_CASE(13) GG_CASE(14) GG_CASE(15) GG_CASE(16) GG_CASE(17) GG_CASE(18)
+        GG_CASE(19) GG_CASE(20) GG_CASE(21) GG_CASE(22) GG_CASE(23) GG_CASE(24)
+#undef GG_CASE
+        default: return GG_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int gg_cat_step_cl(const gg_cat_step_cl_args* a, gg_stream_t stream) {
+    GG_REQUIRE(a != nullptr && a->logits && a->labels_in && a->labels_out && a->coef, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->B > 0 && a->V > 0 && a->C >= 2, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->Cpad == 16 && a->C <= 16, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(a->mode == GG_CAT_SAMPLE || a->mode == GG_CAT_ARGMAX, GG_ERR_BAD_ARG);
+    GG_REQUIRE(aligned(a->logits, 16), GG_ERR_ALIGNMENT);
+    if (a->next_x) {
+        GG_REQUIRE(a->Cin_pad % 8 == 0 && a->Cin_pad >= a->C + a->n_cond, GG_ERR_BAD_ARG);
+        GG_REQUIRE(aligned(a->next_x, 16), GG_ERR_ALIGNMENT);
+    }
+    const int64_t threads = (int64_t)a->B * a->V * 4;
+    const unsigned blocks = (unsigned)((threads + 255) / 256);
+    cat_step_cl_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*a);
+    return launch_result();
+}
+
+extern "C" int gg_ddim_update(const gg_ddim_args* a, gg_stream_t stream) {
+    GG_REQUIRE(a != nullptr && a->x && a->e_t && a->coef && a->x_prev && a->n > 0, GG_ERR_BAD_ARG);
+    const bool vec = (a->n % 4 == 0) && aligned(a->x, 16) && aligned(a->e_t, 16) && aligned(a->x_prev, 16) &&
+                     (!a->noise || aligned(a->noise, 16)) && (!a->pred_x0 || aligned(a->pred_x0, 16));
+    if (vec) {
+        const unsigned blocks = (unsigned)((a->n / 4 + 255) / 256);
+        ddim_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(*a);
+    } else {
+        const unsigned blocks = (unsigned)((a->n + 255) / 256);
+        ddim_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(*a);
+    }
+    return launch_result();
+}
+
+extern "C" int gg_nchw_to_cl(const float* x1, int32_t C1, const float* x2, int32_t C2, void* y_cl, int32_t Cpad, int32_t N,
+                             int64_t V, gg_stream_t stream) {
+    GG_REQUIRE(x1 && y_cl && C1 > 0 && C2 >= 0 && (C2 == 0 || x2) && N > 0 && V > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE(Cpad % 8 == 0 && Cpad >= C1 + C2, GG_ERR_BAD_ARG);
+    GG_REQUIRE(aligned(y_cl, 16), GG_ERR_ALIGNMENT);
+    const unsigned blocks = (unsigned)(((int64_t)N * V + 255) / 256);
+    nchw_to_cl_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x1, C1, x2, C2, reinterpret_cast<__nv_bfloat16*>(y_cl), Cpad, N, V);
+    return launch_result();
+}
+
+extern "C" int gg_cl_to_nchw(const void* x_cl, int32_t Cstride, int32_t src_is_f32, float* y, int32_t C, int32_t N, int64_t V,
+                             int32_t softmax, gg_stream_t stream) {
+    GG_REQUIRE(x_cl && y && C > 0 && Cstride >= C && N > 0 && V > 0, GG_ERR_BAD_ARG);
+    const unsigned blocks = (unsigned)(((int64_t)N * V + 255) / 256);
+    if (src_is_f32) cl_to_nchw_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(x_cl, Cstride, y, C, N, V, softmax);
+    else cl_to_nchw_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(x_cl, Cstride, y, C, N, V, softmax);
+    return launch_result();
+}

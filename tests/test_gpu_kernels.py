@@ -1,0 +1,347 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI.
+
+Integer / label outputs: bit-exact against the CPU oracle (oracle/).  Float kernels: against
+a plain torch fp32 reference of the same op on bf16-rounded operands; tolerances are stated
+at each assert (bf16 output rounding = 2^-9 relative; fp32 accumulation order differs)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import golden  # noqa: E402
+from gpu_util import attention_ref, cl_from_nchw, conv_ref, heads_of, nchw_from_cl, no_tf32, rel_err  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from jointimagegeneration_b200 import _C, ops as o
+    assert torch.cuda.is_available()
+    _C.check(_C.lib().gg_device_check(), "gg_device_check")
+    return o
+
+
+def dev(x):
+    return torch.as_tensor(x).cuda()
+
+
+# ------------------------------------------------------------------------------ posterior
+def _posterior_case(ops, B, C, spatial, t, seed, T=1000):
+    from oracle import diffusion, weights
+    _, alphas, cumalphas = diffusion.cosine_schedule(T)
+    V = int(np.prod(spatial))
+    xt = weights.uniform_one_hot(seed, B, C, spatial)
+    rs = np.random.RandomState(seed + 1)
+    x0 = torch.softmax(torch.from_numpy(rs.standard_normal((B, C) + tuple(spatial)).astype(np.float32)) * 3, 1)
+    q = weights.exp_noise(seed + 2, (B * V, C))
+    a, g = diffusion.step_coefficients(alphas, cumalphas, t)
+    coef = torch.tensor([[a, g]] * B, dtype=torch.float32)
+    return xt, x0, q, coef, a, g, V
+
+
+@pytest.mark.parametrize("B,C,spatial,t", [(2, 12, (4, 8, 8), 1000), (2, 12, (4, 8, 8), 500), (2, 12, (4, 8, 8), 2),
+                                           (2, 12, (4, 8, 8), 1), (1, 12, (32, 32, 32), 777), (3, 4, (5, 7, 3), 17),
+                                           (2, 19, (6, 10), 300), (1, 2, (3, 3, 3), 9), (2, 12, (3, 5, 7), 640)])
+def test_posterior_and_sampling_bit_exact(ops, B, C, spatial, t):
+    """posterior probs, sampled labels, argmax labels and normalised probs: bit-exact vs oracle
+    (covers ragged V % 4 != 0 shapes -> scalar path, and C from 2 to 19)."""
+    from oracle import diffusion
+    xt, x0, q, coef, a, g, V = _posterior_case(ops, B, C, spatial, t, seed=100 + t)
+    xt_n, x0_n = xt.reshape(B, C, V).numpy(), x0.reshape(B, C, V).numpy()
+    want = np.stack([diffusion.theta_post_prob_closed(a, g, xt_n[b], x0_n[b]) for b in range(B)])
+    got, _, _ = ops.cat_posterior_sample(dev(x0), dev(xt), dev(coef), ops.CAT_POSTERIOR)
+    assert np.array_equal(got.reshape(B, C, V).cpu().numpy(), want), "posterior not bit-exact"
+    # sample
+    clamped = np.maximum(want, np.float32(1e-12))
+    qb = q.reshape(B, V, C)
+    idx = np.stack([diffusion.categorical_sample(clamped[b], qb[b]) for b in range(B)])
+    labels = torch.empty((B, V), dtype=torch.uint8, device="cuda")
+    out = torch.empty_like(dev(x0))
+    ops.cat_posterior_sample(dev(x0), dev(xt), dev(coef), ops.CAT_SAMPLE, q=dev(q), out=out, labels=labels)
+    assert np.array_equal(labels.cpu().numpy(), idx.astype(np.uint8)), "sampled labels differ"
+    oh = np.stack([diffusion.one_hot(idx[b], C) for b in range(B)])
+    assert np.array_equal(out.reshape(B, C, V).cpu().numpy(), oh)
+    # argmax (last step, 'majority') with int64 one-hot like F.one_hot
+    S = clamped[:, 0].copy()
+    for c in range(1, C):
+        S = (S + clamped[:, c]).astype(np.float32)
+    pn = (clamped / S[:, None]).astype(np.float32)
+    o64 = torch.empty(x0.shape, dtype=torch.int64, device="cuda")
+    ops.cat_posterior_sample(dev(x0), dev(xt), dev(coef), ops.CAT_ARGMAX, out=None, out_i64=o64, labels=labels)
+    assert np.array_equal(labels.cpu().numpy(), pn.argmax(1).astype(np.uint8))
+    assert np.array_equal(o64.reshape(B, C, V).argmax(1).cpu().numpy(), pn.argmax(1))
+    assert int(o64.sum()) == B * V
+    # normalised probabilities ('confidence')
+    pr, _, _ = ops.cat_posterior_sample(dev(x0), dev(xt), dev(coef), ops.CAT_PROBS)
+    assert np.array_equal(pr.reshape(B, C, V).cpu().numpy(), pn)
+
+
+def test_posterior_matches_reference_golden(ops):
+    """Against vectors produced by the UNMODIFIED reference's theta_post_prob (tests/golden)."""
+    from oracle import diffusion, weights
+    g = golden("posterior_cases")
+    C, B, spatial = int(g["C"]), int(g["B"]), tuple(g["spatial"])
+    _, alphas, cumalphas = diffusion.cosine_schedule(1000)
+    for t in (1, 2, 17, 500, 999, 1000):
+        xt = weights.uniform_one_hot(100 + t, B, C, spatial)
+        a, gg = diffusion.step_coefficients(alphas, cumalphas, t)
+        coef = torch.tensor([[a, gg]] * B, dtype=torch.float32)
+        got, _, _ = ops.cat_posterior_sample(dev(g[f"x0_{t}"]), dev(xt), dev(coef), ops.CAT_POSTERIOR)
+        # closed form vs the reference's O(C^2) einsum: <= 1e-6 abs (different fp32 evaluation order)
+        assert np.abs(got.cpu().numpy() - g[f"post_{t}"]).max() <= 1e-6
+    coef = torch.tensor([list(diffusion.step_coefficients(alphas, cumalphas, 300))] * B, dtype=torch.float32)
+    got, _, _ = ops.cat_posterior_sample(dev(g["soft_x0"]), dev(g["soft_xt"]), dev(coef), ops.CAT_POSTERIOR)
+    assert np.abs(got.cpu().numpy() - g["soft_post_300"]).max() <= 1e-6
+
+
+def test_sample_given_and_philox(ops):
+    from oracle import diffusion, weights
+    B, C, spatial = 2, 12, (4, 4, 8)
+    V = int(np.prod(spatial))
+    p = torch.softmax(torch.from_numpy(np.random.RandomState(5).standard_normal((B, C) + spatial).astype(np.float32)), 1)
+    q = weights.exp_noise(6, (B * V, C))
+    labels = torch.empty((B, V), dtype=torch.uint8, device="cuda")
+    ops.cat_posterior_sample(dev(p), None, None, ops.CAT_SAMPLE_GIVEN, q=dev(q), clamp_min=0.0, labels=labels)
+    want = np.stack([diffusion.categorical_sample(p[b].reshape(C, V).numpy(), q.reshape(B, V, C)[b]) for b in range(B)])
+    assert np.array_equal(labels.cpu().numpy(), want.astype(np.uint8))
+    # in-kernel Philox: deterministic per (seed, offset), different across offsets, uniform-ish over classes
+    big = torch.full((1, C, 64, 64, 16), 1.0 / C, device="cuda")
+    l1 = torch.empty((1, 65536), dtype=torch.uint8, device="cuda")
+    l2 = torch.empty_like(l1)
+    l3 = torch.empty_like(l1)
+    ops.cat_posterior_sample(big, None, None, ops.CAT_SAMPLE_GIVEN, clamp_min=0.0, labels=l1, seed=7, offset=1)
+    ops.cat_posterior_sample(big, None, None, ops.CAT_SAMPLE_GIVEN, clamp_min=0.0, labels=l2, seed=7, offset=1)
+    ops.cat_posterior_sample(big, None, None, ops.CAT_SAMPLE_GIVEN, clamp_min=0.0, labels=l3, seed=7, offset=2)
+    assert torch.equal(l1, l2) and not torch.equal(l1, l3)
+    hist = torch.bincount(l1.flatten().long(), minlength=C).float() / 65536
+    assert float((hist - 1.0 / C).abs().max()) < 0.01
+
+
+def test_cat_step_cl_matches_oracle_outside_near_ties(ops):
+    from oracle import diffusion, weights
+    B, C, spatial, t = 2, 12, (4, 8, 8), 400
+    V = int(np.prod(spatial))
+    _, alphas, cumalphas = diffusion.cosine_schedule(1000)
+    a, g = diffusion.step_coefficients(alphas, cumalphas, t)
+    rs = np.random.RandomState(3)
+    logits = rs.standard_normal((B * V, 16)).astype(np.float32) * 2
+    lab = rs.randint(0, C, size=(B * V,)).astype(np.uint8)
+    q = weights.exp_noise(4, (B * V, C))
+    x0 = torch.softmax(torch.from_numpy(logits[:, :C]), -1).numpy().reshape(B, V, C).transpose(0, 2, 1)
+    xt = np.eye(C, dtype=np.float32)[lab].reshape(B, V, C).transpose(0, 2, 1)
+    probs = np.stack([diffusion.theta_post_prob_closed(a, g, xt[b], x0[b]) for b in range(B)])
+    probs = np.maximum(probs, np.float32(1e-12))
+    want = np.stack([diffusion.categorical_sample(probs[b], q.reshape(B, V, C)[b]) for b in range(B)]).reshape(-1)
+    tie = np.stack([diffusion.near_tie_mask(probs[b], q.reshape(B, V, C)[b], rel=1e-4) for b in range(B)]).reshape(-1)
+    coef = torch.tensor([[a, g]] * B, dtype=torch.float32)
+    lout = torch.empty(B * V, dtype=torch.uint8, device="cuda")
+    nx = torch.empty((B * V, 16), dtype=torch.bfloat16, device="cuda")
+    pout = torch.empty((B, C, V), dtype=torch.float32, device="cuda")
+    ops.cat_step_cl(dev(logits), dev(lab), dev(coef), lout, B, V, C, q=dev(q), next_x=nx, probs_out=pout)
+    got = lout.cpu().numpy()
+    assert np.array_equal(got[~tie], want[~tie].astype(np.uint8))
+    assert tie.mean() < 0.01
+    # fused softmax + posterior (shuffle-order sums, expf): 1e-5 relative to the largest prob
+    assert np.abs(pout.cpu().numpy() - probs).max() <= 1e-5
+    nxr = nx.float().cpu().numpy()
+    assert np.array_equal(nxr[:, :C].argmax(1), got) and np.all(nxr[:, C:] == 0) and np.all(nxr.sum(1) == 1)
+
+
+# ------------------------------------------------------------------------------------ DDIM
+@pytest.mark.parametrize("shape,eta", [((2, 4, 16, 16), 0.0), ((2, 4, 16, 16), 0.5), ((3, 1, 5, 7), 1.0), ((16, 4, 64, 64), 0.0)])
+def test_ddim_update_bit_exact(ops, shape, eta):
+    from oracle import configs, ddim
+    betas = ddim.make_beta_schedule_linear(1000, configs.LDM_SCHEDULE["linear_start"], configs.LDM_SCHEDULE["linear_end"])
+    acp = ddim.alphas_cumprod_f32(betas)
+    ts = ddim.make_ddim_timesteps(50, 1000)
+    tab = ddim.ddim_tables(acp, ts, eta)
+    rs = np.random.RandomState(11)
+    x = rs.standard_normal(shape).astype(np.float32)
+    e = rs.standard_normal(shape).astype(np.float32)
+    nz = rs.standard_normal(shape).astype(np.float32)
+    for index in (49, 20, 0):
+        co = [tab["alphas"][index], tab["alphas_prev"][index], tab["sigmas"][index], tab["sqrt_one_minus_alphas"][index]]
+        want_prev, want_x0 = ddim.ddim_update(x, e, *co, nz, 1.0)
+        coef = torch.tensor(co, dtype=torch.float64).float().cuda()
+        got_prev, got_x0 = ops.ddim_update(dev(x), dev(e), coef, dev(nz))
+        assert np.array_equal(got_prev.cpu().numpy(), want_prev) and np.array_equal(got_x0.cpu().numpy(), want_x0)
+        if eta == 0.0:  # noise pointer omitted == reference value (sigma = 0)
+            got2, _ = ops.ddim_update(dev(x), dev(e), coef, None)
+            assert np.array_equal(got2.cpu().numpy(), want_prev)
+
+
+# --------------------------------------------------------------------------- layout bridges
+def test_layout_bridges(ops):
+    rs = np.random.RandomState(0)
+    x1 = torch.from_numpy(rs.standard_normal((2, 12, 3, 5, 7)).astype(np.float32))
+    x2 = torch.from_numpy(rs.standard_normal((2, 1, 3, 5, 7)).astype(np.float32))
+    y = ops.nchw_to_cl(dev(x1), dev(x2), c_pad=16)
+    assert y.shape == (2, 3, 5, 7, 16)
+    want = torch.cat([x1, x2, torch.zeros(2, 3, 3, 5, 7)], 1).to(torch.bfloat16).permute(0, 2, 3, 4, 1)
+    assert torch.equal(y.cpu(), want)
+    back = ops.cl_to_nchw(y, 13, (3, 5, 7))
+    assert torch.equal(back.cpu(), torch.cat([x1, x2], 1).to(torch.bfloat16).float())
+    lg = torch.from_numpy(rs.standard_normal((2, 3, 5, 7, 16)).astype(np.float32))
+    sm = ops.cl_to_nchw(dev(lg), 12, (3, 5, 7), softmax=True)
+    want = torch.softmax(lg[..., :12], -1).permute(0, 4, 1, 2, 3)
+    assert float((sm.cpu() - want).abs().max()) <= 1e-6
+
+
+# ------------------------------------------------------------------------------- GroupNorm
+@pytest.mark.parametrize("N,sp,C1,C2,silu,eps", [(2, (4, 8, 8), 64, 0, True, 1e-5), (2, (1, 16, 16), 160, 0, False, 1e-6),
+                                                  (1, (8, 16, 16), 128, 64, True, 1e-5), (2, (1, 1, 37), 320, 0, True, 1e-5),
+                                                  (1, (16, 32, 32), 32, 0, True, 1e-5), (2, (2, 4, 4), 640, 320, True, 1e-5)])
+def test_group_norm_silu(ops, N, sp, C1, C2, silu, eps):
+    no_tf32()
+    rs = np.random.RandomState(1)
+    C = C1 + C2
+    x = torch.from_numpy(rs.standard_normal((N, C) + sp).astype(np.float32)) * 2 + 0.5
+    gamma = torch.from_numpy(rs.standard_normal(C).astype(np.float32))
+    beta = torch.from_numpy(rs.standard_normal(C).astype(np.float32))
+    xc = cl_from_nchw(x.cuda())
+    x1 = xc[..., :C1].contiguous()
+    x2 = xc[..., C1:].contiguous() if C2 else None
+    y = ops.group_norm_cl(x1, x2, gamma.cuda(), beta.cuda(), eps=eps, silu=silu)
+    xr = nchw_from_cl(xc)
+    want = torch.nn.functional.group_norm(xr, 32, gamma.cuda(), beta.cuda(), eps)
+    if silu:
+        want = torch.nn.functional.silu(want)
+    # bf16 output rounding (2^-9 relative) dominates
+    assert rel_err(nchw_from_cl(y), want) <= 6e-3
+
+
+# ------------------------------------------------------------------------------ convolution
+def _conv_case(ops, N, sp, Cs, Cout, dims, k=3, stride=1, bias=True, emb=False, residual=False, extra_C=0, f32_out=False,
+               seed=0, block_n=0, brick=None):
+    no_tf32()
+    rs = np.random.RandomState(seed)
+    sp3 = (1,) * (3 - len(sp)) + tuple(sp)
+    xs = [torch.from_numpy(rs.standard_normal((N,) + sp3 + (c,)).astype(np.float32)).cuda().to(torch.bfloat16) for c in Cs]
+    Cin = sum(Cs)
+    w = torch.from_numpy((rs.standard_normal((Cout, Cin) + (k,) * dims) / math.sqrt(Cin * k ** dims)).astype(np.float32)).cuda()
+    b = torch.from_numpy(rs.standard_normal(Cout).astype(np.float32)).cuda() if bias else None
+    extra, extra_w, srcs = [], [], [(x, False) for x in xs]
+    if extra_C:
+        xe = torch.from_numpy(rs.standard_normal((N,) + sp3 + (extra_C,)).astype(np.float32)).cuda().to(torch.bfloat16)
+        we = torch.from_numpy((rs.standard_normal((Cout, extra_C)) / math.sqrt(extra_C)).astype(np.float32)).cuda()
+        extra.append((xe, we))
+        extra_w.append(we)
+        srcs.append((xe, True))
+    wp = ops.pack_conv_weight(w, Cs, extra=extra_w)
+    Cout8 = (Cout + 7) // 8 * 8
+    if stride == 1:
+        osp = sp3
+    else:
+        f = lambda n, on: (n - 1) // 2 + 1 if on else n
+        osp = (f(sp3[0], dims >= 3), f(sp3[1], dims >= 2), f(sp3[2], True))
+    e = torch.from_numpy(rs.standard_normal((N, Cout8)).astype(np.float32)).cuda() if emb else None
+    r = torch.from_numpy(rs.standard_normal((N,) + osp + (Cout8,)).astype(np.float32)).cuda().to(torch.bfloat16) if residual else None
+    y = torch.full((N,) + osp + (Cout8,), float("nan"), dtype=torch.float32 if f32_out else torch.bfloat16, device="cuda")
+    a = ops.make_conv_args(srcs, wp, Cout, y, dims=dims, ksize=k, stride=stride, bias=ops.pad_vec(b, Cout), emb=e,
+                           residual=r, block_n=block_n, brick=brick)
+    assert ops.conv_packed_k(a) == wp.shape[1]
+    ops.conv_fwd(a)
+    torch.cuda.synchronize()
+    want = conv_ref(xs, w, b, dims, stride, e, r, extra)
+    got = nchw_from_cl(y, Cout)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert not torch.isnan(got).any(), f"{int(torch.isnan(got).sum())} outputs never written"
+    return rel_err(got, want), got, want
+
+
+CONV_CASES = {
+    "linear_64": dict(N=2, sp=(256,), Cs=[64], Cout=64, dims=1, k=1),
+    "linear_128_160": dict(N=2, sp=(100,), Cs=[128], Cout=160, dims=1, k=1),
+    "linear_ragged": dict(N=3, sp=(37,), Cs=[320], Cout=960, dims=1, k=1, bias=False),
+    "conv2d_64": dict(N=2, sp=(16, 16), Cs=[64], Cout=64, dims=2),
+    "conv3d_64_128_all": dict(N=1, sp=(8, 8, 8), Cs=[64], Cout=128, dims=3, emb=True, residual=True),
+    "conv3d_c16": dict(N=1, sp=(8, 8, 8), Cs=[16], Cout=64, dims=3),
+    "conv3d_concat_skip": dict(N=2, sp=(4, 8, 8), Cs=[128, 64], Cout=64, dims=3, extra_C=192),
+    "conv3d_stride2": dict(N=2, sp=(8, 8, 8), Cs=[64], Cout=64, dims=3, stride=2),
+    "conv2d_stride2_odd": dict(N=1, sp=(15, 17), Cs=[32], Cout=32, dims=2, stride=2),
+    "conv3d_head_f32": dict(N=1, sp=(8, 8, 8), Cs=[64], Cout=12, dims=3, f32_out=True),
+    "conv2d_160_320": dict(N=2, sp=(16, 16), Cs=[160], Cout=320, dims=2, emb=True),
+    "conv3d_many_tiles": dict(N=2, sp=(16, 32, 32), Cs=[128], Cout=128, dims=3, residual=True),
+    "conv3d_tiny_spatial": dict(N=3, sp=(2, 2, 2), Cs=[320, 320], Cout=320, dims=3, emb=True),
+    "conv2d_bn64_brick": dict(N=1, sp=(32, 32), Cs=[64], Cout=64, dims=2, block_n=64, brick=(1, 1, 8, 16)),
+}
+
+
+@pytest.mark.parametrize("name", list(CONV_CASES))
+def test_conv_tcgen05(ops, name):
+    err, _, _ = _conv_case(ops, **CONV_CASES[name])
+    # bf16 operands are identical on both sides; fp32 accumulation order + bf16 output rounding
+    tol = 2e-5 if CONV_CASES[name].get("f32_out") else 6e-3
+    assert err <= tol, f"{name}: rel err {err}"
+
+
+# -------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,H,T,d", [(2, 4, 64, 32), (1, 8, 2048, 32), (2, 10, 256, 32), (3, 2, 16, 32), (1, 5, 100, 32),
+                                     (1, 2, 130, 64)])
+def test_attention_legacy(ops, B, H, T, d):
+    no_tf32()
+    rs = np.random.RandomState(2)
+    qkv = torch.from_numpy(rs.standard_normal((B, T, 3 * H * d)).astype(np.float32)).cuda().to(torch.bfloat16)
+    out = ops.attention_legacy(qkv, H)
+    f = qkv.float().reshape(B, T, H, 3, d)
+    q, k, v = (f[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+    want = attention_ref(q, k, v, 1.0 / math.sqrt(d))
+    got = heads_of(out, H)
+    assert rel_err(got, want) <= 1e-2   # bf16 P and bf16 output
+
+
+def test_attention_cross(ops):
+    no_tf32()
+    rs = np.random.RandomState(3)
+    B, H, Tq, Tk, d = 2, 5, 64, 7, 32
+    q = torch.from_numpy(rs.standard_normal((B, Tq, H * d)).astype(np.float32)).cuda().to(torch.bfloat16)
+    kv = torch.from_numpy(rs.standard_normal((B, Tk, 2 * H * d)).astype(np.float32)).cuda().to(torch.bfloat16)
+    o = torch.empty_like(q)
+    W = H * d
+    a = ops.make_attn_args(q, kv, kv[..., W:], o, B, H, Tq, Tk, d, d ** -0.5, (Tq * W, W, d), (Tk * 2 * W, 2 * W, d),
+                           (Tk * 2 * W, 2 * W, d), (Tq * W, W, d))
+    a.v = kv.data_ptr() + W * 2
+    ops.attention_fwd(a)
+    want = attention_ref(heads_of(q, H), heads_of(kv[..., :W], H), heads_of(kv[..., W:], H), d ** -0.5)
+    assert rel_err(heads_of(o, H), want) <= 1e-2
+
+
+# ------------------------------------------------------------------------------ small pieces
+def test_timestep_embedding_and_small_linear(ops):
+    from oracle import nets
+    t = torch.tensor([1000.0, 981.0, 1.0, 21.0, 500.0])
+    for dim in (64, 160, 128):
+        got = ops.timestep_embedding(t.cuda(), dim)
+        want = nets.timestep_embedding(t, dim)
+        assert float((got.cpu() - want).abs().max()) <= 2e-4   # |arg| up to 1e3 rad: sinf/cosf/expf ulps
+    rs = np.random.RandomState(4)
+    for M, K, N in ((1, 64, 256), (8, 256, 1000), (16, 640, 333)):
+        x = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32))
+        w = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32) / math.sqrt(K))
+        b = torch.from_numpy(rs.standard_normal(N).astype(np.float32))
+        got = ops.small_linear(x.cuda(), w.cuda(), b.cuda(), act_in=True, act_out=True)
+        want = torch.nn.functional.silu(torch.nn.functional.linear(torch.nn.functional.silu(x), w, b))
+        assert float((got.cpu() - want).abs().max()) <= 1e-4
+
+
+def test_layernorm_geglu_upsample(ops):
+    rs = np.random.RandomState(5)
+    x = torch.from_numpy(rs.standard_normal((3, 50, 320)).astype(np.float32)).cuda().to(torch.bfloat16)
+    g = torch.from_numpy(rs.standard_normal(320).astype(np.float32)).cuda()
+    b = torch.from_numpy(rs.standard_normal(320).astype(np.float32)).cuda()
+    got = ops.layernorm(x, g, b)
+    want = torch.nn.functional.layer_norm(x.float(), (320,), g, b, 1e-5)
+    assert rel_err(got, want) <= 6e-3
+    h = torch.from_numpy(rs.standard_normal((3, 50, 2 * 1280)).astype(np.float32)).cuda().to(torch.bfloat16)
+    got = ops.geglu(h)
+    a, gate = h.float().chunk(2, -1)
+    assert rel_err(got, a * torch.nn.functional.gelu(gate)) <= 6e-3
+    u = torch.from_numpy(rs.standard_normal((2, 3, 4, 5, 16)).astype(np.float32)).cuda().to(torch.bfloat16)
+    got = ops.upsample2x(u, 3)
+    want = torch.nn.functional.interpolate(nchw_from_cl(u), scale_factor=2, mode="nearest")
+    assert torch.equal(nchw_from_cl(got), want)
+    got2 = ops.upsample2x(u[:, :1].contiguous(), 2)
+    want2 = torch.nn.functional.interpolate(nchw_from_cl(u[:, :1])[:, :, 0], scale_factor=2, mode="nearest")
+    assert torch.equal(nchw_from_cl(got2)[:, :, 0], want2)
