@@ -61,7 +61,8 @@ enum gg_cat_mode {
     GG_CAT_PROBS = 3,       /* posterior -> clamp -> normalise -> probs                            */
     GG_CAT_SAMPLE_GIVEN = 4,/* x0 IS the distribution: normalise -> argmax(p/q) -> one-hot
                                (OneHotCategoricalBCHW(probs).sample(), one_hot_categorical.py:30) */
-    GG_CAT_ARGMAX_GIVEN = 5 /* x0 IS the distribution: normalise -> argmax -> one-hot             */
+    GG_CAT_ARGMAX_GIVEN = 5,/* x0 IS the distribution: normalise -> argmax -> one-hot             */
+    GG_CAT_PROBS_GIVEN = 6  /* x0 IS the distribution: normalise -> probs (prob_sample, :48-50)   */
 };
 
 typedef struct {
@@ -119,6 +120,9 @@ typedef struct {
     float* pred_x0;         /* may be NULL */
     int64_t n;              /* elements */
     float temperature;
+    const float* e_uncond;  /* NULL, or unconditional eps: e = e_u + guidance_scale * (e_t - e_u)
+                               (classifier-free guidance, ddim.py:175-179) before the update   */
+    float guidance_scale;
 } gg_ddim_args;
 
 int gg_ddim_update(const gg_ddim_args* a, gg_stream_t stream);

@@ -49,7 +49,8 @@ class CatStepCLArgs(C.Structure):
 
 class DdimArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("e_t", C.c_void_p), ("noise", C.c_void_p), ("coef", C.c_void_p),
-                ("x_prev", C.c_void_p), ("pred_x0", C.c_void_p), ("n", C.c_int64), ("temperature", C.c_float)]
+                ("x_prev", C.c_void_p), ("pred_x0", C.c_void_p), ("n", C.c_int64), ("temperature", C.c_float),
+                ("e_uncond", C.c_void_p), ("guidance_scale", C.c_float)]
 
 
 class GnFinalizeArgs(C.Structure):

@@ -1,0 +1,250 @@
+"""Drop-in for ccdm/ddpm/models/diffusion_denoising.py: schedules (:18-39), DiffusionModel
+(:42-139) and DenoisingModel (:142-227), with the per-step math on sm_100a kernels.
+
+The reverse chain (forward_denoising, :176-227) runs entirely on the device.  Two execution
+forms of the same step are provided:
+
+* ``interface`` (default): exactly the reference's tensor interface per step --
+  ``unet(...)["diffusion_out"]`` fp32 [B, C, *sp] -> fused posterior + clamp + draw kernel ->
+  fp32 one-hot ``xt``.  Noise ``q ~ Exp(1)`` is drawn per step from torch's generator exactly as
+  the reference's ``torch.multinomial`` does (same stream, same order), or injected (``q_noise``).
+* ``resident``: the sampler loop never leaves the channels-last device layout -- head-conv
+  logits -> fused softmax + posterior + draw -> next UNet input written in place (uint8 labels,
+  Philox in-kernel noise).  Only the last step goes through the interface form to produce the
+  reference's output tensor.
+
+The posterior uses the O(C) closed form of theta_post_prob -- no
+[B, C, C, D, H, W] intermediates.
+"""
+import logging
+import math
+from typing import Optional, Union
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from .one_hot_categorical import OneHotCategoricalBCHW
+
+LOGGER = logging.getLogger(__name__)
+
+
+def linear_schedule(time_steps: int, start=1e-2, end=0.2):
+    betas = torch.linspace(start, end, time_steps)
+    alphas = 1 - betas
+    return betas, alphas, torch.cumprod(alphas, dim=0)
+
+
+def cosine_schedule(time_steps: int, s: float = 8e-3):
+    """:25-39.  The argument ``s`` is ignored in the reference as well (overwritten by 0.008)."""
+    s = 0.008
+    steps = torch.arange(0, time_steps)
+    cumalphas = torch.cos(((steps / time_steps + s) / (1 + s)) * (math.pi / 2)) ** 2
+    curve = lambda u: math.cos((u + s) / (1.0 + s) * math.pi / 2) ** 2  # noqa: E731
+    betas = torch.tensor([min(1 - curve((i + 1) / time_steps) / curve(i / time_steps), 0.999) for i in range(time_steps)])
+    return betas, 1 - betas, cumalphas
+
+
+class DiffusionModel(nn.Module):
+    betas: Tensor
+    alphas: Tensor
+    cumalphas: Tensor
+
+    def __init__(self, schedule: str, time_steps: int, num_classes: int, schedule_params=None, dims=3):
+        super().__init__()
+        fn = {"linear": linear_schedule, "cosine": cosine_schedule}[schedule]
+        betas, alphas, cumalphas = fn(time_steps, **schedule_params) if schedule_params is not None else fn(time_steps)
+        self.dims = dims
+        self.register_buffer("betas", betas)
+        self.register_buffer("alphas", alphas)
+        self.register_buffer("cumalphas", cumalphas)
+        self.num_classes = num_classes
+
+    @property
+    def time_steps(self):
+        return len(self.betas)
+
+    # -- forward (noising) process: training-side helpers, not on the sampler hot path ------
+    def _bc(self, v: Tensor, extra: int = 0) -> Tensor:
+        return v[(...,) + (None,) * (self.dims + 1 + extra)]
+
+    def q_xt_given_xtm1(self, xtm1: Tensor, t: Tensor) -> OneHotCategoricalBCHW:
+        betas = self._bc(self.betas[t - 1])
+        return OneHotCategoricalBCHW((1 - betas) * xtm1 + betas / self.num_classes)
+
+    def q_xt_given_x0(self, x0: Tensor, t: Tensor) -> OneHotCategoricalBCHW:
+        ca = self._bc(self.cumalphas[t - 1])
+        return OneHotCategoricalBCHW(ca * x0 + (1 - ca) / self.num_classes)
+
+    def theta_post(self, xt: Tensor, x0: Tensor, t: Tensor) -> Tensor:
+        """:92-103 (x0 one-hot; training loss target -- plain tensor ops, not on the sampler path)."""
+        a, g = self._step_coef(t)
+        a, g = self._bc(a), self._bc(g)
+        theta = (a * xt + (1 - a) / self.num_classes) * (g * x0 + (1 - g) / self.num_classes)
+        return theta / theta.sum(dim=1, keepdim=True)
+
+    # -- reverse process -------------------------------------------------------------------
+    def _step_coef(self, t: Tensor):
+        """(alpha_t, cumalpha_{t-1}) per sample for 1-based t; t == 1 -> (0, 1)  (:114-122)."""
+        tt = t.long() - 1
+        a = self.alphas[tt].clone().float()
+        g = self.cumalphas[tt - 1].clone().float()
+        a[tt == 0] = 0.0
+        g[tt == 0] = 1.0
+        return a, g
+
+    def step_coef_tensor(self, t: Tensor) -> Tensor:
+        a, g = self._step_coef(t)
+        return torch.stack([a, g], dim=1).contiguous()
+
+    @torch.no_grad()
+    def theta_post_prob(self, xt: Tensor, theta_x0: Tensor, t: Tensor) -> Tensor:
+        """:105-139  theta_post(x_{t-1} | x_t, p(x0)) -- one fused kernel, O(C) per voxel."""
+        coef = self.step_coef_tensor(t.to(self.alphas.device)).to(xt.device)
+        out, _, _ = ops.cat_posterior_sample(theta_x0.float().contiguous(), xt.float().contiguous(), coef, ops.CAT_POSTERIOR)
+        return out
+
+
+class DenoisingModel(nn.Module):
+    def __init__(self, diffusion: DiffusionModel, unet: nn.Module, dataset_file: str, step_T_sample: str = "majority", dims=3,
+                 loop: str = "interface"):
+        super().__init__()
+        self.diffusion = diffusion
+        self.unet = unet
+        self.dims = dims
+        self.dataset_file = dataset_file
+        self.step_T_sample = step_T_sample
+        self.loop = loop                 # "interface" | "resident"
+        self.use_cuda_graph = False      # capture the UNet forward of the loop in a CUDA graph
+        self.q_noise = None              # optional injected noise: indexable [step] -> fp32 [B*V, C]
+        self.philox_seed = 0
+        self.record = None               # optional list: receives the uint8 label volume after every step
+
+    @property
+    def time_steps(self):
+        return self.diffusion.time_steps
+
+    def forward(self, x: Tensor, condition: Tensor, feature_condition: Tensor = None, t: Optional[Tensor] = None,
+                label_ref_logits: Optional[Tensor] = None, validation: bool = False, context=None) -> Union[Tensor, dict]:
+        if self.training:
+            if not isinstance(t, Tensor):
+                raise ValueError("'t' needs to be a Tensor at training time")
+            if not isinstance(x, Tensor):
+                raise ValueError("'x' needs to be a Tensor at training time")
+            return self.forward_step(x, condition, feature_condition, t, context=context)
+        if validation:
+            return self.forward_step(x, condition, feature_condition, t, context=context)
+        if t is None:
+            return self.forward_denoising(x, condition, feature_condition, label_ref_logits=label_ref_logits, context=context)
+        return self.forward_denoising(x, condition, feature_condition, int(t.item()), label_ref_logits, context=context)
+
+    def forward_step(self, x, condition, feature_condition, t, context=None):
+        return self.unet(x, condition, feature_condition=feature_condition, timesteps=t, context=context)
+
+    def _t_values(self, init_t):
+        if init_t is None:
+            init_t = self.time_steps
+        if init_t > 10000:                      # step skipping (:190-197)
+            K = init_t % 10000
+            assert 0 < K <= self.time_steps
+            if K == self.time_steps:
+                return list(range(K, 0, -1))
+            LOGGER.warning(f"Override default {self.time_steps} time steps with {K}.")
+            return [round(v) for v in np.linspace(self.time_steps, 1, K)]
+        return list(range(init_t, 0, -1))
+
+    @torch.no_grad()
+    def forward_denoising(self, x: Optional[Tensor], condition: Tensor, feature_condition: Tensor, init_t: Optional[int] = None,
+                          label_ref_logits: Optional[Tensor] = None, context: Tensor = None) -> dict:
+        if label_ref_logits is not None:
+            raise NotImplementedError("guidance branch is broken in the reference (undefined attributes, SURVEY.md D4)")
+        if feature_condition is not None:
+            raise NotImplementedError("feature_condition is not used by the shipped ruijin config")
+        dev = next(self.unet.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("DenoisingModel needs its parameters on a CUDA device (no CPU path exists)")
+        t_values = self._t_values(init_t)
+        xt = x.to(dev, torch.float32).contiguous()
+        cond = condition.to(dev, torch.float32).contiguous() if condition is not None else None
+        if context is not None:
+            context = context.to(dev)
+        B, Cc = xt.shape[:2]
+        spatial = tuple(xt.shape[2:])
+        V = int(math.prod(spatial))
+        coefs = self.diffusion.step_coef_tensor(torch.tensor(t_values)).to(dev)          # [steps, 2]
+        coefs = coefs[:, None, :].expand(-1, B, -1).contiguous()                          # [steps, B, 2]
+        if self.loop == "resident" and len(t_values) > 1:
+            xt = self._resident_steps(xt, cond, context, t_values[:-1], coefs, spatial)
+            t_values, coefs, step0 = t_values[-1:], coefs[-1:], len(t_values) - 1
+        else:
+            step0 = 0
+        unet = self.unet
+        plan = unet.plan_for(B, spatial, context)
+        if self.use_cuda_graph and plan.graph is None:
+            plan.capture()
+        if "context" in plan.inputs:
+            plan.inputs["context"].copy_(unet._ctx_cl(context, B))
+        probs_x0 = torch.empty_like(xt)
+        labels = torch.empty((B, V), dtype=torch.uint8, device=dev) if self.record is not None else None
+        for i, t in enumerate(t_values):
+            # x0pred = unet(xt, condition, None, t_.float(), context)["diffusion_out"]      (:203-207)
+            ops.nchw_to_cl(xt, cond, c_pad=unet.in_channels_padded, out=plan.inputs["x"])
+            plan.inputs["t"].fill_(float(t))
+            plan.run()
+            ops.cl_to_nchw(plan.outputs["head"], Cc, spatial, softmax=True, out=probs_x0)
+            # probs = theta_post_prob(xt, x0pred, t_); clamp(1e-12); sample / argmax / probs   (:209-224)
+            if t > 1:
+                q = None
+                if self.q_noise is not None:
+                    q = self.q_noise[step0 + i].to(dev, torch.float32).contiguous()
+                else:
+                    q = torch.empty((B * V, Cc), dtype=torch.float32, device=dev).exponential_(1)
+                nxt = torch.empty_like(xt)
+                ops.cat_posterior_sample(probs_x0, xt, coefs[i], ops.CAT_SAMPLE, q=q, out=nxt, labels=labels)
+                xt = nxt
+            elif self.step_T_sample is None or self.step_T_sample == "majority":
+                o64 = torch.empty(xt.shape, dtype=torch.int64, device=dev)
+                ops.cat_posterior_sample(probs_x0, xt, coefs[i], ops.CAT_ARGMAX, out_i64=o64, labels=labels)
+                xt = o64
+            elif self.step_T_sample == "confidence":
+                out = torch.empty_like(xt)
+                ops.cat_posterior_sample(probs_x0, xt, coefs[i], ops.CAT_PROBS, out=out)
+                xt = out
+            if self.record is not None and (t > 1 or self.step_T_sample in (None, "majority")):
+                self.record.append(labels.clone())
+        return {"diffusion_out": xt}
+
+    def _resident_steps(self, xt, cond, context, t_values, coefs, spatial):
+        """Steps t > 1 without leaving the channels-last device layout; returns fp32 one-hot xt."""
+        unet = self.unet
+        dev = xt.device
+        B, Cc = xt.shape[:2]
+        V = int(math.prod(spatial))
+        plan = unet.plan_for(B, spatial, context)
+        if "context" in plan.inputs:
+            plan.inputs["context"].copy_(unet._ctx_cl(context, B))
+        xin = plan.inputs["x"]
+        ops.nchw_to_cl(xt, cond, c_pad=unet.in_channels_padded, out=xin)
+        lab_a = torch.empty((B * V,), dtype=torch.uint8, device=dev)
+        lab_b = torch.empty_like(lab_a)
+        ops.cat_posterior_sample(xt, None, None, ops.CAT_ARGMAX_GIVEN, clamp_min=0.0, labels=lab_a.view(B, V))
+        n_cond = cond.shape[1] if cond is not None else 0
+        cond_cl = None
+        if cond is not None:
+            cond_cl = ops.nchw_to_cl(cond, None, c_pad=8)[..., :n_cond].contiguous()
+        if self.use_cuda_graph and plan.graph is None:
+            plan.capture()
+            ops.nchw_to_cl(xt, cond, c_pad=unet.in_channels_padded, out=xin)
+        for i, t in enumerate(t_values):
+            plan.inputs["t"].fill_(float(t))
+            plan.run()
+            q = None
+            if self.q_noise is not None:
+                q = self.q_noise[i].to(dev, torch.float32).contiguous()
+            ops.cat_step_cl(plan.outputs["head"], lab_a, coefs[i], lab_b, B, V, Cc, mode=ops.CAT_SAMPLE, q=q, cond=cond_cl,
+                            n_cond=n_cond, next_x=xin, seed=self.philox_seed, offset=i)
+            lab_a, lab_b = lab_b, lab_a
+            if self.record is not None:
+                self.record.append(lab_a.view(B, V).clone())
+        return ops.cl_to_nchw(xin, Cc, spatial)

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) cat_posterior_kernel(const gg_cat_args a,
     const int64_t v0 = (gi - (int64_t)b * groups_per_sample) * VPT;
     const int64_t V = a.V;
     const int mode = a.mode;
-    const bool given = (mode == GG_CAT_SAMPLE_GIVEN || mode == GG_CAT_ARGMAX_GIVEN);
+    const bool given = (mode >= GG_CAT_SAMPLE_GIVEN);
     const bool draw = (mode == GG_CAT_SAMPLE || mode == GG_CAT_SAMPLE_GIVEN);
     int nv = VPT;
     if (!VEC) nv = (int)min((int64_t)VPT, V - v0);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) cat_posterior_kernel(const gg_cat_args a,
 #pragma unroll
         for (int c = 0; c < C; ++c) p[c][j] = __fdiv_rn(p[c][j], P);
     }
-    if (mode == GG_CAT_PROBS) {
+    if (mode == GG_CAT_PROBS || mode == GG_CAT_PROBS_GIVEN) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             if (VEC) store_plane<VPT>(outp + (int64_t)c * V, p[c]);
@@ -418,6 +418,12 @@ __global__ void __launch_bounds__(256) ddim_kernel(const gg_ddim_args a) {
         const int64_t i4 = i * 4;
         if (i4 >= a.n) return;
         float4 x = ldg_nc_f4(a.x + i4), e = ldg_nc_f4(a.e_t + i4);
+        if (a.e_uncond) {
+            const float4 u = ldg_nc_f4(a.e_uncond + i4);
+            const float s = a.guidance_scale;
+            e.x = __fadd_rn(u.x, __fmul_rn(s, __fsub_rn(e.x, u.x))); e.y = __fadd_rn(u.y, __fmul_rn(s, __fsub_rn(e.y, u.y)));
+            e.z = __fadd_rn(u.z, __fmul_rn(s, __fsub_rn(e.z, u.z))); e.w = __fadd_rn(u.w, __fmul_rn(s, __fsub_rn(e.w, u.w)));
+        }
         float4 n = a.noise ? ldg_nc_f4(a.noise + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 xp, p0;
         one(x.x, e.x, n.x, xp.x, p0.x); one(x.y, e.y, n.y, xp.y, p0.y);
@@ -427,7 +433,9 @@ __global__ void __launch_bounds__(256) ddim_kernel(const gg_ddim_args a) {
     } else {
         if (i >= a.n) return;
         float xp, p0;
-        one(a.x[i], a.e_t[i], a.noise ? a.noise[i] : 0.f, xp, p0);
+        float e = a.e_t[i];
+        if (a.e_uncond) e = __fadd_rn(a.e_uncond[i], __fmul_rn(a.guidance_scale, __fsub_rn(e, a.e_uncond[i])));
+        one(a.x[i], e, a.noise ? a.noise[i] : 0.f, xp, p0);
         a.x_prev[i] = xp;
         if (a.pred_x0) a.pred_x0[i] = p0;
     }
@@ -492,10 +500,10 @@ using namespace gg;
 extern "C" int gg_cat_posterior_sample(const gg_cat_args* a, gg_stream_t stream) {
     GG_REQUIRE(a != nullptr && a->x0 != nullptr, GG_ERR_BAD_ARG);
     GG_REQUIRE(a->B > 0 && a->V > 0, GG_ERR_BAD_ARG);
-    GG_REQUIRE(a->mode >= GG_CAT_POSTERIOR && a->mode <= GG_CAT_ARGMAX_GIVEN, GG_ERR_BAD_ARG);
-    const bool given = a->mode == GG_CAT_SAMPLE_GIVEN || a->mode == GG_CAT_ARGMAX_GIVEN;
+    GG_REQUIRE(a->mode >= GG_CAT_POSTERIOR && a->mode <= GG_CAT_PROBS_GIVEN, GG_ERR_BAD_ARG);
+    const bool given = a->mode >= GG_CAT_SAMPLE_GIVEN;
     if (!given) GG_REQUIRE(a->xt != nullptr && a->coef != nullptr, GG_ERR_BAD_ARG);
-    if (a->mode == GG_CAT_POSTERIOR || a->mode == GG_CAT_PROBS) GG_REQUIRE(a->out != nullptr, GG_ERR_BAD_ARG);
+    if (a->mode == GG_CAT_POSTERIOR || a->mode == GG_CAT_PROBS || a->mode == GG_CAT_PROBS_GIVEN) GG_REQUIRE(a->out != nullptr, GG_ERR_BAD_ARG);
     else GG_REQUIRE(a->out != nullptr || a->out_i64 != nullptr || a->labels != nullptr, GG_ERR_BAD_ARG);
     cudaStream_t s = as_stream(stream);
     switch (a->C) {
@@ -527,7 +535,8 @@ extern "C" int gg_cat_step_cl(const gg_cat_step_cl_args* a, gg_stream_t stream) 
 extern "C" int gg_ddim_update(const gg_ddim_args* a, gg_stream_t stream) {
     GG_REQUIRE(a != nullptr && a->x && a->e_t && a->coef && a->x_prev && a->n > 0, GG_ERR_BAD_ARG);
     const bool vec = (a->n % 4 == 0) && aligned(a->x, 16) && aligned(a->e_t, 16) && aligned(a->x_prev, 16) &&
-                     (!a->noise || aligned(a->noise, 16)) && (!a->pred_x0 || aligned(a->pred_x0, 16));
+                     (!a->noise || aligned(a->noise, 16)) && (!a->pred_x0 || aligned(a->pred_x0, 16)) &&
+                     (!a->e_uncond || aligned(a->e_uncond, 16));
     if (vec) {
         const unsigned blocks = (unsigned)((a->n / 4 + 255) / 256);
         ddim_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(*a);

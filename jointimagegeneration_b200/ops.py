@@ -12,7 +12,7 @@ import torch
 
 from . import _C
 
-CAT_POSTERIOR, CAT_SAMPLE, CAT_ARGMAX, CAT_PROBS, CAT_SAMPLE_GIVEN, CAT_ARGMAX_GIVEN = range(6)
+CAT_POSTERIOR, CAT_SAMPLE, CAT_ARGMAX, CAT_PROBS, CAT_SAMPLE_GIVEN, CAT_ARGMAX_GIVEN, CAT_PROBS_GIVEN = range(7)
 BLOCK_K = 64
 
 
@@ -34,7 +34,7 @@ def cat_posterior_sample(x0, xt, coef, mode, q=None, clamp_min=1e-12, out=None, 
     _chk(x0, torch.float32)
     B, Cc = x0.shape[:2]
     V = x0[0, 0].numel()
-    given = mode in (CAT_SAMPLE_GIVEN, CAT_ARGMAX_GIVEN)
+    given = mode >= CAT_SAMPLE_GIVEN
     if not given:
         _chk(xt, torch.float32)
         _chk(coef, torch.float32)
@@ -62,17 +62,21 @@ def cat_step_cl(logits, labels_in, coef, labels_out, B, V, Cc, mode=CAT_SAMPLE, 
     _C.check(_C.lib().gg_cat_step_cl(C.byref(a), _C.stream()), "gg_cat_step_cl")
 
 
-def ddim_update(x, e_t, coef, noise=None, temperature=1.0, want_pred_x0=True, x_prev=None, pred_x0=None):
-    """K14.  coef: device fp32 [4] = (a_t, a_prev, sigma_t, sqrt(1 - a_t))."""
+def ddim_update(x, e_t, coef, noise=None, temperature=1.0, want_pred_x0=True, x_prev=None, pred_x0=None,
+                e_uncond=None, guidance_scale=1.0):
+    """K14.  coef: device fp32 [4] = (a_t, a_prev, sigma_t, sqrt(1 - a_t)).  With e_uncond the
+    classifier-free-guidance combination e = e_u + s (e_t - e_u) (ddim.py:175-179) is fused in."""
     _chk(x, torch.float32), _chk(e_t, torch.float32), _chk(coef, torch.float32)
     if noise is not None:
         _chk(noise, torch.float32)
+    if e_uncond is not None:
+        _chk(e_uncond, torch.float32)
     if x_prev is None:
         x_prev = torch.empty_like(x)
     if pred_x0 is None and want_pred_x0:
         pred_x0 = torch.empty_like(x)
     a = _C.DdimArgs(_C.ptr(x), _C.ptr(e_t), _C.ptr(noise), _C.ptr(coef), _C.ptr(x_prev), _C.ptr(pred_x0), x.numel(),
-                    float(temperature))
+                    float(temperature), _C.ptr(e_uncond), float(guidance_scale))
     _C.check(_C.lib().gg_ddim_update(C.byref(a), _C.stream()), "gg_ddim_update")
     return x_prev, pred_x0
 
@@ -237,7 +241,7 @@ def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=Non
             out_spatial = (f(D, dims >= 3), f(H, dims >= 2), f(W, True))
     a.Do, a.Ho, a.Wo = out_spatial
     a.w_packed = _C.ptr(_chk(w_packed, torch.bfloat16))
-    a.bias = _C.ptr(bias)
+    a.bias = bias if isinstance(bias, int) else _C.ptr(bias)
     a.emb = _C.ptr(emb)
     a.emb_stride = emb.shape[-1] if emb is not None else 0
     a.residual = _C.ptr(residual)
