@@ -49,6 +49,7 @@ class _Arena:
         self.device = device
         self.free: List[torch.Tensor] = []
         self.owner: Dict[int, torch.Tensor] = {}
+        self.stores: List[torch.Tensor] = []     # every backing allocation; the plan keeps them alive
         self.total = 0
 
     def alloc(self, shape, dtype) -> torch.Tensor:
@@ -63,6 +64,7 @@ class _Arena:
             store = self.free.pop(best)
         else:
             store = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.stores.append(store)
             self.total += nbytes
         n = int(math.prod(shape))
         es = torch.empty((), dtype=dtype).element_size()
@@ -207,7 +209,16 @@ class UNetEngine:
 
     def _pack(self, conv: M.ParamConv, splits, extra=()):
         key = (id(conv.weight), tuple(splits), tuple(id(e) for e in extra))
-        return self._cached(key, lambda: ops.pack_conv_weight(conv.weight, splits, extra=[e for e in extra]))
+
+        def make():
+            w = conv.weight.detach()
+            missing = sum(splits) - w.shape[1]
+            if missing > 0:      # activation channels were zero-padded to a multiple of 8 (e.g. 13 -> 16)
+                assert len(splits) == 1
+                w = torch.cat([w, w.new_zeros((w.shape[0], missing) + tuple(w.shape[2:]))], 1)
+            return ops.pack_conv_weight(w, splits, extra=[e for e in extra])
+
+        return self._cached(key, make)
 
     # ------------------------------------------------------------------------------ layers
     def _resblock(self, plan, ar, rb: M.ResBlock, x1: Act, x2: Optional[Act], emb_ptr: int, emb_stride: int) -> Act:
@@ -481,6 +492,7 @@ class UNetEngine:
         ar.release(a.t)
         plan.outputs["head"] = head.t
         plan.keep.extend([emb_all, emb, e1, temb])
+        plan.keep.append(ar.stores)      # kernels hold raw pointers into these: they must outlive the plan
         plan.arena_bytes = ar.total
         return plan
 
