@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- denoising steps/sec of the GuideGen CCDM mask sampler on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+Workload (config.workload): BASELINE.json configs[1] -- CCDM 3-D UNet (ccdm/params.yml:69-75) mask
+sampler, volume 128x128x64 (tensor [B, 12, 64, 128, 128]), 12 classes, batch 8 per GPU, bf16.
+One "step" = one reverse-diffusion step of the whole batch: UNet forward + categorical posterior
++ categorical draw + next-input assembly.  N > 1: independent chains are sharded over the ranks
+(batch 8 per GPU, no data-path collective) -> weak scaling; value = N * K / max-over-ranks time.
+
+Keys beyond the base contract: "roofline" (dominant kernel = the tcgen05 implicit-GEMM conv, tensor
+bound, timed live with CUDA events per launch in a separate instrumented pass), "roofline_hbm"
+(the fused per-voxel posterior/sampling kernel), "cpu_baseline", "kernel_ms" (per-kernel share of
+one step), "volumes_per_sec" (= value * batch / 1000 steps).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CCDM_NET = dict(base_channels=64, channel_mult=[1, 2, 2, 4, 5], attention_resolutions=[32, 16, 8], num_heads=1,
+                num_head_channels=32, softmax_output=True)                       # ccdm/params.yml:69-75
+WORKLOADS = {
+    # name: (spatial D,H,W, classes, batch, chain length, FLOP per sample-forward from BASELINE.md section 3)
+    "ccdm_cfg2": dict(spatial=(64, 128, 128), C=12, batch=8, T=1000, flop_per_sample=6.324e12,
+                      desc="CCDM mask sampler 128x128x64 (tensor [8,12,64,128,128]), 12 classes, 1000-step chain, batch 8, bf16"),
+    "ccdm_cfg1": dict(spatial=(32, 32, 32), C=12, batch=1, T=10, flop_per_sample=1.97e11,
+                      desc="CCDM mask sampler 32x32x32, 12 classes, 10 steps, batch 1"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+
+
+def randomize_zero_modules(model, seed):
+    """The reference zero-initialises the last conv of every ResBlock, every attention proj_out and the
+    output conv: a random-init network would return a constant.  Re-draw those."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.ndim >= 2 and float(p.abs().max()) == 0.0:
+                fan_in = p[0].numel()
+                p.copy_(torch.randn(p.shape, generator=g) / fan_in ** 0.5)
+            elif p.ndim == 1 and name.endswith("bias") and float(p.abs().max()) == 0.0 and "norm" not in name and ".0.bias" not in name:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+
+
+# =============================================================================== this repo's arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from jointimagegeneration_b200 import _C, ops
+    from jointimagegeneration_b200.ccdm import build_model
+
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N > 1 with torch.distributed.run)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _C.check(_C.lib().gg_device_check(), "gg_device_check")
+    K, W = args.steps, max(args.warmup, 3)
+    B, Cc, sp, T = args.batch or wl["batch"], wl["C"], wl["spatial"], wl["T"]
+    V = sp[0] * sp[1] * sp[2]
+
+    torch.manual_seed(1234 + rank)
+    model = build_model(T, "cosine", {"s": 0.008}, [(1,) + sp, (Cc,) + sp], None, "unet_openai", dict(CCDM_NET), "synthetic",
+                        "majority", dims=3)
+    randomize_zero_modules(model.unet, 7)
+    model = model.to(dev).eval()
+    model.loop, model.use_cuda_graph, model.philox_seed = "resident", True, 99 + rank
+
+    # ---- synthetic inputs, resident in HBM before the timed region
+    lab0 = torch.randint(0, Cc, (B,) + sp, device=dev)
+    x_T = torch.zeros((B, Cc) + sp, dtype=torch.float32, device=dev).scatter_(1, lab0[:, None], 1.0)
+    cond = torch.zeros((B, 1) + sp, dtype=torch.float32, device=dev)          # ruijin.py:181-182: zeros
+    t_values = list(range(T, 0, -1))
+    coefs = model.diffusion.step_coef_tensor(torch.tensor(t_values)).to(dev)[:, None, :].expand(-1, B, -1).contiguous()
+    st = model.resident_begin(x_T, cond)
+    plan = st["plan"]
+
+    def step(i):
+        model.resident_step(st, t_values[i % (T - 1)], coefs[i % (T - 1)], offset=i)
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = world * K / (ms / 1e3)
+    launches_per_step = plan.num_launches + 1                                   # UNet plan + fused per-voxel kernel
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    x_host = x_T.cpu().pin_memory()
+    c_host = cond.cpu().pin_memory()
+    out_host = torch.empty((B, Cc) + sp, dtype=torch.int64).pin_memory()
+    Ke = max(2, min(K, 10))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = model(x_host, c_host, t=torch.tensor(10000 + Ke))["diffusion_out"]   # reference's own K-step knob (:190-197)
+    out_host.copy_(res, non_blocking=False)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tm = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_s = float(tm.item())
+    e2e = {"value": world * Ke / e2e_s, "unit": "steps/s", "steps": Ke,
+           "h2d_bytes_per_step": (x_host.numel() * 4 + c_host.numel() * 4) // Ke,
+           "d2h_bytes_per_step": out_host.numel() * 8 // Ke,
+           "call": "DenoisingModel.forward(x_host, condition_host, t=10000+K) -> int64 one-hot on host (loop='resident', CUDA graph)"}
+
+    line = {"metric": "denoising steps/sec", "value": value, "unit": "steps/s (1 step = UNet forward + categorical posterior/draw for a batch of %d volumes)" % B,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": args.workload, "global_batch": B * world, "batch_per_gpu": B,
+                       "volume": list(sp), "classes": Cc, "network": "ccdm/params.yml unet_openai (95.4 M params), random init, zero-init modules re-randomised",
+                       "text_conditioning": "off -- the reference cannot construct its text-conditioned CCDM (SURVEY.md D1/D2); --text enables ours",
+                       "parallelism": "independent chains sharded over ranks (dp%d), no per-step collective" % world,
+                       "l2": "inputs larger than L2 (activations are GBs per step); no explicit flush",
+                       "rng": "in-kernel Philox", "cuda_graph": True},
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches_per_step * K,
+            "volumes_per_sec": value * B / T}
+
+    if rank == 0:
+        peaks = load_peaks()
+        # ---- instrumented pass: CUDA-event time of every launch of one step (eager, same stream)
+        kinds = {}
+        torch.cuda.synchronize()
+        reps = 2
+        for _ in range(reps):
+            evs = []
+            s = _C.stream()
+            for fn, fargs in plan.steps:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _C.check(fn(*fargs, s), fn.__name__)
+                b.record()
+                evs.append((fn.__name__, a, b))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.cat_step_cl(plan.outputs["head"], st["lab_a"], coefs[5], st["lab_b"], B, V, Cc, mode=ops.CAT_SAMPLE,
+                            cond=st["cond_cl"], n_cond=st["n_cond"], next_x=st["xin"], seed=1, offset=12345)
+            b.record()
+            evs.append(("gg_cat_step_cl", a, b))
+            torch.cuda.synchronize()
+            for name, a, b in evs:
+                d = kinds.setdefault(name, [0.0, 0])
+                d[0] += a.elapsed_time(b) / reps
+                d[1] += 1
+        kernel_ms = {k: round(v[0], 4) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
+        n_conv = kinds["gg_conv_fwd"][1] // reps
+        conv_ms = kinds["gg_conv_fwd"][0]
+        attn_flops = 0.022e12 / 6.324e12 * wl["flop_per_sample"]
+        conv_alg = (wl["flop_per_sample"] - attn_flops) * B
+        ach = conv_alg / (conv_ms / 1e3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "conv_tcgen05_kernel (all %d launches of one step)" % n_conv,
+                            "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+                            "traffic": None, "algorithmic_flop": conv_alg, "issued_flop": plan.flops, "avg_launch_ms": conv_ms / n_conv,
+                            "peak_source": peaks["source"] + " (bf16 sustained: kernel timed inside a long step)",
+                            "whole_step_frac": wl["flop_per_sample"] * B / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
+        cat_ms = kinds["gg_cat_step_cl"][0]
+        alg_b = 50.0 * B * V
+        act_b = (64 + 1 + 1 + 2 * plan.inputs["x"].shape[-1] + 2) * B * V
+        line["roofline_hbm"] = {"bound": "hbm", "kernel": "cat_step_cl_kernel (softmax + posterior + clamp + draw + next input)",
+                                "achieved": alg_b / (cat_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": alg_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                "algorithmic_bytes": alg_b, "moved_bytes": act_b,
+                                "moved_frac": act_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "launch_ms": cat_ms}
+        line["kernel_ms"] = kernel_ms
+        line["arena_bytes"] = plan.arena_bytes
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(args, wl, budget_s=20.0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ============================================================================ CPU reference arm
+def _oracle_step_fn(wl, B, sp):
+    """One denoising step of the CPU oracle (restated reference, fp32 torch on all host threads) on a
+    [B, C, *sp] sample.  bench.py may execute oracle/ only here (cpu_baseline / --impl reference)."""
+    import numpy as np
+    import torch
+    from oracle import diffusion, nets, weights
+    Cc, T = wl["C"], wl["T"]
+    sd = weights.synth_state_dict(weights.reference_shapes("CCDM_PARAMS_YML"), 1)
+    _, alphas, cumalphas = diffusion.cosine_schedule(T)
+    V = int(np.prod(sp))
+    xt = weights.uniform_one_hot(2, B, Cc, sp)
+    cond = torch.zeros(B, 1, *sp)
+    q = torch.from_numpy(weights.exp_noise(3, (1, B * V, Cc)))
+
+    def step():
+        def unet_fn(x, t):
+            return nets.unet_forward(sd, x, t, input_condition=cond, softmax_output=True, num_head_channels=32)
+        return diffusion.forward_denoising(unet_fn, alphas, cumalphas, xt, q, time_steps=T, t_values=[T // 2])
+    return step
+
+
+def cpu_reference(args, wl, budget_s=20.0, steps=1, warmup=0):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    full_vox = wl["spatial"][0] * wl["spatial"][1] * wl["spatial"][2] * (args.batch or wl["batch"])
+    # probe a small crop to size the sample for ~budget seconds of CPU work
+    probe_sp = tuple(max(16, s // 8) for s in wl["spatial"])   # 4 stride-2 levels need multiples of 16
+    f = _oracle_step_fn(wl, 1, probe_sp)
+    f()
+    t0 = time.perf_counter()
+    f()
+    probe_s = time.perf_counter() - t0
+    per_vox = probe_s / (probe_sp[0] * probe_sp[1] * probe_sp[2])
+    target_vox = budget_s / max(1, steps + warmup) / per_vox
+    sp = list(probe_sp)
+    full = list(wl["spatial"])
+    # grow the crop by doubling dims (last first) while it stays within budget and within the volume
+    for ax in (2, 1, 0, 2, 1, 0, 2, 1, 0):
+        if sp[ax] * 2 <= full[ax] and sp[0] * sp[1] * sp[2] * 2 <= target_vox:
+            sp[ax] *= 2
+    sp = tuple(sp)
+    f = _oracle_step_fn(wl, 1, sp)
+    for _ in range(warmup):
+        f()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f()
+    dt = (time.perf_counter() - t0) / steps
+    scale = full_vox / (sp[0] * sp[1] * sp[2])
+    return {"value": 1.0 / (dt * scale), "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": "oracle port (fp32 torch CPU restatement of the reference) on 1 volume crop %dx%dx%d = 1/%.0f of a batch step; "
+                      "%.2f s per sample step, extrapolated linearly in voxels" % (sp[0], sp[1], sp[2], scale, dt),
+            "sample_seconds_per_step": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    K, W = args.steps, args.warmup
+    # bounded: the whole run (W + K sample steps) stays within ~2.5 minutes of CPU work
+    cb = cpu_reference(args, wl, budget_s=float(os.environ.get("BENCH_CPU_BUDGET_S", 150.0)), steps=max(1, K), warmup=max(0, min(W, 1)))
+    B = args.batch or wl["batch"]
+    line = {"impl": "reference", "metric": "denoising steps/sec", "value": cb["value"],
+            "unit": "steps/s (1 step = UNet forward + categorical posterior/draw for a batch of %d volumes)" % B,
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": args.workload, "global_batch": B, "note": "CPU arm runs on rank 0 only; "
+                       "the reference is pure Python/PyTorch and /root/reference does not travel to the GPU box, so the oracle port "
+                       "(pinned against the unmodified reference in tests/test_oracle_pinning.py) stands in for it"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ccdm_cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override batch per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -217,34 +217,49 @@ class DenoisingModel(nn.Module):
 
     def _resident_steps(self, xt, cond, context, t_values, coefs, spatial):
         """Steps t > 1 without leaving the channels-last device layout; returns fp32 one-hot xt."""
+        st = self.resident_begin(xt, cond, context)
+        for i, t in enumerate(t_values):
+            q = None
+            if self.q_noise is not None:
+                q = self.q_noise[i].to(xt.device, torch.float32).contiguous()
+            self.resident_step(st, t, coefs[i], q=q, offset=i)
+            if self.record is not None:
+                self.record.append(st["lab_a"].view(st["B"], st["V"]).clone())
+        return self.resident_end(st)
+
+    # -- device-resident sampler state (also used by bench.py to time exactly K steps) -----------
+    def resident_begin(self, xt, cond, context=None) -> dict:
+        """xt fp32 one-hot [B, C, *sp] and cond [B, 1, *sp] on the device -> loop state: the UNet
+        plan (input buffer filled), uint8 label ping-pong buffers, channels-last condition."""
         unet = self.unet
         dev = xt.device
         B, Cc = xt.shape[:2]
+        spatial = tuple(xt.shape[2:])
         V = int(math.prod(spatial))
         plan = unet.plan_for(B, spatial, context)
         if "context" in plan.inputs:
             plan.inputs["context"].copy_(unet._ctx_cl(context, B))
         xin = plan.inputs["x"]
+        if self.use_cuda_graph and plan.graph is None:
+            plan.capture()
         ops.nchw_to_cl(xt, cond, c_pad=unet.in_channels_padded, out=xin)
         lab_a = torch.empty((B * V,), dtype=torch.uint8, device=dev)
         lab_b = torch.empty_like(lab_a)
         ops.cat_posterior_sample(xt, None, None, ops.CAT_ARGMAX_GIVEN, clamp_min=0.0, labels=lab_a.view(B, V))
         n_cond = cond.shape[1] if cond is not None else 0
-        cond_cl = None
-        if cond is not None:
-            cond_cl = ops.nchw_to_cl(cond, None, c_pad=8)[..., :n_cond].contiguous()
-        if self.use_cuda_graph and plan.graph is None:
-            plan.capture()
-            ops.nchw_to_cl(xt, cond, c_pad=unet.in_channels_padded, out=xin)
-        for i, t in enumerate(t_values):
-            plan.inputs["t"].fill_(float(t))
-            plan.run()
-            q = None
-            if self.q_noise is not None:
-                q = self.q_noise[i].to(dev, torch.float32).contiguous()
-            ops.cat_step_cl(plan.outputs["head"], lab_a, coefs[i], lab_b, B, V, Cc, mode=ops.CAT_SAMPLE, q=q, cond=cond_cl,
-                            n_cond=n_cond, next_x=xin, seed=self.philox_seed, offset=i)
-            lab_a, lab_b = lab_b, lab_a
-            if self.record is not None:
-                self.record.append(lab_a.view(B, V).clone())
-        return ops.cl_to_nchw(xin, Cc, spatial)
+        cond_cl = ops.nchw_to_cl(cond, None, c_pad=8)[..., :n_cond].contiguous() if cond is not None else None
+        return dict(plan=plan, xin=xin, lab_a=lab_a, lab_b=lab_b, cond_cl=cond_cl, n_cond=n_cond, B=B, C=Cc, V=V,
+                    spatial=spatial)
+
+    def resident_step(self, st: dict, t: int, coef: Tensor, q: Optional[Tensor] = None, offset: int = 0):
+        """One reverse step t -> t-1 (t > 1): UNet forward, then ONE fused kernel: softmax over the
+        head logits + posterior + clamp + draw + next UNet input (one-hot | condition) in place."""
+        plan = st["plan"]
+        plan.inputs["t"].fill_(float(t))
+        plan.run()
+        ops.cat_step_cl(plan.outputs["head"], st["lab_a"], coef, st["lab_b"], st["B"], st["V"], st["C"], mode=ops.CAT_SAMPLE,
+                        q=q, cond=st["cond_cl"], n_cond=st["n_cond"], next_x=st["xin"], seed=self.philox_seed, offset=offset)
+        st["lab_a"], st["lab_b"] = st["lab_b"], st["lab_a"]
+
+    def resident_end(self, st: dict) -> Tensor:
+        return ops.cl_to_nchw(st["xin"], st["C"], st["spatial"])

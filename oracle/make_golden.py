@@ -215,6 +215,26 @@ def ddim_tables(name="ddim_tables"):
     print(name, "ok")
 
 
+def param_shapes(name="param_shapes"):
+    """Parameter names/shapes of the reference networks (taken from the reference modules): lets the
+    oracle build synthetic state_dicts on machines without /root/reference."""
+    import json
+    out = {}
+    rc = refshim.ccdm()
+    for key, params, C, sp in (("CCDM_PARAMS_YML", configs.CCDM_PARAMS_YML, 12, (32, 32, 32)), ("CCDM_TINY", configs.CCDM_TINY, 4, (8, 8, 8)),
+                               ("CCDM_TINY_C12", configs.CCDM_TINY, 12, (8, 8, 8))):
+        m = rc.build_model(time_steps=10, schedule="cosine", schedule_params={"s": 0.008}, input_shapes=[(1,) + sp, (C,) + sp],
+                           cond_encoded_shape=None, backbone="unet_openai", backbone_params=dict(params),
+                           dataset_file="x", step_T_sample="majority", dims=3)
+        out[key] = {k[5:]: list(v) for k, v in weights.shapes_of(m).items() if k.startswith("unet.")}
+    rl = refshim.ldm()
+    for key in ("LDM_AE", "LDM_PIXEL", "LDM_TINY", "LDM_TINY_XATTN"):
+        out[key] = {k: list(v) for k, v in weights.shapes_of(rl.UNetModel(**getattr(configs, key))).items()}
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".json"), "w") as f:
+        json.dump(out, f)
+    print(name, {k: len(v) for k, v in out.items()})
+
+
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -223,6 +243,8 @@ def main(argv):
     def want(k):
         return "all" in which or k in which
 
+    if want("shapes"):
+        param_shapes()
     if want("posterior"):
         posterior_cases()
     if want("ddim_tables"):

@@ -55,3 +55,12 @@ def uniform_one_hot(seed: int, B: int, C: int, spatial) -> torch.Tensor:
 
 def normal(seed: int, shape) -> torch.Tensor:
     return torch.from_numpy(np.random.RandomState(seed).standard_normal(shape).astype(np.float32))
+
+
+def reference_shapes(name: str) -> Dict[str, tuple]:
+    """Parameter shapes of a named reference network (oracle/param_shapes.json, written by
+    make_golden.py from the reference modules themselves)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "param_shapes.json")) as f:
+        return {k: tuple(v) for k, v in json.load(f)[name].items()}
