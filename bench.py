@@ -219,6 +219,23 @@ def run_ours(args):
                 d = kinds.setdefault(name, [0.0, 0])
                 d[0] += a.elapsed_time(b) / reps
                 d[1] += 1
+        if args.detail:
+            import ctypes
+            rows = []
+            for (fn, fargs), (name, a, b) in zip(plan.steps, evs):
+                d = a.elapsed_time(b)
+                if name == "gg_conv_fwd":
+                    ca = ctypes.cast(fargs[0], ctypes.POINTER(_C.ConvArgs)).contents if not hasattr(fargs[0], "_obj") else fargs[0]._obj
+                    cin = sum(ca.src[i].C for i in range(ca.nsrc))
+                    kk = _C.lib().gg_conv_packed_k(ctypes.byref(ca))
+                    fl = 2.0 * ca.N * ca.Do * ca.Ho * ca.Wo * ca.Cout * kk
+                    rows.append("conv N%d in %dx%dx%d out %dx%dx%d Cin %d(nsrc %d) Cout %d taps %dx%dx%d s%d K %d : %.3f ms %.0f TF/s"
+                                % (ca.N, ca.D, ca.H, ca.W, ca.Do, ca.Ho, ca.Wo, cin, ca.nsrc, ca.Cout, ca.kd, ca.kh, ca.kw, ca.stride, kk, d,
+                                   fl / d / 1e9))
+                else:
+                    rows.append("%s : %.3f ms" % (name, d))
+            with open(os.path.join(ROOT, "gpurun_out", "bench_detail.txt"), "w") as f:
+                f.write("\n".join(rows) + "\n")
         kernel_ms = {k: round(v[0], 4) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
         n_conv = kinds["gg_conv_fwd"][1] // reps
         conv_ms = kinds["gg_conv_fwd"][0]
@@ -335,6 +352,7 @@ def main():
     ap.add_argument("--workload", default="ccdm_cfg2", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override batch per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="write per-launch times of one step to gpurun_out/bench_detail.txt")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

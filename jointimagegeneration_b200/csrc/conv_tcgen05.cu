@@ -129,6 +129,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred)
+        : "r"(0xffffffffu));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------ kernel
@@ -171,75 +181,81 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
 
     if (warp == 0) {
         // ================================================================ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles_n;
-                int mt = tile / p.n_tiles_n;
-                const int iw = mt % p.tw; mt /= p.tw;
-                const int ih = mt % p.th; mt /= p.th;
-                const int id = mt % p.td; mt /= p.td;
-                const int n0 = mt * p.bn, d0 = id * p.bd, h0 = ih * p.bh, w0 = iw * p.bw;
-                int kb = 0;
-                for (int s = 0; s < p.nseg; ++s) {
-                    const ConvSeg sg = p.seg[s];
-                    for (int a = 0; a < sg.kd; ++a)
-                        for (int b = 0; b < sg.kh; ++b)
-                            for (int c = 0; c < sg.kw; ++c) {
-                                int mi = sg.map0, od, oh, ow;
-                                if (sg.stride2) {
-                                    // input = 2*o + k - 1: k=0 -> odd grid at o-1, k=1 -> even grid at o, k=2 -> odd grid at o
-                                    const int pd = sg.s2d ? ((a + 1) & 1) : 0, ph = sg.s2h ? ((b + 1) & 1) : 0,
-                                              pw = sg.s2w ? ((c + 1) & 1) : 0;
-                                    mi += pd * 4 + ph * 2 + pw;
-                                    od = sg.s2d ? (a == 0 ? -1 : 0) : sg.od + a;
-                                    oh = sg.s2h ? (b == 0 ? -1 : 0) : sg.oh + b;
-                                    ow = sg.s2w ? (c == 0 ? -1 : 0) : sg.ow + c;
-                                } else {
-                                    od = sg.od + a; oh = sg.oh + b; ow = sg.ow + c;
-                                }
-                                for (int j = 0; j < sg.nchunks; ++j) {
-                                    mbar_wait(&empty[stage], phase ^ 1u);
+        // the whole warp runs the loop (uniform control flow); one elected lane issues the copies
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles_n;
+            int mt = tile / p.n_tiles_n;
+            const int iw = mt % p.tw; mt /= p.tw;
+            const int ih = mt % p.th; mt /= p.th;
+            const int id = mt % p.td; mt /= p.td;
+            const int n0 = mt * p.bn, d0 = id * p.bd, h0 = ih * p.bh, w0 = iw * p.bw;
+            int kb = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const ConvSeg sg = p.seg[s];
+                for (int a = 0; a < sg.kd; ++a)
+                    for (int b = 0; b < sg.kh; ++b)
+                        for (int c = 0; c < sg.kw; ++c) {
+                            int mi = sg.map0, od, oh, ow;
+                            if (sg.stride2) {
+                                // input = 2*o + k - 1: k=0 -> odd grid at o-1, k=1 -> even grid at o, k=2 -> odd grid at o
+                                const int pd = sg.s2d ? ((a + 1) & 1) : 0, ph = sg.s2h ? ((b + 1) & 1) : 0,
+                                          pw = sg.s2w ? ((c + 1) & 1) : 0;
+                                mi += pd * 4 + ph * 2 + pw;
+                                od = sg.s2d ? (a == 0 ? -1 : 0) : sg.od + a;
+                                oh = sg.s2h ? (b == 0 ? -1 : 0) : sg.oh + b;
+                                ow = sg.s2w ? (c == 0 ? -1 : 0) : sg.ow + c;
+                            } else {
+                                od = sg.od + a; oh = sg.oh + b; ow = sg.ow + c;
+                            }
+                            for (int j = 0; j < sg.nchunks; ++j) {
+                                mbar_wait(&empty[stage], phase ^ 1u);
+                                if (elect_one()) {
                                     mbar_expect_tx(&full[stage], stage_bytes);
                                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                                     tma_load_5d(sa, &p.amap[mi], &full[stage], j * BK, w0 + ow, h0 + oh, d0 + od, n0);
                                     tma_load_2d(sa + A_BYTES, &p.wmap, &full[stage], kb * BK, nt * BN);
-                                    ++kb;
-                                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                                 }
+                                __syncwarp();
+                                ++kb;
+                                if (++stage == stages) { stage = 0; phase ^= 1u; }
                             }
-                }
+                        }
             }
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            int stage = 0;
-            uint32_t phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        // whole warp loops (uniform control flow, no per-instruction election); one elected lane
+        // issues the four K=16 MMAs of a stage and the commit that frees it
+        // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t smem_base = smem_u32(smem);
+        int stage = 0;
+        uint32_t phase = 0, acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                if (elect_one()) {
+                    const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // +32 bytes per K=16 step inside the 128-byte swizzle atom (encoded >> 4)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    // +32 bytes per K=16 step inside the 128-byte swizzle atom (encoded >> 4)
+                    umma_bf16(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+                    umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                    umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                    umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
                     umma_commit(&empty[stage]);
-                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    if (kb == p.num_kb - 1) umma_commit(&tfull[acc]);
                 }
-                umma_commit(&tfull[acc]);
-                acc ^= 1u;
-                if (acc == 0) acc_phase ^= 1u;
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
         }
     } else {
         // ================================================================ epilogue (warps 2..5)

@@ -280,6 +280,8 @@ __device__ __forceinline__ float quad_max(float v) {
 }
 
 __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_args a) {
+    // Production form: fast intrinsics (ex2/lg2/rcp approximations); the draw is arg-max of p_c / q_c
+    // -- the common normaliser 1/sum(p) cannot change the arg-max, so it is only applied to probs_out.
     const int64_t Vt = (int64_t)a.B * a.V;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t vox = t >> 2;
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_a
     const int b = (int)(vx / a.V);
     // softmax over the head conv's logits (unet.py:720), classes [4*sub, 4*sub+4)
     float4 lg = ldg_nc_f4(a.logits + vx * a.Cpad + 4 * sub);
+    const int lab = a.labels_in[vx];
     float l[4] = {lg.x, lg.y, lg.z, lg.w};
     float m = -INFINITY;
 #pragma unroll
@@ -300,26 +303,20 @@ __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_a
     m = quad_max(m);
     float ex[4], se = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { ex[e] = (4 * sub + e < C) ? expf(l[e] - m) : 0.f; se += ex[e]; }
+    for (int e = 0; e < 4; ++e) { ex[e] = __expf(l[e] - m); se += ex[e]; }       // exp(-inf) = 0 for padding classes
     se = quad_sum(se);
-    const float inv = 1.0f / se;
+    const float inv = __fdividef(1.0f, se);
     // posterior (closed form) with x_t given as a label
-    const int lab = a.labels_in[vx];
     const float al = __ldg(a.coef + 2 * b), g = __ldg(a.coef + 2 * b + 1);
     const float k = (1.0f - al) / (float)C, h = (1.0f - g) / (float)C;
-    float u[4], r[4], U = 0.f, R = 0.f;
+    // u_c = alpha [c == lab] + k; U = sum_c u_c = alpha + C k = 1
+    float u[4], r[4], R = 0.f;
+    const float hU = h * (al + (float)C * k);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int c = 4 * sub + e;
-        u[e] = c < C ? ((c == lab ? al : 0.f) + k) : 0.f;
-        U += u[e];
-    }
-    U = quad_sum(U);
-    const float hU = h * U;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int c = 4 * sub + e;
-        r[e] = c < C ? (ex[e] * inv) / (g * u[e] + hU) : 0.f;
+        u[e] = (c == lab ? al : 0.f) + k;
+        r[e] = c < C ? __fdividef(ex[e] * inv, fmaf(g, u[e], hU)) : 0.f;
         R += r[e];
     }
     R = quad_sum(R);
@@ -328,10 +325,9 @@ __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_a
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int c = 4 * sub + e;
-        p[e] = c < C ? fmaxf(u[e] * (g * r[e] + hR), a.clamp_min) : 0.f;
+        p[e] = c < C ? fmaxf(u[e] * fmaf(g, r[e], hR), a.clamp_min) : 0.f;
         P += p[e];
     }
-    P = quad_sum(P);
     float best = -1.f;
     int bi = 0;
     if (a.mode == GG_CAT_SAMPLE) {
@@ -349,13 +345,13 @@ __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_a
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float v = (4 * sub + e < C) ? __fdiv_rn(__fdiv_rn(p[e], P), q[e]) : -1.f;
+            const float v = (4 * sub + e < C) ? __fdividef(p[e], q[e]) : -1.f;
             if (v > best) { best = v; bi = 4 * sub + e; }
         }
     } else {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float v = (4 * sub + e < C) ? __fdiv_rn(p[e], P) : -1.f;
+            const float v = (4 * sub + e < C) ? p[e] : -1.f;
             if (v > best) { best = v; bi = 4 * sub + e; }
         }
     }
@@ -371,7 +367,7 @@ __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_a
         const int64_t v = vx - (int64_t)b * a.V;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-            if (4 * sub + e < C) a.probs_out[((int64_t)b * C + 4 * sub + e) * a.V + v] = p[e];
+            if (4 * sub + e < C) a.probs_out[((int64_t)b * C + 4 * sub + e) * a.V + v] = p[e];      // clamped, un-normalised
     }
     if (sub == 0) a.labels_out[vx] = (uint8_t)bi;
     if (a.next_x != nullptr) {
