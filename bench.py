@@ -35,7 +35,13 @@ WORKLOADS = {
                       desc="CCDM mask sampler 128x128x64 (tensor [8,12,64,128,128]), 12 classes, 1000-step chain, batch 8, bf16"),
     "ccdm_cfg1": dict(spatial=(32, 32, 32), C=12, batch=1, T=10, flop_per_sample=1.97e11,
                       desc="CCDM mask sampler 32x32x32, 12 classes, 10 steps, batch 1"),
+    "ldm_cfg3": dict(spatial=(64, 64), C=4, batch=16, T=50, flop_per_sample=1.24e11, kind="ldm",
+                     desc="LDM conditional CT slice generator (ruijin-ldm_from_controlnet_ae.yaml UNet), latent 4x64x64, "
+                          "concat mask/prev-slice context, DDIM 50 steps eta 0, batch 16, bf16"),
 }
+LDM_AE_NET = dict(dims=2, image_size=512, in_channels=8, out_channels=4, model_channels=160, attention_resolutions=[8, 4, 2],
+                  num_res_blocks=2, channel_mult=[1, 2, 4, 4, 5], num_head_channels=32)      # ruijin-ldm_from_controlnet_ae.yaml:17-40
+LDM_SCHEDULE = dict(timesteps=1000, linear_start=0.0015, linear_end=0.0195)
 
 
 def load_peaks():
@@ -104,6 +110,8 @@ def run_ours(args):
     from jointimagegeneration_b200.ccdm import build_model
 
     wl = WORKLOADS[args.workload]
+    if wl.get("kind") == "ldm":
+        return run_ours_ldm(args)
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -250,15 +258,156 @@ def run_ours(args):
         cat_ms = kinds["gg_cat_step_cl"][0]
         alg_b = 50.0 * B * V
         act_b = (64 + 1 + 1 + 2 * plan.inputs["x"].shape[-1] + 2) * B * V
-        line["roofline_hbm"] = {"bound": "hbm", "kernel": "cat_step_cl_kernel (softmax + posterior + clamp + draw + next input)",
-                                "achieved": alg_b / (cat_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                "frac": alg_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                                "algorithmic_bytes": alg_b, "moved_bytes": act_b,
-                                "moved_frac": act_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "launch_ms": cat_ms}
+        line["roofline_hbm_resident"] = {"bound": "hbm", "kernel": "cat_step_cl_kernel (softmax + posterior + clamp + Philox draw + next input)",
+                                         "achieved": alg_b / (cat_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                         "frac": alg_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                         "algorithmic_bytes": alg_b, "moved_bytes": act_b,
+                                         "moved_frac": act_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "launch_ms": cat_ms}
+        # the per-voxel kernel at the reference's tensor interface (fp32 [B,C,V] in/out, injected Exp(1) noise):
+        # 16*C = 192 B/voxel algorithmic; tensors (4 x 403 MB) exceed L2
+        x0p = torch.softmax(torch.randn((B, Cc) + sp, device=dev), 1)
+        qn = torch.empty((B * V, Cc), device=dev).exponential_(1)
+        outp = torch.empty_like(x0p)
+        for _ in range(2):
+            ops.cat_posterior_sample(x0p, x_T, coefs[5], ops.CAT_SAMPLE, q=qn, out=outp)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(5):
+            ops.cat_posterior_sample(x0p, x_T, coefs[5], ops.CAT_SAMPLE, q=qn, out=outp)
+        eb.record()
+        torch.cuda.synchronize()
+        pm = ea.elapsed_time(eb) / 5
+        ib = 16.0 * Cc * B * V
+        line["roofline_hbm"] = {"bound": "hbm", "kernel": "cat_posterior_kernel<12> (theta_post_prob + clamp + categorical draw, reference interface)",
+                                "achieved": ib / (pm / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": ib / (pm / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": ib,
+                                "launch_ms": pm, "peak_source": peaks["source"] + " (copy bandwidth)"}
+        del x0p, qn, outp
         line["kernel_ms"] = kernel_ms
         line["arena_bytes"] = plan.arena_bytes
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(args, wl, budget_s=20.0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def instrument_plan(plan, extra=None, reps=2):
+    """CUDA-event time of every launch of one planned forward (eager, current stream) -> {name: [ms, count]}."""
+    import torch
+    from jointimagegeneration_b200 import _C
+    kinds = {}
+    torch.cuda.synchronize()
+    for _ in range(reps):
+        evs = []
+        s = _C.stream()
+        for fn, fargs in plan.steps:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _C.check(fn(*fargs, s), fn.__name__)
+            b.record()
+            evs.append((fn.__name__, a, b))
+        if extra is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            name = extra()
+            b.record()
+            evs.append((name, a, b))
+        torch.cuda.synchronize()
+        for name, a, b in evs:
+            d = kinds.setdefault(name, [0.0, 0])
+            d[0] += a.elapsed_time(b) / reps
+            d[1] += 1
+    return {k: (v[0], v[1] // reps) for k, v in kinds.items()}
+
+
+def run_ours_ldm(args):
+    """BASELINE config 3: one step = UNet eps-prediction for the batch + fused DDIM update."""
+    import torch
+    import torch.distributed as dist
+    from jointimagegeneration_b200 import _C, ops
+    from jointimagegeneration_b200.ldm import DDIMSampler, LatentDiffusion, UNetModel
+
+    wl = WORKLOADS[args.workload]
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    assert world == args.gpus
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    B, S = args.batch or wl["batch"], wl["T"]
+    hw = wl["spatial"]
+    torch.manual_seed(4321 + rank)
+    unet = UNetModel(**LDM_AE_NET)
+    randomize_zero_modules(unet, 7)
+    ld = LatentDiffusion(unet, conditioning_key="concat", **LDM_SCHEDULE).to(dev).eval()
+    unet.use_cuda_graph = True
+    sampler = DDIMSampler(ld)
+    sampler.make_schedule(S, ddim_eta=0.0, verbose=False)
+    x = torch.randn((B, 4) + hw, device=dev)
+    c = torch.randn((B, 4) + hw, device=dev)
+    steps_t = [int(v) for v in sampler.ddim_timesteps[::-1]]
+    ts = [torch.full((B,), v, device=dev, dtype=torch.long) for v in steps_t]
+    state = {"x": x}
+
+    def step(i):
+        j = i % S
+        state["x"], _ = sampler.p_sample_ddim(state["x"], c, ts[j], 2, index=S - 1 - j)
+        if j == S - 1:
+            state["x"] = x
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    if world > 1:
+        tm = torch.tensor([ms], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    value = world * K / (ms / 1e3)
+    plan = unet.plan_for(B, hw)
+    # e2e: the public call sample_cond makes (sample_diffusion.py:212), host conditioning in, host samples out
+    c_host = c.cpu().pin_memory()
+    out_host = torch.empty((B, 4) + hw).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    smp, _ = sampler.sample(S=S, batch_size=B, shape=(4,) + hw, conditioning=c_host.to(dev, non_blocking=True), eta=0.0, verbose=False, dims=2)
+    out_host.copy_(smp)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    line = {"metric": "denoising steps/sec", "value": value, "unit": "steps/s (1 step = UNet eps forward + DDIM update for a batch of %d latents)" % B,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": args.workload, "global_batch": B * world, "batch_per_gpu": B,
+                       "l2": "working set (267.5 M params bf16 + activations) exceeds L2; no explicit flush", "cuda_graph": True,
+                       "parallelism": "independent samples sharded over ranks (dp%d)" % world},
+            "clocks": clk, "gpu_launches": (plan.num_launches + 3) * K,
+            "e2e": {"value": world * S / e2e_s, "unit": "steps/s", "steps": S, "h2d_bytes_per_step": c_host.numel() * 4 // S,
+                    "d2h_bytes_per_step": out_host.numel() * 4 // S, "call": "DDIMSampler.sample(S=50, conditioning=host tensor) -> host"},
+            "slices_per_sec": value * B / S}
+    if rank == 0:
+        peaks = load_peaks()
+        kinds = instrument_plan(plan)
+        conv_ms, n_conv = kinds["gg_conv_fwd"]
+        ach = wl["flop_per_sample"] * B / (conv_ms / 1e3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "conv_tcgen05_kernel (all %d launches of one step)" % n_conv, "achieved": ach,
+                            "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": None,
+                            "algorithmic_flop": wl["flop_per_sample"] * B, "issued_flop": plan.flops,
+                            "peak_source": peaks["source"] + " (bf16 sustained)",
+                            "whole_step_frac": wl["flop_per_sample"] * B / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
+        line["kernel_ms"] = {k: round(v[0], 4) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -272,6 +421,16 @@ def _oracle_step_fn(wl, B, sp):
     import numpy as np
     import torch
     from oracle import diffusion, nets, weights
+    if wl.get("kind") == "ldm":
+        from oracle import ddim
+        sd = weights.synth_state_dict(weights.reference_shapes("LDM_AE"), 1)
+        acp = ddim.alphas_cumprod_f32(ddim.make_beta_schedule_linear(1000, LDM_SCHEDULE["linear_start"], LDM_SCHEDULE["linear_end"]))
+        x = weights.normal(2, (B, 4) + tuple(sp))
+        c = weights.normal(3, (B, 4) + tuple(sp))
+
+        def step_ldm():
+            return ddim.ddim_sample(lambda xx, tt: nets.unet_forward(sd, torch.cat([xx, c], 1), tt, num_head_channels=32), acp, x, 1, 0.0)
+        return step_ldm
     Cc, T = wl["C"], wl["T"]
     sd = weights.synth_state_dict(weights.reference_shapes("CCDM_PARAMS_YML"), 1)
     _, alphas, cumalphas = diffusion.cosine_schedule(T)
@@ -291,6 +450,17 @@ def cpu_reference(args, wl, budget_s=20.0, steps=1, warmup=0):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if wl.get("kind") == "ldm":
+        B = args.batch or wl["batch"]
+        f = _oracle_step_fn(wl, 1, wl["spatial"])
+        f()
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps)):
+            f()
+        dt = (time.perf_counter() - t0) / max(1, steps)
+        return {"value": 1.0 / (dt * B), "unit": "steps/s", "cores": cores, "kind": "port",
+                "sample": "oracle port on 1 of the %d latents of a batch step; %.2f s per sample step, extrapolated x%d" % (B, dt, B),
+                "sample_seconds_per_step": dt}
     full_vox = wl["spatial"][0] * wl["spatial"][1] * wl["spatial"][2] * (args.batch or wl["batch"])
     # probe a small crop to size the sample for ~budget seconds of CPU work
     probe_sp = tuple(max(16, s // 8) for s in wl["spatial"])   # 4 stride-2 levels need multiples of 16

@@ -101,6 +101,9 @@ typedef struct {
     float clamp_min;
     int32_t mode;           /* GG_CAT_SAMPLE or GG_CAT_ARGMAX */
     uint64_t seed, offset;
+    int64_t vox_base;       /* global index of this call's first voxel (depth-slab shards): the Philox
+                               counter is keyed on the GLOBAL voxel index, so draws do not depend on the
+                               number of slabs / ranks                                              */
 } gg_cat_step_cl_args;
 
 int gg_cat_step_cl(const gg_cat_step_cl_args* a, gg_stream_t stream);
@@ -185,6 +188,9 @@ typedef struct {
     const void* x;          /* CL bf16 [N, D, H, W, C] */
     int32_t C;              /* multiple of 8 */
     int32_t centre_only;    /* 1: contributes only a 1x1 (centre) term */
+    int32_t d_shift;        /* added to the depth coordinate of every read of this source: a depth slab stored
+                               with leading halo planes is read at  d_out + tap + d_shift              */
+    int32_t reserved;
 } gg_conv_src;
 
 typedef struct {

@@ -44,7 +44,7 @@ class CatStepCLArgs(C.Structure):
                 ("cond", C.c_void_p), ("labels_out", C.c_void_p), ("next_x", C.c_void_p), ("probs_out", C.c_void_p),
                 ("B", C.c_int32), ("C", C.c_int32), ("Cpad", C.c_int32), ("n_cond", C.c_int32), ("Cin_pad", C.c_int32),
                 ("V", C.c_int64), ("clamp_min", C.c_float), ("mode", C.c_int32), ("seed", C.c_uint64),
-                ("offset", C.c_uint64)]
+                ("offset", C.c_uint64), ("vox_base", C.c_int64)]
 
 
 class DdimArgs(C.Structure):
@@ -61,7 +61,7 @@ class GnFinalizeArgs(C.Structure):
 
 
 class ConvSrc(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("C", C.c_int32), ("centre_only", C.c_int32)]
+    _fields_ = [("x", C.c_void_p), ("C", C.c_int32), ("centre_only", C.c_int32), ("d_shift", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ConvArgs(C.Structure):

@@ -181,7 +181,7 @@ class DenoisingModel(nn.Module):
             step0 = 0
         unet = self.unet
         plan = unet.plan_for(B, spatial, context)
-        if self.use_cuda_graph and plan.graph is None:
+        if self.use_cuda_graph and plan.graph is None and not plan.has_py:
             plan.capture()
         if "context" in plan.inputs:
             plan.inputs["context"].copy_(unet._ctx_cl(context, B))
@@ -240,7 +240,7 @@ class DenoisingModel(nn.Module):
         if "context" in plan.inputs:
             plan.inputs["context"].copy_(unet._ctx_cl(context, B))
         xin = plan.inputs["x"]
-        if self.use_cuda_graph and plan.graph is None:
+        if self.use_cuda_graph and plan.graph is None and not plan.has_py:
             plan.capture()
         ops.nchw_to_cl(xt, cond, c_pad=unet.in_channels_padded, out=xin)
         lab_a = torch.empty((B * V,), dtype=torch.uint8, device=dev)
@@ -248,8 +248,10 @@ class DenoisingModel(nn.Module):
         ops.cat_posterior_sample(xt, None, None, ops.CAT_ARGMAX_GIVEN, clamp_min=0.0, labels=lab_a.view(B, V))
         n_cond = cond.shape[1] if cond is not None else 0
         cond_cl = ops.nchw_to_cl(cond, None, c_pad=8)[..., :n_cond].contiguous() if cond is not None else None
+        slab = unet.engine.slab
+        vox_base = slab.rank * V if slab is not None else 0      # slabs are equal-sized, contiguous in depth
         return dict(plan=plan, xin=xin, lab_a=lab_a, lab_b=lab_b, cond_cl=cond_cl, n_cond=n_cond, B=B, C=Cc, V=V,
-                    spatial=spatial)
+                    spatial=spatial, vox_base=vox_base)
 
     def resident_step(self, st: dict, t: int, coef: Tensor, q: Optional[Tensor] = None, offset: int = 0):
         """One reverse step t -> t-1 (t > 1): UNet forward, then ONE fused kernel: softmax over the
@@ -258,7 +260,8 @@ class DenoisingModel(nn.Module):
         plan.inputs["t"].fill_(float(t))
         plan.run()
         ops.cat_step_cl(plan.outputs["head"], st["lab_a"], coef, st["lab_b"], st["B"], st["V"], st["C"], mode=ops.CAT_SAMPLE,
-                        q=q, cond=st["cond_cl"], n_cond=st["n_cond"], next_x=st["xin"], seed=self.philox_seed, offset=offset)
+                        q=q, cond=st["cond_cl"], n_cond=st["n_cond"], next_x=st["xin"], seed=self.philox_seed, offset=offset,
+                        vox_base=st["vox_base"])
         st["lab_a"], st["lab_b"] = st["lab_b"], st["lab_a"]
 
     def resident_end(self, st: dict) -> Tensor:

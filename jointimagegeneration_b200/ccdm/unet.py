@@ -68,6 +68,13 @@ class UNetModel(nn.Module):
             self._engine = UNetEngine(self, self.dims, self.num_heads, self.num_head_channels)
         return self._engine
 
+    def enable_slab(self, comm):
+        """Depth-slab decomposition of ONE volume over the ranks of ``comm`` (sharding.SlabComm): every
+        forward then takes this rank's slab [1, C, D/world, H, W] and exchanges halos / GroupNorm
+        partial sums / attention keys+values with the other ranks (BASELINE config 5).  None disables."""
+        self.engine.slab = comm
+        self.engine.plans.clear()
+
     def invalidate(self):
         """Re-pack weights on the next forward (call after changing parameters in place)."""
         if self._engine is not None:

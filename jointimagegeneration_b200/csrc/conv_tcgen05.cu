@@ -36,6 +36,7 @@ struct ConvSeg {
     int od, oh, ow;  // offset of tap 0 (input coordinate = output coordinate + o + tap)
     int stride2;   // 1: tap -> parity map (map0 + parity code) and offset {-1, 0, 0}
     int s2d, s2h, s2w;  // which dims are strided (dims < 3 leave d (and h) unstrided)
+    int dshift;    // extra depth offset of this source (halo-padded depth slabs)
 };
 
 struct alignas(64) ConvParams {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
                                 if (elect_one()) {
                                     mbar_expect_tx(&full[stage], stage_bytes);
                                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                                    tma_load_5d(sa, &p.amap[mi], &full[stage], j * BK, w0 + ow, h0 + oh, d0 + od, n0);
+                                    tma_load_5d(sa, &p.amap[mi], &full[stage], j * BK, w0 + ow, h0 + oh, d0 + od + sg.dshift, n0);
                                     tma_load_2d(sa + A_BYTES, &p.wmap, &full[stage], kb * BK, nt * BN);
                                 }
                                 __syncwarp();
@@ -477,6 +478,7 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
         ConvSeg& sg = p.seg[s];
         sg.map0 = nmaps;
         sg.nchunks = (src.C + BK - 1) / BK;
+        sg.dshift = src.d_shift;
         const int64_t C = src.C;
         if (src.centre_only || a->stride == 1) {
             GG_REQUIRE(nmaps + 1 <= MAX_MAPS, GG_ERR_UNSUPPORTED);

@@ -47,10 +47,11 @@ __device__ __forceinline__ void store_plane(float* p, const float (&src)[VPT]) {
 
 template <int C, int VPT, bool VEC>
 __global__ void __launch_bounds__(256) cat_posterior_kernel(const gg_cat_args a, const int64_t groups_per_sample) {
+    // grid = (groups of VPT voxels, sample): no 64-bit division on the per-thread path
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= groups_per_sample * a.B) return;
-    const int b = (int)(gi / groups_per_sample);
-    const int64_t v0 = (gi - (int64_t)b * groups_per_sample) * VPT;
+    if (gi >= groups_per_sample) return;
+    const int b = blockIdx.y;
+    const int64_t v0 = gi * VPT;
     const int64_t V = a.V;
     const int mode = a.mode;
     const bool given = (mode >= GG_CAT_SAMPLE_GIVEN);
@@ -257,8 +258,8 @@ static int launch_cat(const gg_cat_args& a, cudaStream_t s) {
                      (a.out == nullptr || aligned(a.out, 16)) && (a.q == nullptr || aligned(a.q, 16)) &&
                      (a.out_i64 == nullptr || aligned(a.out_i64, 16)) && (a.labels == nullptr || aligned(a.labels, 4));
     const int64_t gps = (a.V + VPT - 1) / VPT;
-    const int64_t total = gps * a.B;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (a.B > 65535) return GG_ERR_UNSUPPORTED;
+    const dim3 blocks((unsigned)((gps + 255) / 256), (unsigned)a.B);
     if (vec) cat_posterior_kernel<C, VPT, true><<<blocks, 256, 0, s>>>(a, gps);
     else cat_posterior_kernel<C, VPT, false><<<blocks, 256, 0, s>>>(a, gps);
     return launch_result();
@@ -282,14 +283,13 @@ __device__ __forceinline__ float quad_max(float v) {
 __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_args a) {
     // Production form: fast intrinsics (ex2/lg2/rcp approximations); the draw is arg-max of p_c / q_c
     // -- the common normaliser 1/sum(p) cannot change the arg-max, so it is only applied to probs_out.
-    const int64_t Vt = (int64_t)a.B * a.V;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t vox = t >> 2;
-    const int sub = (int)(t & 3);
-    const bool live = vox < Vt;
-    const int64_t vx = live ? vox : Vt - 1;
+    // grid = (64-voxel blocks of one sample, sample)
+    const int b = blockIdx.y;
+    const int64_t vl = (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2);
+    const int sub = threadIdx.x & 3;
+    const bool live = vl < a.V;
+    const int64_t vx = (int64_t)b * a.V + (live ? vl : a.V - 1);
     const int C = a.C;
-    const int b = (int)(vx / a.V);
     // softmax over the head conv's logits (unet.py:720), classes [4*sub, 4*sub+4)
     float4 lg = ldg_nc_f4(a.logits + vx * a.Cpad + 4 * sub);
     const int lab = a.labels_in[vx];
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_a
 #pragma unroll
             for (int e = 0; e < 4; ++e) if (4 * sub + e < C) q[e] = __ldg(a.q + vx * C + 4 * sub + e);
         } else {
-            const uint64_t cc = (uint64_t)vx * 4 + sub;
+            const uint64_t cc = ((uint64_t)vx + (uint64_t)a.vox_base) * 4 + sub;    // global voxel index: slab-invariant
             uint4 rr = philox4x32_10(make_uint4((uint32_t)cc, (uint32_t)(cc >> 32), (uint32_t)a.offset,
                                                 (uint32_t)(a.offset >> 32)),
                                      make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_a
     }
     if (!live) return;
     if (a.probs_out != nullptr) {
-        const int64_t v = vx - (int64_t)b * a.V;
+        const int64_t v = vl;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (4 * sub + e < C) a.probs_out[((int64_t)b * C + 4 * sub + e) * a.V + v] = p[e];      // clamped, un-normalised
@@ -442,10 +442,10 @@ __global__ void __launch_bounds__(256) ddim_kernel(const gg_ddim_args a) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_cl_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
                                                          int C2, __nv_bfloat16* __restrict__ y, int Cpad, int N, int64_t V) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)N * V) return;
-    const int n = (int)(i / V);
-    const int64_t v = i - (int64_t)n * V;
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int n = blockIdx.y;
+    const int64_t i = (int64_t)n * V + v;
     __nv_bfloat16* row = y + i * Cpad;
     for (int c0 = 0; c0 < Cpad; c0 += 8) {
         uint32_t w[4];
@@ -469,10 +469,10 @@ __global__ void __launch_bounds__(256) nchw_to_cl_kernel(const float* __restrict
 template <bool F32>
 __global__ void __launch_bounds__(256) cl_to_nchw_kernel(const void* __restrict__ x, int Cs, float* __restrict__ y, int C,
                                                          int N, int64_t V, int softmax) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)N * V) return;
-    const int n = (int)(i / V);
-    const int64_t v = i - (int64_t)n * V;
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int n = blockIdx.y;
+    const int64_t i = (int64_t)n * V + v;
     auto ld = [&](int c) -> float {
         if (F32) return __ldg(reinterpret_cast<const float*>(x) + i * Cs + c);
         return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i * Cs + c]);
@@ -522,8 +522,8 @@ extern "C" int gg_cat_step_cl(const gg_cat_step_cl_args* a, gg_stream_t stream) 
         GG_REQUIRE(a->Cin_pad % 8 == 0 && a->Cin_pad >= a->C + a->n_cond, GG_ERR_BAD_ARG);
         GG_REQUIRE(aligned(a->next_x, 16), GG_ERR_ALIGNMENT);
     }
-    const int64_t threads = (int64_t)a->B * a->V * 4;
-    const unsigned blocks = (unsigned)((threads + 255) / 256);
+    GG_REQUIRE(a->B <= 65535, GG_ERR_UNSUPPORTED);
+    const dim3 blocks((unsigned)((a->V + 63) / 64), (unsigned)a->B);
     cat_step_cl_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*a);
     return launch_result();
 }
@@ -548,7 +548,8 @@ extern "C" int gg_nchw_to_cl(const float* x1, int32_t C1, const float* x2, int32
     GG_REQUIRE(x1 && y_cl && C1 > 0 && C2 >= 0 && (C2 == 0 || x2) && N > 0 && V > 0, GG_ERR_BAD_ARG);
     GG_REQUIRE(Cpad % 8 == 0 && Cpad >= C1 + C2, GG_ERR_BAD_ARG);
     GG_REQUIRE(aligned(y_cl, 16), GG_ERR_ALIGNMENT);
-    const unsigned blocks = (unsigned)(((int64_t)N * V + 255) / 256);
+    GG_REQUIRE(N <= 65535, GG_ERR_UNSUPPORTED);
+    const dim3 blocks((unsigned)((V + 255) / 256), (unsigned)N);
     nchw_to_cl_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x1, C1, x2, C2, reinterpret_cast<__nv_bfloat16*>(y_cl), Cpad, N, V);
     return launch_result();
 }
@@ -556,7 +557,8 @@ extern "C" int gg_nchw_to_cl(const float* x1, int32_t C1, const float* x2, int32
 extern "C" int gg_cl_to_nchw(const void* x_cl, int32_t Cstride, int32_t src_is_f32, float* y, int32_t C, int32_t N, int64_t V,
                              int32_t softmax, gg_stream_t stream) {
     GG_REQUIRE(x_cl && y && C > 0 && Cstride >= C && N > 0 && V > 0, GG_ERR_BAD_ARG);
-    const unsigned blocks = (unsigned)(((int64_t)N * V + 255) / 256);
+    GG_REQUIRE(N <= 65535, GG_ERR_UNSUPPORTED);
+    const dim3 blocks((unsigned)((V + 255) / 256), (unsigned)N);
     if (src_is_f32) cl_to_nchw_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(x_cl, Cstride, y, C, N, V, softmax);
     else cl_to_nchw_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(x_cl, Cstride, y, C, N, V, softmax);
     return launch_result();

@@ -51,14 +51,14 @@ def cat_posterior_sample(x0, xt, coef, mode, q=None, clamp_min=1e-12, out=None, 
 
 
 def cat_step_cl(logits, labels_in, coef, labels_out, B, V, Cc, mode=CAT_SAMPLE, q=None, cond=None, n_cond=0,
-                next_x=None, probs_out=None, clamp_min=1e-12, seed=0, offset=0):
+                next_x=None, probs_out=None, clamp_min=1e-12, seed=0, offset=0, vox_base=0):
     """Device-resident sampler-loop form (channels-last)."""
     _chk(logits, torch.float32)
     Cpad = logits.shape[-1]
     Cin_pad = next_x.shape[-1] if next_x is not None else 0
     a = _C.CatStepCLArgs(_C.ptr(logits), _C.ptr(labels_in), _C.ptr(q), _C.ptr(coef), _C.ptr(cond), _C.ptr(labels_out),
                          _C.ptr(next_x), _C.ptr(probs_out), B, Cc, Cpad, n_cond, Cin_pad, V, float(clamp_min), mode,
-                         seed, offset)
+                         seed, offset, vox_base)
     _C.check(_C.lib().gg_cat_step_cl(C.byref(a), _C.stream()), "gg_cat_step_cl")
 
 
@@ -211,7 +211,8 @@ def pad_vec(v: Optional[torch.Tensor], n: int) -> Optional[torch.Tensor]:
 
 
 def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=None, emb=None, residual=None,
-                   taps=None, offsets=None, out_spatial=None, y_strides=None, block_n=0, brick=None) -> _C.ConvArgs:
+                   taps=None, offsets=None, out_spatial=None, y_strides=None, block_n=0, brick=None, d_shift=0,
+                   y_f32=False) -> _C.ConvArgs:
     """srcs: list of (CL tensor [N, D, H, W, C], centre_only).  y: CL tensor [N, Do, Ho, Wo, >= Cout8]
     (bf16 or fp32).  Returns the filled gg_conv_args (keeps nothing alive: the caller owns the tensors)."""
     a = _C.ConvArgs()
@@ -224,6 +225,7 @@ def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=Non
         a.src[i].x = _C.ptr(t)
         a.src[i].C = t.shape[-1]
         a.src[i].centre_only = int(bool(centre))
+        a.src[i].d_shift = d_shift
     a.N, a.D, a.H, a.W, a.dims = N, D, H, W, dims
     if taps is None:
         k = ksize
@@ -244,15 +246,15 @@ def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=Non
     a.bias = bias if isinstance(bias, int) else _C.ptr(bias)
     a.emb = _C.ptr(emb)
     a.emb_stride = emb.shape[-1] if emb is not None else 0
-    a.residual = _C.ptr(residual)
-    a.res_stride = residual.shape[-1] if residual is not None else 0
-    a.y = _C.ptr(y)
+    a.residual = residual if isinstance(residual, int) else _C.ptr(residual)
+    a.res_stride = 0 if residual is None else (cout + 7) // 8 * 8 if isinstance(residual, int) else residual.shape[-1]
+    a.y = y if isinstance(y, int) else _C.ptr(y)
     if y_strides is None:
-        cs = y.shape[-1]
+        cs = (cout + 7) // 8 * 8 if isinstance(y, int) else y.shape[-1]
         Do, Ho, Wo = out_spatial
         y_strides = (Do * Ho * Wo * cs, Ho * Wo * cs, Wo * cs, cs)
     a.y_sn, a.y_sd, a.y_sh, a.y_sw = y_strides
-    a.y_is_f32 = int(y.dtype == torch.float32)
+    a.y_is_f32 = int(y_f32) if isinstance(y, int) else int(y.dtype == torch.float32)
     a.Cout = cout
     a.block_n = block_n
     if brick is not None:

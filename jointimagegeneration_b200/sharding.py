@@ -67,3 +67,61 @@ def global_minmax(x: torch.Tensor, group=None) -> Tuple[float, float]:
         dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     return float(mn), float(mx)
+
+
+class SlabComm:
+    """Communication of the depth-slab decomposition of ONE volume (config 5): rank r owns a contiguous
+    range of depth planes of every activation.  Three couplings per forward:
+    one-plane halos before every 3-tap-in-depth conv, GroupNorm statistics over the whole volume
+    (all-gather of the per-rank partial sums, combined in a fixed order on every rank -> identical
+    statistics everywhere), and keys/values of the whole volume at the attention sites.
+    Works over any torch.distributed backend (nccl on B200, gloo in the CPU tests); world == 1
+    degenerates to zero halos / copies, which tests the padded layout on a single GPU."""
+
+    def __init__(self, group=None):
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.bytes_sent = 0
+        self.n_exchanges = 0
+        self.n_gathers = 0
+
+    def exchange_halo(self, t: torch.Tensor, lead: int, depth: int, need_lo: bool = True, need_hi: bool = True):
+        """t: [1, lead + depth + trail, H, W, C]; fills plane lead-1 from the previous rank's last interior
+        plane and plane lead+depth from the next rank's first one (zeros at the ends of the volume)."""
+        r, R = self.rank, self.world
+        lo_halo, hi_halo = t[0, lead - 1], t[0, lead + depth]
+        first, last = t[0, lead], t[0, lead + depth - 1]
+        p2p = []
+        if need_lo:
+            if r > 0:
+                p2p.append(dist.P2POp(dist.irecv, lo_halo, self._peer(r - 1), self.group))
+            else:
+                lo_halo.zero_()
+            if r < R - 1:
+                p2p.append(dist.P2POp(dist.isend, last, self._peer(r + 1), self.group))
+        if need_hi:
+            if r < R - 1:
+                p2p.append(dist.P2POp(dist.irecv, hi_halo, self._peer(r + 1), self.group))
+            else:
+                hi_halo.zero_()
+            if r > 0:
+                p2p.append(dist.P2POp(dist.isend, first, self._peer(r - 1), self.group))
+        self.n_exchanges += 1
+        if p2p:
+            self.bytes_sent += sum(op.tensor.numel() * op.tensor.element_size() for op in p2p if op.op is dist.isend)
+            for w in dist.batch_isend_irecv(p2p):
+                w.wait()
+
+    def _peer(self, group_rank: int) -> int:
+        return group_rank if self.group is None else dist.get_global_rank(self.group, group_rank)
+
+    def all_gather(self, out: torch.Tensor, inp: torch.Tensor):
+        """out (flattened) = concatenation over ranks of inp (flattened)."""
+        self.n_gathers += 1
+        if self.world == 1:
+            out.view(-1).copy_(inp.reshape(-1))
+            return
+        dist.all_gather_into_tensor(out.view(-1), inp.reshape(-1), group=self.group)

@@ -27,19 +27,36 @@ from . import unet_modules as M
 
 @dataclass
 class Act:
-    t: torch.Tensor          # CL bf16 (or fp32 for head logits) [N, D, H, W, C]
+    """An activation.  ``t`` is the FULL tensor [N, lead + D + trail, H, W, C]; lead/trail are halo
+    planes along depth (depth-slab mode only, N == 1 there so the interior is contiguous)."""
+    t: torch.Tensor          # CL bf16 (or fp32 for head logits)
+    lead: int = 0
+    trail: int = 0
+    halo_valid: bool = False
 
     @property
     def N(self): return self.t.shape[0]
 
     @property
-    def sp(self): return tuple(self.t.shape[1:4])
+    def sp(self): return (self.t.shape[1] - self.lead - self.trail, self.t.shape[2], self.t.shape[3])
 
     @property
     def C(self): return self.t.shape[-1]
 
     @property
-    def S(self): return self.t.shape[1] * self.t.shape[2] * self.t.shape[3]
+    def S(self): return self.sp[0] * self.sp[1] * self.sp[2]
+
+    @property
+    def plane_bytes(self): return self.t.shape[2] * self.t.shape[3] * self.t.shape[4] * self.t.element_size()
+
+    @property
+    def ip(self) -> int:
+        """device pointer of the interior (first non-halo plane)"""
+        return self.t.data_ptr() + self.lead * self.plane_bytes
+
+    @property
+    def interior(self) -> torch.Tensor:
+        return self.t[:, self.lead:self.t.shape[1] - self.trail]
 
 
 class _Arena:
@@ -80,7 +97,15 @@ class _Arena:
             self.free.append(store)
 
 
+class _PyStep:
+    def __init__(self, fn):
+        self.fn = fn
+        self.__name__ = getattr(fn, "__name__", "py_step")
+
+
 class Plan:
+    has_py = False
+
     def __init__(self):
         self.steps = []       # (cfunc, args tuple without the stream)
         self.keep = []        # ctypes structs / tensors that must outlive the plan
@@ -93,18 +118,28 @@ class Plan:
     def add(self, fn, *args):
         self.steps.append((fn, args))
 
+    def add_py(self, fn, *args):
+        """A host-side step (collective / halo exchange): called as fn(*args), enqueues on the current stream."""
+        self.steps.append((_PyStep(fn), args))
+        self.has_py = True
+
     def run(self):
         if self.graph is not None:
             self.graph.replay()
             return
         s = _C.stream()
         for fn, args in self.steps:
+            if isinstance(fn, _PyStep):
+                fn.fn(*args)
+                continue
             st = fn(*args, s)
             if st != 0:
                 _C.check(st, fn.__name__)
 
     def capture(self):
         """Capture the forward into a CUDA graph (after one eager warm-up run)."""
+        if self.has_py:
+            raise RuntimeError("plans with collectives (depth-slab mode) run eagerly")
         self.run()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -128,6 +163,7 @@ class UNetEngine:
         self.num_heads = num_heads
         self.num_head_channels = num_head_channels
         self.fused_upsample = fused_upsample
+        self.slab = None            # sharding.SlabComm: depth-slab decomposition of ONE volume over ranks
         self.plans: Dict[tuple, Plan] = {}
         self._wcache: Dict[tuple, torch.Tensor] = {}
         self.lib = None
@@ -153,50 +189,94 @@ class UNetEngine:
     def _vec8(self, key, make, n):
         return self._cached(key, lambda: ops.pad_vec(make(), n))
 
+    # halo planes of every activation in depth-slab mode: [spare, halo_lo | interior | halo_hi]
+    # (the spare plane lets the stride-2 parity maps start one plane early, see _conv)
+    @property
+    def _lead(self): return 2 if self.slab is not None else 0
+
+    @property
+    def _trail(self): return 1 if self.slab is not None else 0
+
+    def _new_act(self, ar, N, sp, Cc, dtype=torch.bfloat16) -> Act:
+        lead, trail = self._lead, self._trail
+        assert lead == 0 or N == 1, "depth-slab mode handles one volume (N == 1)"
+        t = ar.alloc((N, sp[0] + lead + trail, sp[1], sp[2], Cc), dtype)
+        return Act(t, lead, trail)
+
+    def _exchange(self, plan, x: Act, need_lo=True, need_hi=True):
+        if self.slab is None or x.lead == 0 or x.halo_valid:
+            return
+        plan.add_py(self.slab.exchange_halo, x.t, x.lead, x.sp[0], need_lo, need_hi)
+        x.halo_valid = need_lo and need_hi
+
     # --------------------------------------------------------------------------- primitives
     def _gn(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm, silu: bool) -> Act:
         lib = self.lib
         N, S = x1.N, x1.S
         C1, C2 = x1.C, (x2.C if x2 is not None else 0)
-        n1 = ops.gn_num_chunks(S, C1)
-        p1 = ar.alloc((N, n1, C1, 2), torch.float32)
-        plan.add(lib.gg_gn_partial, _C.ptr(x1.t), N, S, C1, _C.ptr(p1))
-        p2, n2 = None, 0
-        if x2 is not None:
-            n2 = ops.gn_num_chunks(S, C2)
-            p2 = ar.alloc((N, n2, C2, 2), torch.float32)
-            plan.add(lib.gg_gn_partial, _C.ptr(x2.t), N, S, C2, _C.ptr(p2))
+        R = self.slab.world if self.slab is not None else 1
+
+        def partial(x, Cx):
+            n = ops.gn_num_chunks(S, Cx)
+            p = ar.alloc((N, n, Cx, 2), torch.float32)
+            plan.add(lib.gg_gn_partial, x.ip, N, S, Cx, _C.ptr(p))
+            if R > 1:       # every rank needs the statistics of the whole volume: gather the partials
+                g = ar.alloc((N, R * n, Cx, 2), torch.float32)
+                plan.add_py(self.slab.all_gather, g, p)
+                ar.release(p)
+                return g, R * n
+            return p, n
+
+        p1, n1 = partial(x1, C1)
+        p2, n2 = partial(x2, C2) if x2 is not None else (None, 0)
         ss = ar.alloc((N, C1 + C2, 2), torch.float32)
         fa = _C.GnFinalizeArgs(_C.ptr(p1), C1, n1, _C.ptr(p2), C2, n2, _C.ptr(self._f32(norm.weight)),
-                               _C.ptr(self._f32(norm.bias)), _C.ptr(ss), N, norm.groups, S, float(norm.eps))
+                               _C.ptr(self._f32(norm.bias)), _C.ptr(ss), N, norm.groups, S * R, float(norm.eps))
         plan.keep.append(fa)
         plan.add(lib.gg_gn_finalize, C.byref(fa))
-        y = ar.alloc((N,) + x1.sp + (C1 + C2,), torch.bfloat16)
-        plan.add(lib.gg_gn_apply, _C.ptr(x1.t), C1, _C.ptr(x2.t if x2 is not None else None), C2, _C.ptr(ss), _C.ptr(y), N, S,
-                 int(silu))
+        y = self._new_act(ar, N, x1.sp, C1 + C2)
+        plan.add(lib.gg_gn_apply, x1.ip, C1, x2.ip if x2 is not None else 0, C2, _C.ptr(ss), y.ip, N, S, int(silu))
         ar.release(p1), ar.release(p2), ar.release(ss)
-        return Act(y)
+        return y
 
     def _conv(self, plan: Plan, ar: _Arena, srcs: List[Tuple[Act, bool]], w_packed: torch.Tensor, cout: int, *, dims: int,
               ksize: int = 3, stride: int = 1, bias=None, emb=None, emb_stride=0, residual: Optional[Act] = None,
-              f32_out: bool = False, taps=None, offsets=None, y: Optional[torch.Tensor] = None, y_strides=None,
-              out_spatial=None) -> Act:
+              f32_out: bool = False, taps=None, offsets=None, y_ptr: Optional[int] = None, y_strides=None,
+              out_spatial=None, out: Optional[Act] = None) -> Act:
         x0 = srcs[0][0]
         N, (D, H, W) = x0.N, x0.sp
         cout8 = (cout + 7) // 8 * 8
         if taps is None:
             taps = (ksize if dims >= 3 else 1, ksize if dims >= 2 else 1, ksize)
+        if offsets is None:
+            offsets = tuple(-(t // 2) for t in taps)
         if out_spatial is None:
             if stride == 1:
                 out_spatial = (D, H, W)
             else:
                 f = lambda n, on: (n - 1) // 2 + 1 if on else n
                 out_spatial = (f(D, dims >= 3), f(H, dims >= 2), f(W, True))
-        if y is None:
-            y = ar.alloc((N,) + tuple(out_spatial) + (cout8,), torch.float32 if f32_out else torch.bfloat16)
-        a = ops.make_conv_args([(s.t, c) for s, c in srcs], w_packed, cout, y, dims=dims, ksize=ksize, stride=stride,
-                               bias=bias, emb=None, residual=residual.t if residual is not None else None, taps=taps,
-                               offsets=offsets, out_spatial=out_spatial, y_strides=y_strides)
+        if out is None:
+            out = self._new_act(ar, N, out_spatial, cout8, torch.float32 if f32_out else torch.bfloat16)
+        lead = x0.lead
+        d_shift, kernel_out_sp, y_base = lead, tuple(out_spatial), (y_ptr if y_ptr is not None else out.ip)
+        if lead and taps[0] > 1:
+            for a, centre in srcs:
+                if not centre:
+                    self._exchange(plan, a, need_lo=True, need_hi=(stride == 1))
+        if lead and stride == 2 and dims >= 3:
+            # depth-slab stride 2: the padded buffer is [spare, halo_lo, interior...]; with the interior at
+            # padded index d + 2 the reference's  2o + k - 1  becomes  2(o+1) + k - 1  in padded indices, i.e.
+            # the ordinary strided conv over the WHOLE padded tensor whose output plane o' = o + 1.  Output
+            # plane o' = 0 is garbage and lands in the output's halo_lo plane (overwritten by its next exchange).
+            assert D % 2 == 0 and out.lead >= 1
+            d_shift = 0
+            kernel_out_sp = (out_spatial[0] + 1, out_spatial[1], out_spatial[2])
+            y_base = out.ip - out.plane_bytes
+        a = ops.make_conv_args([(s.t, c) for s, c in srcs], w_packed, cout, y_base, dims=dims, ksize=ksize, stride=stride,
+                               bias=bias, emb=None, residual=residual.ip if residual is not None else None, taps=taps,
+                               offsets=offsets, out_spatial=kernel_out_sp, y_strides=y_strides, d_shift=d_shift,
+                               y_f32=f32_out)
         if emb is not None:
             a.emb = emb
             a.emb_stride = emb_stride
@@ -205,7 +285,7 @@ class UNetEngine:
         plan.keep.append(a)
         plan.add(self.lib.gg_conv_fwd, C.byref(a))
         plan.flops += 2 * N * int(math.prod(out_spatial)) * cout * w_packed.shape[1]
-        return Act(y)
+        return out
 
     def _pack(self, conv: M.ParamConv, splits, extra=()):
         key = (id(conv.weight), tuple(splits), tuple(id(e) for e in extra))
@@ -259,23 +339,31 @@ class UNetEngine:
         N, S, Cc = x.N, x.S, x.C
         H = ab.num_heads
         d = Cc // H
+        R = self.slab.world if self.slab is not None else 1
         xn = self._gn(plan, ar, x, None, ab.norm, False)
         bq = self._vec8((id(ab.qkv.bias), "b"), lambda: ab.qkv.bias, 3 * Cc)
         qkv = self._conv(plan, ar, [(xn, False)], self._pack(ab.qkv, [Cc]), 3 * Cc, dims=3, ksize=1, bias=_C.ptr(bq))
         ar.release(xn.t)
-        o = ar.alloc((N,) + x.sp + (Cc,), torch.bfloat16)
-        base = qkv.t.data_ptr()
+        o = self._new_act(ar, N, x.sp, Cc)
         W3 = 3 * Cc
-        aa = _C.AttnArgs(base, base + d * 2, base + 2 * d * 2, _C.ptr(o), S * W3, S * W3, S * W3, S * Cc, W3, W3, W3, Cc,
-                         3 * d, 3 * d, 3 * d, d, N, H, S, S, d, 1.0 / math.sqrt(d))
+        qbase = kbase = qkv.ip
+        Tk = S
+        gathered = None
+        if R > 1:
+            # queries stay local, keys/values of the whole volume are gathered (slabs are contiguous in depth,
+            # tokens are ordered (d, h, w), so rank order == global token order)
+            gathered = ar.alloc((R * S, W3), torch.bfloat16)
+            plan.add_py(self.slab.all_gather, gathered, qkv.interior)
+            kbase, Tk = gathered.data_ptr(), R * S
+        aa = _C.AttnArgs(qbase, kbase + d * 2, kbase + 2 * d * 2, o.ip, S * W3, Tk * W3, Tk * W3, S * Cc, W3, W3, W3, Cc,
+                         3 * d, 3 * d, 3 * d, d, N, H, S, Tk, d, 1.0 / math.sqrt(d))
         plan.keep.append(aa)
         plan.add(self.lib.gg_attention_fwd, C.byref(aa))
-        plan.flops += 4 * N * H * S * S * d
-        ar.release(qkv.t)
+        plan.flops += 4 * N * H * S * Tk * d
+        ar.release(qkv.t), ar.release(gathered)
         bp = self._vec8((id(ab.proj_out.bias), "b"), lambda: ab.proj_out.bias, Cc)
-        out = self._conv(plan, ar, [(Act(o), False)], self._pack(ab.proj_out, [Cc]), Cc, dims=3, ksize=1, bias=_C.ptr(bp),
-                         residual=x)
-        ar.release(o)
+        out = self._conv(plan, ar, [(o, False)], self._pack(ab.proj_out, [Cc]), Cc, dims=3, ksize=1, bias=_C.ptr(bp), residual=x)
+        ar.release(o.t)
         return out
 
     def _linear(self, plan, ar, x: Act, lin_w: torch.Tensor, key, cout, bias_t=None, residual=None) -> Act:
@@ -294,7 +382,7 @@ class UNetEngine:
             w = self._cached((id(ca.to_q.weight), "qkv"),
                              lambda: torch.cat([ca.to_q.weight, ca.to_k.weight, ca.to_v.weight], 0).detach())
             qkv = self._linear(plan, ar, xq, w, (id(ca.to_q.weight), "qkvp"), 3 * inner)
-            base = qkv.t.data_ptr()
+            base = qkv.ip
             Tk, rs = Tq, 3 * inner
             qp, kp, vp = base, base + inner * 2, base + 2 * inner * 2
             q_str, k_str = (Tq * rs, rs, d), (Tk * rs, rs, d)
@@ -304,11 +392,11 @@ class UNetEngine:
             w = self._cached((id(ca.to_k.weight), "kv"), lambda: torch.cat([ca.to_k.weight, ca.to_v.weight], 0).detach())
             kv = self._linear(plan, ar, ctx, w, (id(ca.to_k.weight), "kvp"), 2 * inner)
             Tk = ctx.S
-            qp, kp, vp = q.t.data_ptr(), kv.t.data_ptr(), kv.t.data_ptr() + inner * 2
+            qp, kp, vp = q.ip, kv.ip, kv.ip + inner * 2
             q_str, k_str = (Tq * inner, inner, d), (Tk * 2 * inner, 2 * inner, d)
             bufs = [q.t, kv.t]
-        o = ar.alloc((N,) + xq.sp + (inner,), torch.bfloat16)
-        aa = _C.AttnArgs(qp, kp, vp, _C.ptr(o), q_str[0], k_str[0], k_str[0], Tq * inner, q_str[1], k_str[1], k_str[1], inner,
+        o = self._new_act(ar, N, xq.sp, inner)
+        aa = _C.AttnArgs(qp, kp, vp, o.ip, q_str[0], k_str[0], k_str[0], Tq * inner, q_str[1], k_str[1], k_str[1], inner,
                          d, d, d, d, N, H, Tq, Tk, d, float(ca.scale))
         plan.keep.append(aa)
         plan.add(self.lib.gg_attention_fwd, C.byref(aa))
@@ -316,17 +404,19 @@ class UNetEngine:
         for b in bufs:
             ar.release(b)
         lo = ca.to_out[0]
-        out = self._linear(plan, ar, Act(o), lo.weight, (id(lo.weight), "p"), lo.out_features, lo.bias, residual)
-        ar.release(o)
+        out = self._linear(plan, ar, o, lo.weight, (id(lo.weight), "p"), lo.out_features, lo.bias, residual)
+        ar.release(o.t)
         return out
 
     def _layernorm(self, plan, ar, x: Act, norm: M.ParamNorm) -> Act:
-        y = ar.alloc(tuple(x.t.shape), torch.bfloat16)
-        plan.add(self.lib.gg_layernorm, _C.ptr(x.t), _C.ptr(self._f32(norm.weight)), _C.ptr(self._f32(norm.bias)), _C.ptr(y),
+        y = self._new_act(ar, x.N, x.sp, x.C)
+        plan.add(self.lib.gg_layernorm, x.ip, _C.ptr(self._f32(norm.weight)), _C.ptr(self._f32(norm.bias)), y.ip,
                  x.N * x.S, x.C, float(norm.eps))
-        return Act(y)
+        return y
 
     def _spatial_transformer(self, plan, ar, st: M.SpatialTransformer, x: Act, ctx: Optional[Act]) -> Act:
+        if self.slab is not None:
+            raise NotImplementedError("depth-slab mode covers the shipped CCDM network (AttentionBlock), not SpatialTransformer")
         xn = self._gn(plan, ar, x, None, st.norm, False)
         pin = st.proj_in
         h = self._linear(plan, ar, xn, pin.weight.reshape(pin.out_channels, -1), (id(pin.weight), "p"), pin.out_channels, pin.bias)
@@ -343,12 +433,12 @@ class UNetEngine:
             f1 = self._linear(plan, ar, n3, gp.weight, (id(gp.weight), "p"), gp.out_features, gp.bias)
             ar.release(n3.t)
             inner = gp.out_features // 2
-            g = ar.alloc((h3.N,) + h3.sp + (inner,), torch.bfloat16)
-            plan.add(self.lib.gg_geglu, _C.ptr(f1.t), _C.ptr(g), h3.N * h3.S, inner)
+            g = self._new_act(ar, h3.N, h3.sp, inner)
+            plan.add(self.lib.gg_geglu, f1.ip, g.ip, h3.N * h3.S, inner)
             ar.release(f1.t)
             l2 = blk.ff.net[2]
-            h = self._linear(plan, ar, Act(g), l2.weight, (id(l2.weight), "p"), l2.out_features, l2.bias, h3)
-            ar.release(g), ar.release(h3.t)
+            h = self._linear(plan, ar, g, l2.weight, (id(l2.weight), "p"), l2.out_features, l2.bias, h3)
+            ar.release(g.t), ar.release(h3.t)
         po = st.proj_out
         out = self._linear(plan, ar, h, po.weight.reshape(po.out_channels, -1), (id(po.weight), "p"), po.out_channels, po.bias, x)
         ar.release(h.t)
@@ -363,26 +453,24 @@ class UNetEngine:
         dims = up.dims
         N, (D, H, W), Cc = x.N, x.sp, x.C
         fd, fh = (2 if dims >= 3 else 1), (2 if dims >= 2 else 1)
-        if not up.use_conv:
-            y = ar.alloc((N, D * fd, H * fh, W * 2, Cc), torch.bfloat16)
-            plan.add(self.lib.gg_upsample2x, _C.ptr(x.t), _C.ptr(y), N, D, H, W, Cc, dims)
-            return Act(y)
+        Do, Ho, Wo = D * fd, H * fh, W * 2
+        if not up.use_conv or not self.fused_upsample:
+            y = self._new_act(ar, N, (Do, Ho, Wo), Cc)
+            plan.add(self.lib.gg_upsample2x, x.ip, y.ip, N, D, H, W, Cc, dims)
+            if not up.use_conv:
+                return y
+            b = self._vec8((id(up.conv.bias), "b"), lambda: up.conv.bias, up.out_channels)
+            out = self._conv(plan, ar, [(y, False)], self._pack(up.conv, [Cc]), up.out_channels, dims=dims, bias=_C.ptr(b))
+            ar.release(y.t)
+            return out
         cout = up.out_channels
         b = self._vec8((id(up.conv.bias), "b"), lambda: up.conv.bias, cout)
-        if not self.fused_upsample:
-            y = ar.alloc((N, D * fd, H * fh, W * 2, Cc), torch.bfloat16)
-            plan.add(self.lib.gg_upsample2x, _C.ptr(x.t), _C.ptr(y), N, D, H, W, Cc, dims)
-            out = self._conv(plan, ar, [(Act(y), False)], self._pack(up.conv, [Cc]), cout, dims=dims, bias=_C.ptr(b))
-            ar.release(y)
-            return out
         # nearest-x2 upsample folded into the conv: for output parity class pi (per dim) the 3-tap
         # filter over the upsampled grid collapses to 2 taps over the coarse grid at offsets
         # {pi - 1, pi}; taps that hit the same coarse voxel have their weights summed (exact, done in
         # fp32 before the bf16 rounding).  27 -> 8 taps = 3.4x fewer MACs; the upsampled tensor is
         # never materialised.  Each class writes a stride-2 view of the output.
-        Do, Ho, Wo = D * fd, H * fh, W * 2
-        out = ar.alloc((N, Do, Ho, Wo, cout), torch.bfloat16)
-        es = 2
+        out = self._new_act(ar, N, (Do, Ho, Wo), cout)
         for pd in range(fd):
             for ph in range(fh):
                 for pw in range(2):
@@ -390,11 +478,11 @@ class UNetEngine:
                                       lambda: ops.pack_conv_weight(_fold_upsample_weight(up.conv.weight, dims, (pd, ph, pw)), [Cc]))
                     taps = (2 if dims >= 3 else 1, 2 if dims >= 2 else 1, 2)
                     offs = (pd - 1 if dims >= 3 else 0, ph - 1 if dims >= 2 else 0, pw - 1)
-                    yv = out[:, pd::fd, ph::fh, pw::2]
+                    yp = out.ip + ((pd * Ho + ph) * Wo + pw) * cout * 2
                     ystr = (Do * Ho * Wo * cout, fd * Ho * Wo * cout, fh * Wo * cout, 2 * cout)
-                    self._conv(plan, ar, [(x, False)], wp, cout, dims=dims, bias=_C.ptr(b), taps=taps, offsets=offs, y=yv,
-                               y_strides=ystr, out_spatial=(D, H, W))
-        return Act(out)
+                    self._conv(plan, ar, [(x, False)], wp, cout, dims=dims, bias=_C.ptr(b), taps=taps, offsets=offs, y_ptr=yp,
+                               y_strides=ystr, out_spatial=(D, H, W), out=out)
+        return out
 
     # -------------------------------------------------------------------------------- plan
     def build_plan(self, N: int, spatial: Tuple[int, ...], in_ch_pad: int, ctx_shape=None, f32_head: bool = True) -> Plan:
@@ -403,9 +491,13 @@ class UNetEngine:
         dev = self._dev()
         plan, ar = Plan(), _Arena(dev)
         sp3 = (1,) * (3 - len(spatial)) + tuple(spatial)
-        x_in = torch.zeros((N,) + sp3 + (in_ch_pad,), dtype=torch.bfloat16, device=dev)
+        lead, trail = self._lead, self._trail
+        x_full = torch.zeros((N, sp3[0] + lead + trail) + sp3[1:] + (in_ch_pad,), dtype=torch.bfloat16, device=dev)
+        x_act = Act(x_full, lead, trail)
+        x_in = x_act.interior                       # contiguous: lead > 0 only with N == 1
         t_in = torch.zeros((N,), dtype=torch.float32, device=dev)
         plan.inputs["x"], plan.inputs["t"] = x_in, t_in
+        plan.keep.append(x_full)
         ctx = None
         if ctx_shape is not None:
             L, cd = ctx_shape
@@ -462,6 +554,7 @@ class UNetEngine:
                     new = self._upsample(plan, ar, layer, h)
                 elif isinstance(layer, M.ParamConv):
                     b = self._vec8((id(layer.bias), "b"), lambda: layer.bias, layer.out_channels)
+                    h.halo_valid = False           # the sampler rewrites the input between forwards
                     new = self._conv(plan, ar, [(h, False)], self._pack(layer, [h.C]), layer.out_channels, dims=layer.dims,
                                      bias=_C.ptr(b))
                 else:
@@ -474,9 +567,9 @@ class UNetEngine:
             return h
 
         hs: List[Act] = []
-        h = Act(x_in)
+        h = x_act
         for block in m.input_blocks:
-            h = run_block(block, h, None, hs + [Act(x_in)])
+            h = run_block(block, h, None, hs + [x_act])
             hs.append(h)
         h = run_block(m.middle_block, h, None, hs)
         for block in m.output_blocks:
@@ -490,7 +583,7 @@ class UNetEngine:
         head = self._conv(plan, ar, [(a, False)], self._pack(oc, [a.C]), oc.out_channels, dims=oc.dims, bias=_C.ptr(b),
                           f32_out=f32_head)
         ar.release(a.t)
-        plan.outputs["head"] = head.t
+        plan.outputs["head"] = head.interior
         plan.keep.extend([emb_all, emb, e1, temb])
         plan.keep.append(ar.stores)      # kernels hold raw pointers into these: they must outlive the plan
         plan.arena_bytes = ar.total

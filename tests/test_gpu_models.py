@@ -284,3 +284,20 @@ def test_no_fallback_when_library_missing(monkeypatch):
     monkeypatch.setattr(_C, "LIB_PATH", "/nonexistent/libguidegen_sm100.so")
     with pytest.raises(_C.GuideGenLibraryError):
         _C.lib()
+
+
+def test_slab_layout_single_rank_equals_plain_plan():
+    """Depth-slab mode with world == 1 (halo-padded activations, d_shift reads, the stride-2 and
+    folded-upsample index tricks, zero halos) must reproduce the plain plan bit for bit."""
+    from jointimagegeneration_b200.sharding import SlabComm
+    from oracle import configs, weights
+    for params, C, spatial in ((configs.CCDM_TINY, 4, (8, 8, 8)), (configs.CCDM_PARAMS_YML, 12, (16, 32, 16))):
+        m, _ = _ccdm(params, 10, C, spatial, 5)
+        x = weights.uniform_one_hot(3, 1, C, spatial).cuda()
+        cond = torch.zeros(1, 1, *spatial).cuda()
+        t = torch.full((1,), 7.0).cuda()
+        ref = m.unet(x, cond, None, t)["diffusion_out"].clone()
+        m.unet.enable_slab(SlabComm())
+        got = m.unet(x, cond, None, t)["diffusion_out"]
+        assert torch.equal(ref, got), float((ref - got).abs().max())
+        m.unet.enable_slab(None)
