@@ -35,6 +35,9 @@ WORKLOADS = {
                       desc="CCDM mask sampler 128x128x64 (tensor [8,12,64,128,128]), 12 classes, 1000-step chain, batch 8, bf16"),
     "ccdm_cfg1": dict(spatial=(32, 32, 32), C=12, batch=1, T=10, flop_per_sample=1.97e11,
                       desc="CCDM mask sampler 32x32x32, 12 classes, 10 steps, batch 1"),
+    "ccdm_cfg5": dict(spatial=(128, 256, 256), C=12, batch=1, T=1000, flop_per_sample=5.182e13, attn_flop=1.41e12, slab=True,
+                      desc="CCDM mask sampler, ONE 256x256x128 volume (tensor [1,12,128,256,256]) split into depth slabs over the "
+                           "GPUs: halo exchange per 3x3x3 conv, GroupNorm partial-sum gather, attention K/V gather (NCCL)"),
     "ldm_cfg3": dict(spatial=(64, 64), C=4, batch=16, T=50, flop_per_sample=1.24e11, kind="ldm",
                      desc="LDM conditional CT slice generator (ruijin-ldm_from_controlnet_ae.yaml UNet), latent 4x64x64, "
                           "concat mask/prev-slice context, DDIM 50 steps eta 0, batch 16, bf16"),
@@ -88,6 +91,21 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
 
 
+def build_and_seed_like(module, seed):
+    """Deterministic state_dict (same on every rank) for replicated-weight multi-rank runs."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in module.state_dict().items():
+        if v.ndim >= 2:
+            out[k] = (torch.randn(v.shape, generator=g) / v[0].numel() ** 0.5).to(v.device)
+        elif k.endswith("weight"):
+            out[k] = (1.0 + 0.1 * torch.randn(v.shape, generator=g)).to(v.device)
+        else:
+            out[k] = (0.05 * torch.randn(v.shape, generator=g)).to(v.device)
+    return out
+
+
 def randomize_zero_modules(model, seed):
     """The reference zero-initialises the last conv of every ResBlock, every attention proj_out and the
     output conv: a random-init network would return a constant.  Re-draw those."""
@@ -123,6 +141,11 @@ def run_ours(args):
     _C.check(_C.lib().gg_device_check(), "gg_device_check")
     K, W = args.steps, max(args.warmup, 3)
     B, Cc, sp, T = args.batch or wl["batch"], wl["C"], wl["spatial"], wl["T"]
+    slab = bool(wl.get("slab"))
+    full_sp = sp
+    if slab:
+        assert sp[0] % (16 * world) == 0, "depth must split into slabs that are multiples of 16 planes"
+        sp = (sp[0] // world, sp[1], sp[2])
     V = sp[0] * sp[1] * sp[2]
 
     torch.manual_seed(1234 + rank)
@@ -131,6 +154,16 @@ def run_ours(args):
     randomize_zero_modules(model.unet, 7)
     model = model.to(dev).eval()
     model.loop, model.use_cuda_graph, model.philox_seed = "resident", True, 99 + rank
+    comm = None
+    if slab:
+        torch.manual_seed(1234)                       # every rank holds the same weights
+        model.unet.load_state_dict({k: v for k, v in build_and_seed_like(model.unet, 1234).items()})
+        model.philox_seed = 99
+        if world > 1:
+            from jointimagegeneration_b200.sharding import SlabComm
+            comm = SlabComm()
+            model.unet.enable_slab(comm)
+            model.use_cuda_graph = False              # collectives between kernels: eager launches
 
     # ---- synthetic inputs, resident in HBM before the timed region
     lab0 = torch.randint(0, Cc, (B,) + sp, device=dev)
@@ -164,7 +197,7 @@ def run_ours(args):
         tmax = torch.tensor([ms], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax.item())
-    value = world * K / (ms / 1e3)
+    value = (1 if slab else world) * K / (ms / 1e3)
     launches_per_step = plan.num_launches + 1                                   # UNet plan + fused per-voxel kernel
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -184,24 +217,29 @@ def run_ours(args):
         tm = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e_s = float(tm.item())
-    e2e = {"value": world * Ke / e2e_s, "unit": "steps/s", "steps": Ke,
+    e2e = {"value": (1 if slab else world) * Ke / e2e_s, "unit": "steps/s", "steps": Ke,
            "h2d_bytes_per_step": (x_host.numel() * 4 + c_host.numel() * 4) // Ke,
            "d2h_bytes_per_step": out_host.numel() * 8 // Ke,
            "call": "DenoisingModel.forward(x_host, condition_host, t=10000+K) -> int64 one-hot on host (loop='resident', CUDA graph)"}
 
     line = {"metric": "denoising steps/sec", "value": value, "unit": "steps/s (1 step = UNet forward + categorical posterior/draw for a batch of %d volumes)" % B,
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if slab else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, "global_batch": B * world, "batch_per_gpu": B,
-                       "volume": list(sp), "classes": Cc, "network": "ccdm/params.yml unet_openai (95.4 M params), random init, zero-init modules re-randomised",
+            "config": {"workload": wl["desc"], "name": args.workload, "global_batch": B if slab else B * world, "batch_per_gpu": B,
+                       "volume": list(full_sp), "local_volume": list(sp), "classes": Cc, "network": "ccdm/params.yml unet_openai (95.4 M params), random init, zero-init modules re-randomised",
                        "text_conditioning": "off -- the reference cannot construct its text-conditioned CCDM (SURVEY.md D1/D2); --text enables ours",
-                       "parallelism": "independent chains sharded over ranks (dp%d), no per-step collective" % world,
+                       "parallelism": ("one volume in %d depth slabs: halo exchange / GN gather / KV gather over NCCL" % world) if slab
+                       else "independent chains sharded over ranks (dp%d), no per-step collective" % world,
                        "l2": "inputs larger than L2 (activations are GBs per step); no explicit flush",
-                       "rng": "in-kernel Philox", "cuda_graph": True},
+                       "rng": "in-kernel Philox", "cuda_graph": bool(model.use_cuda_graph)},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches_per_step * K,
             "volumes_per_sec": value * B / T}
+    if comm is not None:
+        nf = W + K + Ke + 1
+        line["comm"] = {"halo_exchanges_per_forward": comm.n_exchanges / nf, "gathers_per_forward": comm.n_gathers / nf,
+                        "halo_bytes_sent_per_forward": comm.bytes_sent / nf}
 
-    if rank == 0:
+    if rank == 0 or comm is not None:      # slab mode: the instrumented pass contains collectives -> every rank runs it
         peaks = load_peaks()
         # ---- instrumented pass: CUDA-event time of every launch of one step (eager, same stream)
         kinds = {}
@@ -213,7 +251,10 @@ def run_ours(args):
             for fn, fargs in plan.steps:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                _C.check(fn(*fargs, s), fn.__name__)
+                if hasattr(fn, "fn"):
+                    fn.fn(*fargs)                                   # collective / halo exchange (host-side step)
+                else:
+                    _C.check(fn(*fargs, s), fn.__name__)
                 b.record()
                 evs.append((fn.__name__, a, b))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -247,14 +288,15 @@ def run_ours(args):
         kernel_ms = {k: round(v[0], 4) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
         n_conv = kinds["gg_conv_fwd"][1] // reps
         conv_ms = kinds["gg_conv_fwd"][0]
-        attn_flops = 0.022e12 / 6.324e12 * wl["flop_per_sample"]
-        conv_alg = (wl["flop_per_sample"] - attn_flops) * B
+        share = (1.0 / world) if slab else 1.0                          # FLOPs this rank executes
+        attn_flops = wl.get("attn_flop", 0.022e12 / 6.324e12 * wl["flop_per_sample"])
+        conv_alg = (wl["flop_per_sample"] - attn_flops) * B * share
         ach = conv_alg / (conv_ms / 1e3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "conv_tcgen05_kernel (all %d launches of one step)" % n_conv,
                             "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
                             "traffic": None, "algorithmic_flop": conv_alg, "issued_flop": plan.flops, "avg_launch_ms": conv_ms / n_conv,
                             "peak_source": peaks["source"] + " (bf16 sustained: kernel timed inside a long step)",
-                            "whole_step_frac": wl["flop_per_sample"] * B / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
+                            "whole_step_frac": wl["flop_per_sample"] * B * share / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
         cat_ms = kinds["gg_cat_step_cl"][0]
         alg_b = 50.0 * B * V
         act_b = (64 + 1 + 1 + 2 * plan.inputs["x"].shape[-1] + 2) * B * V
@@ -287,7 +329,8 @@ def run_ours(args):
         line["arena_bytes"] = plan.arena_bytes
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(args, wl, budget_s=20.0)
-        print(json.dumps(line), flush=True)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -406,7 +449,7 @@ def run_ours_ldm(args):
                             "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": None,
                             "algorithmic_flop": wl["flop_per_sample"] * B, "issued_flop": plan.flops,
                             "peak_source": peaks["source"] + " (bf16 sustained)",
-                            "whole_step_frac": wl["flop_per_sample"] * B / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
+                            "whole_step_frac": wl["flop_per_sample"] * B * share / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
         line["kernel_ms"] = {k: round(v[0], 4) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -514,6 +557,9 @@ def run_reference(args):
 
 
 def main():
+    # NCCL prints its version banner on STDOUT when NCCL_DEBUG asks for it; stdout must carry ONE JSON line
+    if not os.environ.get("BENCH_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
