@@ -130,6 +130,25 @@ typedef struct {
 
 int gg_ddim_update(const gg_ddim_args* a, gg_stream_t stream);
 
+/* Ancestral DDPM update   latentdiffusion/ldm/models/diffusion/ddpm.py:1060-1120 (p_mean_variance, p_sample),
+ * :215-230 (predict_start_from_noise, q_posterior); used by sample_diffusion.py --vanilla_sample.
+ * coef fp32 [B, 6] = (sqrt_recip_acp[t], sqrt_recipm1_acp[t], posterior_mean_coef1[t], posterior_mean_coef2[t],
+ * posterior_log_variance_clipped[t], nonzero_mask) per sample. */
+typedef struct {
+    const float* x;
+    const float* e_t;
+    const float* noise;     /* NULL: no noise term */
+    const float* coef;      /* [B, 6] device */
+    float* x_prev;
+    float* x0_out;          /* optional predicted x0 (after clipping) */
+    int32_t B;
+    int64_t per_sample;     /* elements per sample */
+    float temperature;
+    int32_t clip_denoised;
+} gg_ddpm_args;
+
+int gg_ddpm_update(const gg_ddpm_args* a, gg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Layout bridges at the drop-in boundary (fp32 NC* <-> CL bf16)
  *   unet.py:775 th.cat([x, input_condition], 1); ddpm.py:1419 torch.cat([x] + c_concat, 1)

@@ -53,6 +53,12 @@ class DdimArgs(C.Structure):
                 ("e_uncond", C.c_void_p), ("guidance_scale", C.c_float)]
 
 
+class DdpmArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("e_t", C.c_void_p), ("noise", C.c_void_p), ("coef", C.c_void_p),
+                ("x_prev", C.c_void_p), ("x0_out", C.c_void_p), ("B", C.c_int32), ("per_sample", C.c_int64),
+                ("temperature", C.c_float), ("clip_denoised", C.c_int32)]
+
+
 class GnFinalizeArgs(C.Structure):
     _fields_ = [("partial1", C.c_void_p), ("C1", C.c_int32), ("nchunks1", C.c_int32),
                 ("partial2", C.c_void_p), ("C2", C.c_int32), ("nchunks2", C.c_int32),
@@ -96,6 +102,7 @@ SYMBOLS = {
     "gg_cat_posterior_sample": (C.c_int, [C.POINTER(CatArgs), _vp]),
     "gg_cat_step_cl": (C.c_int, [C.POINTER(CatStepCLArgs), _vp]),
     "gg_ddim_update": (C.c_int, [C.POINTER(DdimArgs), _vp]),
+    "gg_ddpm_update": (C.c_int, [C.POINTER(DdpmArgs), _vp]),
     "gg_nchw_to_cl": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i64, _vp]),
     "gg_cl_to_nchw": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i32, _vp]),
     "gg_gn_num_chunks": (_i32, [_i64, _i32]),

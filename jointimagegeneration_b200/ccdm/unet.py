@@ -100,6 +100,8 @@ class UNetModel(nn.Module):
 
     def plan_for(self, N, spatial, context=None):
         uses_ctx = any(isinstance(mm, M.SpatialTransformer) for mm in self.modules())
+        if uses_ctx and context is not None and context.shape[-1] != self.context_dim and context.shape[1] == self.context_dim:
+            context = context.transpose(1, 2)          # dataset layout 'c l' 
         ctx_shape = (context.shape[-2], context.shape[-1]) if (uses_ctx and context is not None) else None
         return self.engine.get_plan(N, tuple(spatial), self.in_channels_padded, ctx_shape)
 

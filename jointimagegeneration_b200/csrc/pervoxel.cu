@@ -438,6 +438,28 @@ __global__ void __launch_bounds__(256) ddim_kernel(const gg_ddim_args a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// ancestral DDPM update (ldm/models/diffusion/ddpm.py:1060-1120 p_mean_variance + p_sample)
+//   x0 = sr x - srm1 e ; clip ; mean = c1 x0 + c2 x ; x_prev = mean + nz * exp(0.5 logvar) * (noise * T)
+// coef[b] = (sr, srm1, c1, c2, logvar, nz) gathered per sample by the host wrapper
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ddpm_kernel(const gg_ddpm_args a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.per_sample) return;
+    const int b = blockIdx.y;
+    const float* co = a.coef + 6 * b;
+    const float sr = __ldg(co), srm1 = __ldg(co + 1), c1 = __ldg(co + 2), c2 = __ldg(co + 3), lv = __ldg(co + 4), nz = __ldg(co + 5);
+    const float sd = __fmul_rn(nz, expf(__fmul_rn(0.5f, lv)));
+    const int64_t j = (int64_t)b * a.per_sample + i;
+    const float x = a.x[j], e = a.e_t[j];
+    float x0 = __fsub_rn(__fmul_rn(sr, x), __fmul_rn(srm1, e));
+    if (a.clip_denoised) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
+    const float n = a.noise ? __fmul_rn(a.noise[j], a.temperature) : 0.f;
+    a.x_prev[j] = __fadd_rn(mean, __fmul_rn(sd, n));
+    if (a.x0_out) a.x0_out[j] = x0;
+}
+
+// ------------------------------------------------------------------------------------------
 // layout bridges
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_cl_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
@@ -540,6 +562,14 @@ extern "C" int gg_ddim_update(const gg_ddim_args* a, gg_stream_t stream) {
         const unsigned blocks = (unsigned)((a->n + 255) / 256);
         ddim_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(*a);
     }
+    return launch_result();
+}
+
+extern "C" int gg_ddpm_update(const gg_ddpm_args* a, gg_stream_t stream) {
+    GG_REQUIRE(a != nullptr && a->x && a->e_t && a->coef && a->x_prev && a->B > 0 && a->per_sample > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->B <= 65535, GG_ERR_UNSUPPORTED);
+    const dim3 grid((unsigned)((a->per_sample + 255) / 256), (unsigned)a->B);
+    ddpm_kernel<<<grid, 256, 0, as_stream(stream)>>>(*a);
     return launch_result();
 }
 

@@ -16,7 +16,8 @@ import numpy as np
 import torch
 from torch import nn
 
-from .util import make_beta_schedule
+from .. import ops
+from .util import make_beta_schedule, noise_like
 
 
 class DiffusionWrapper(nn.Module):
@@ -78,6 +79,49 @@ class LatentDiffusion(nn.Module):
         self.register_buffer("log_one_minus_alphas_cumprod", f32(np.log(1. - acp)))
         self.register_buffer("sqrt_recip_alphas_cumprod", f32(np.sqrt(1. / acp)))
         self.register_buffer("sqrt_recipm1_alphas_cumprod", f32(np.sqrt(1. / acp - 1)))
+        # posterior q(x_{t-1} | x_t, x_0)   (ddpm.py:153-163)
+        post_var = (1 - self.v_posterior) * betas * (1. - acp_prev) / (1. - acp) + self.v_posterior * betas
+        self.register_buffer("posterior_variance", f32(post_var))
+        self.register_buffer("posterior_log_variance_clipped", f32(np.log(np.maximum(post_var, 1e-20))))
+        self.register_buffer("posterior_mean_coef1", f32(betas * np.sqrt(acp_prev) / (1. - acp)))
+        self.register_buffer("posterior_mean_coef2", f32((1. - acp_prev) * np.sqrt(alphas) / (1. - acp)))
+
+    @torch.no_grad()
+    def p_sample(self, x, c, t, clip_denoised=False, repeat_noise=False, return_codebook_ids=False, quantize_denoised=False,
+                 return_x0=False, temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None):
+        """ddpm.py:1091-1120 (+ p_mean_variance :1060-1088): the elementwise tail is one fused kernel."""
+        if return_codebook_ids or quantize_denoised or score_corrector is not None or noise_dropout > 0. or self.parameterization != "eps":
+            raise NotImplementedError("branch not taken by sample_diffusion.py --vanilla_sample")
+        e_t = self.apply_model(x, t, c)
+        tt = t.long()
+        coef = torch.stack([self.sqrt_recip_alphas_cumprod[tt], self.sqrt_recipm1_alphas_cumprod[tt], self.posterior_mean_coef1[tt],
+                            self.posterior_mean_coef2[tt], self.posterior_log_variance_clipped[tt], (tt != 0).float()], 1).contiguous()
+        noise = noise_like(x.shape, x.device, repeat_noise)
+        x_prev, x0 = ops.ddpm_update(x.float().contiguous(), e_t, coef, noise, temperature, clip_denoised, want_x0=return_x0)
+        return (x_prev, x0) if return_x0 else x_prev
+
+    @torch.no_grad()
+    def p_sample_loop(self, cond, shape, return_intermediates=False, x_T=None, verbose=False, callback=None, timesteps=None,
+                      quantize_denoised=False, mask=None, x0=None, img_callback=None, start_T=None, log_every_t=None):
+        """ddpm.py:1178-1227 (no inpainting mask / shortened conditioning schedules)."""
+        if mask is not None:
+            raise NotImplementedError("inpainting mask blend is not used by sample_diffusion.py")
+        b = shape[0]
+        img = torch.randn(shape, device=self.device) if x_T is None else x_T
+        timesteps = self.num_timesteps if timesteps is None else timesteps
+        if start_T is not None:
+            timesteps = min(timesteps, start_T)
+        inter = [img]
+        for i in reversed(range(0, timesteps)):
+            ts = torch.full((b,), i, device=self.device, dtype=torch.long)
+            img = self.p_sample(img, cond, ts, clip_denoised=getattr(self, "clip_denoised", False), quantize_denoised=quantize_denoised)
+            if log_every_t and (i % log_every_t == 0 or i == timesteps - 1):
+                inter.append(img)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(img, i)
+        return (img, inter) if return_intermediates else img
 
     @property
     def device(self):

@@ -81,6 +81,20 @@ def ddim_update(x, e_t, coef, noise=None, temperature=1.0, want_pred_x0=True, x_
     return x_prev, pred_x0
 
 
+def ddpm_update(x, e_t, coef, noise=None, temperature=1.0, clip_denoised=False, want_x0=False):
+    """Ancestral DDPM step (ddpm.py:1060-1120).  coef: device fp32 [B, 6]."""
+    _chk(x, torch.float32), _chk(e_t, torch.float32), _chk(coef, torch.float32)
+    if noise is not None:
+        _chk(noise, torch.float32)
+    B = x.shape[0]
+    x_prev = torch.empty_like(x)
+    x0 = torch.empty_like(x) if want_x0 else None
+    a = _C.DdpmArgs(_C.ptr(x), _C.ptr(e_t), _C.ptr(noise), _C.ptr(coef), _C.ptr(x_prev), _C.ptr(x0), B, x[0].numel(),
+                    float(temperature), int(clip_denoised))
+    _C.check(_C.lib().gg_ddpm_update(C.byref(a), _C.stream()), "gg_ddpm_update")
+    return x_prev, x0
+
+
 def nchw_to_cl(x1, x2=None, c_pad=None, out=None):
     """fp32 [N, C1, *sp] (+ [N, C2, *sp]) -> CL bf16 [N, *sp3, Cpad] with zero-filled padding."""
     _chk(x1, torch.float32)

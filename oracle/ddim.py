@@ -95,3 +95,28 @@ def ddim_sample(eps_fn: Callable[[Tensor, Tensor], Tensor], acp_f32: np.ndarray,
         if record is not None:
             record.append((img.clone(), torch.from_numpy(pred_x0)))
     return img
+
+
+def ddpm_tables(betas: np.ndarray):
+    """ddpm.py:118-163 -> dict of f32 arrays used by the ancestral sampler."""
+    alphas = 1.0 - betas
+    acp = np.cumprod(alphas, axis=0)
+    acp_prev = np.append(1.0, acp[:-1])
+    post_var = betas * (1.0 - acp_prev) / (1.0 - acp)
+    return {"sqrt_recip": np.sqrt(1.0 / acp).astype(f32), "sqrt_recipm1": np.sqrt(1.0 / acp - 1).astype(f32),
+            "coef1": (betas * np.sqrt(acp_prev) / (1.0 - acp)).astype(f32),
+            "coef2": ((1.0 - acp_prev) * np.sqrt(alphas) / (1.0 - acp)).astype(f32),
+            "logvar": np.log(np.maximum(post_var, 1e-20)).astype(f32)}
+
+
+def ddpm_update(x, e_t, tab, t: int, noise, temperature=1.0, clip=False):
+    """ddpm.py:215-230,1060-1120 for one timestep index t (0-based), float32 op by op."""
+    x, e = x.astype(f32), e_t.astype(f32)
+    x0 = ((tab["sqrt_recip"][t] * x).astype(f32) - (tab["sqrt_recipm1"][t] * e).astype(f32)).astype(f32)
+    if clip:
+        x0 = np.clip(x0, f32(-1), f32(1))
+    mean = ((tab["coef1"][t] * x0).astype(f32) + (tab["coef2"][t] * x).astype(f32)).astype(f32)
+    nz = f32(0.0 if t == 0 else 1.0)
+    sd = f32(nz * np.exp(f32(0.5) * tab["logvar"][t], dtype=f32))
+    n = (noise.astype(f32) * f32(temperature)).astype(f32)
+    return (mean + (sd * n).astype(f32)).astype(f32), x0

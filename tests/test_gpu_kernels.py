@@ -172,6 +172,24 @@ def test_ddim_update_bit_exact(ops, shape, eta):
             assert np.array_equal(got2.cpu().numpy(), want_prev)
 
 
+def test_ddpm_ancestral_update(ops):
+    """x0 and the mean are bit-exact; the exp(0.5 logvar) factor differs from numpy's by <= 1 ulp."""
+    from oracle import configs, ddim
+    betas = ddim.make_beta_schedule_linear(1000, configs.LDM_SCHEDULE["linear_start"], configs.LDM_SCHEDULE["linear_end"])
+    tab = ddim.ddpm_tables(betas)
+    rs = np.random.RandomState(12)
+    shape = (3, 4, 8, 8)
+    x, e, nz = (rs.standard_normal(shape).astype(np.float32) for _ in range(3))
+    for t in (999, 500, 1, 0):
+        coef = torch.tensor([[tab["sqrt_recip"][t], tab["sqrt_recipm1"][t], tab["coef1"][t], tab["coef2"][t], tab["logvar"][t],
+                              0.0 if t == 0 else 1.0]] * 3, dtype=torch.float32).cuda()
+        for clip in (False, True):
+            want, want0 = ddim.ddpm_update(x, e, tab, t, nz, 1.0, clip)
+            got, got0 = ops.ddpm_update(dev(x), dev(e), coef, dev(nz), 1.0, clip, want_x0=True)
+            assert np.array_equal(got0.cpu().numpy(), want0)
+            assert np.abs(got.cpu().numpy() - want).max() <= 1e-6 * max(1.0, np.abs(want).max())
+
+
 # --------------------------------------------------------------------------- layout bridges
 def test_layout_bridges(ops):
     rs = np.random.RandomState(0)
