@@ -233,10 +233,25 @@ typedef struct {
     int32_t Cout;
     int32_t block_n;                  /* 0 = gg_conv_pick_block_n(Cout); else multiple of 16 <= 256  */
     int32_t brick[4];                 /* 0s = auto; else (bn, bd, bh, bw) with product 128           */
+    /* Fused GroupNorm statistics (nn.py:17-19 on the conv's OUTPUT): when gn_partial != NULL the epilogue also
+     * writes per-channel (sum, sum of squares) of the stored (bf16-rounded) outputs, one row per (M tile, epilogue
+     * warp): fp32 [N, gn_nchunks_total, Cout8, 2], rows [gn_chunk_base, gn_chunk_base + gg_conv_stats_chunks()).
+     * Same layout gg_gn_partial produces, so gg_gn_finalize consumes it directly.  Output planes d < stats_d_min
+     * are excluded (halo plane of a depth-slab strided conv).  Unsupported (status -2) when an M tile spans
+     * samples, i.e. when gg_conv_stats_chunks() returns 0. */
+    float* gn_partial;
+    int32_t gn_chunk_base, gn_nchunks_total, stats_d_min;
+    /* 0: one A tile per (tap, chunk) (any stride / shape).  1: "halo brick" kernel for stride-1 filters: the
+     * 16 x 8 output brick's input window is loaded ONCE per 64-channel chunk and every tap reads it in place
+     * (shifted UMMA descriptors) -- 6x fewer A-operand bytes through shared memory.  Packed-weight K order for
+     * algo 1 is  source -> 64-channel chunk -> tap -> channel. */
+    int32_t algo;
 } gg_conv_args;
 
 /* N tile (accumulator columns) the kernel uses for a given Cout */
 int32_t gg_conv_pick_block_n(int32_t Cout);
+/* rows of gn_partial one launch of `a` fills per sample (4 per M tile), 0 if fused statistics are unsupported */
+int32_t gg_conv_stats_chunks(const gg_conv_args* a);
 /* K extent (columns) of the packed weight matrix for the sources / taps in `a` */
 int64_t gg_conv_packed_k(const gg_conv_args* a);
 int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream);

@@ -79,7 +79,9 @@ class ConvArgs(C.Structure):
                 ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("emb", C.c_void_p), ("emb_stride", C.c_int32),
                 ("residual", C.c_void_p), ("res_stride", C.c_int32), ("y", C.c_void_p),
                 ("y_sn", C.c_int64), ("y_sd", C.c_int64), ("y_sh", C.c_int64), ("y_sw", C.c_int64),
-                ("y_is_f32", C.c_int32), ("Cout", C.c_int32), ("block_n", C.c_int32), ("brick", C.c_int32 * 4)]
+                ("y_is_f32", C.c_int32), ("Cout", C.c_int32), ("block_n", C.c_int32), ("brick", C.c_int32 * 4),
+                ("gn_partial", C.c_void_p), ("gn_chunk_base", C.c_int32), ("gn_nchunks_total", C.c_int32),
+                ("stats_d_min", C.c_int32), ("algo", C.c_int32)]
 
 
 class AttnArgs(C.Structure):
@@ -111,6 +113,7 @@ SYMBOLS = {
     "gg_gn_apply": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i64, _i32, _vp]),
     "gg_conv_pick_block_n": (_i32, [_i32]),
     "gg_conv_packed_k": (_i64, [C.POINTER(ConvArgs)]),
+    "gg_conv_stats_chunks": (_i32, [C.POINTER(ConvArgs)]),
     "gg_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "gg_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "gg_attention_fwd": (C.c_int, [C.POINTER(AttnArgs), _vp]),

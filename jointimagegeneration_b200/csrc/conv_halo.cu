@@ -1,0 +1,405 @@
+// conv_halo.cu -- stride-1 convolution with the input brick (plus halo) resident in shared memory
+//
+// conv_tcgen05.cu reloads the 128-position A tile from L2 for every filter tap.  On B200 that kernel is
+// bound by shared-memory bandwidth (TMA writes + UMMA operand reads ~ 125 B/clk/SM measured), and for the
+// full-resolution Cout = 64 layers two thirds of that traffic is the A operand.  Here ONE TMA box brings
+// the 16 x 8 output brick's input window (18 x 10 positions per depth tap plane for a 3^3 filter, 64
+// channels = 128-byte rows, SWIZZLE_128B) and all kd*kh*kw taps read it in place: tcgen05.mma applies
+// the 128-byte swizzle to the ABSOLUTE shared-memory address (probed on B200: tools/umma_probe.cu),
+// so a descriptor whose start address is shifted by (tap offset) rows and whose 8-row group stride is
+// the halo pitch (10 rows = 1280 B) addresses exactly the rows TMA wrote.  A-operand smem writes drop
+// from 16 KB to ~2.6 KB per tap.
+//
+// The MMA-issuing thread needs ~430 clk per loop iteration (mbarrier wait, election, descriptors, commit),
+// more than the tensor time of four N <= 128 MMAs, so one B stage carries the weights of a whole kw row of
+// taps (3 taps = 12 MMAs per iteration) whenever shared memory allows.
+//
+// The A ring holds depth planes of the halo window (18 x 10 rows = 23 KB each, used by the kh*kw taps of one
+// depth tap), three planes deep, so the next chunk's planes stream in while the current ones are consumed.
+//
+// Roles (224 threads): warp 0 = A (halo) producer, warp 1 = MMA issuer, warps 2..5 = epilogue,
+// warp 6 = B (weight) producer.  K order of the packed weights: source -> 64-channel chunk -> tap.
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace gg {
+
+constexpr int H_BH = 16, H_BW = 8;            // output brick (one depth plane): 16 x 8 = 128 positions
+constexpr int H_MAX_SEGS = 4;
+constexpr int H_THREADS = 224;
+constexpr int H_SMEM_BUDGET = 227 * 1024;
+constexpr int H_ACC_COLS = 256;
+constexpr int H_MAX_SB = 8;
+constexpr int H_MAX_SA = 4;
+
+struct HaloSeg {
+    int nchunks;
+    int kd, kh, kw;        // taps
+    int od, oh, ow;        // input offset of tap 0
+    int dshift;
+    int pitch;             // bw + kw - 1 rows between consecutive h lines of the halo brick
+    int plane;             // (bh + kh - 1) * pitch rows between depth planes
+    uint32_t a_bytes;      // bytes of ONE depth plane of the halo window (= one A stage load)
+    int g;                 // taps (along kw) whose weights share one B stage: kw or 1
+};
+
+struct alignas(64) HaloParams {
+    CUtensorMap amap[H_MAX_SEGS];
+    CUtensorMap wmap;
+    HaloSeg seg[H_MAX_SEGS];
+    int nseg, BN, SA, SB;
+    uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes;
+    int No, Do, Ho, Wo;
+    int th, tw;                    // tiles along h, w (d and n are 1 per tile)
+    int n_tiles_n, total_tiles;
+    int Cout8;
+    const float* bias;
+    const float* emb;
+    int emb_stride;
+    const __nv_bfloat16* residual;
+    int res_stride;
+    void* y;
+    long long y_sn, y_sd, y_sh, y_sw;
+    int y_is_f32;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int G>
+__global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const int SA = p.SA, SB = p.SB, BN = p.BN;
+    uint8_t* smem_b = smem + (size_t)SA * p.a_stage_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)SB * p.b_stage_bytes);
+    uint64_t* a_empty = a_full + H_MAX_SA;
+    uint64_t* b_full = a_empty + H_MAX_SA;
+    uint64_t* b_empty = b_full + H_MAX_SB;
+    uint64_t* tfull = b_empty + H_MAX_SB;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < p.nseg; ++i) prefetch_tmap(&p.amap[i]);
+        prefetch_tmap(&p.wmap);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================ A (halo brick) producer
+        int sa = 0;
+        uint32_t pha = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int mt = tile / p.n_tiles_n;
+            const int iw = mt % p.tw; mt /= p.tw;
+            const int ih = mt % p.th; mt /= p.th;
+            const int d0 = mt % p.Do, n0 = mt / p.Do;
+            const int h0 = ih * H_BH, w0 = iw * H_BW;
+            for (int s = 0; s < p.nseg; ++s) {
+                const HaloSeg sg = p.seg[s];
+                for (int j = 0; j < sg.nchunks; ++j)
+                    for (int a = 0; a < sg.kd; ++a) {
+                        mbar_wait(&a_empty[sa], pha ^ 1u);
+                        if (elect_one()) {
+                            mbar_expect_tx(&a_full[sa], sg.a_bytes);
+                            tma_load_5d(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], &a_full[sa], j * BK, w0 + sg.ow, h0 + sg.oh,
+                                        d0 + sg.od + sg.dshift + a, n0);
+                        }
+                        __syncwarp();
+                        if (++sa == SA) { sa = 0; pha ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == 6) {
+        // ================================================================ B (weights) producer
+        int sb = 0;
+        uint32_t phb = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles_n;
+            int kb = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const HaloSeg sg = p.seg[s];
+                const int nk = sg.nchunks * sg.kd * sg.kh * (sg.kw / sg.g);
+                for (int i = 0; i < nk; ++i) {
+                    mbar_wait(&b_empty[sb], phb ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(&b_full[sb], p.b_tap_bytes * (uint32_t)sg.g);
+                        for (int t = 0; t < sg.g; ++t)
+                            tma_load_2d(smem_b + (size_t)sb * p.b_stage_bytes + (size_t)t * p.b_tap_bytes, &p.wmap, &b_full[sb],
+                                        (kb + t) * BK, nt * BN);
+                    }
+                    __syncwarp();
+                    kb += sg.g;
+                    if (++sb == SB) { sb = 0; phb ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem_b);
+        int sa = 0, sb = 0;
+        uint32_t pha = 0, phb = 0, acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * H_ACC_COLS;
+            uint32_t first = 1;
+            for (int s = 0; s < p.nseg; ++s) {
+                const HaloSeg sg = p.seg[s];
+                // descriptor templates: only the 14-bit start-address field changes per tap / K step
+                const uint64_t a_tmpl = make_sw128_desc_sbo(0, (uint32_t)sg.pitch * 128u);
+                const uint64_t b_tmpl = make_sw128_desc_sbo(0, 1024u);
+                const uint32_t b_tap16 = p.b_tap_bytes >> 4;
+                for (int j = 0; j < sg.nchunks; ++j) {
+                    const bool last_chunk = (s == p.nseg - 1) && (j == sg.nchunks - 1);
+                    for (int a = 0; a < sg.kd; ++a) {
+                        mbar_wait(&a_full[sa], pha);
+                        const uint32_t a_stage16 = (a_base + (uint32_t)sa * p.a_stage_bytes) >> 4;
+                        for (int b = 0; b < sg.kh; ++b) {
+                            const uint32_t row16 = a_stage16 + (uint32_t)(b * sg.pitch) * 8u;      // 128 B rows -> 8 x 16 B
+                            if (G > 1 && sg.g == G) {
+                                mbar_wait(&b_full[sb], phb);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const uint32_t b16 = (b_base + (uint32_t)sb * p.b_stage_bytes) >> 4;
+#pragma unroll
+                                    for (int t = 0; t < G; ++t) {
+                                        const uint64_t ad = a_tmpl | (uint64_t)(row16 + 8u * t), bd = b_tmpl | (uint64_t)(b16 + b_tap16 * t);
+                                        umma_bf16(d_tmem, ad, bd, idesc, (t == 0 && first) ? 0u : 1u);
+                                        umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                                        umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                                        umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                                    }
+                                    umma_commit(&b_empty[sb]);
+                                    if (b == sg.kh - 1) {
+                                        umma_commit(&a_empty[sa]);
+                                        if (last_chunk && a == sg.kd - 1) umma_commit(&tfull[acc]);
+                                    }
+                                }
+                                __syncwarp();
+                                first = 0;
+                                if (++sb == SB) { sb = 0; phb ^= 1u; }
+                            } else {
+                                for (int c = 0; c < sg.kw; ++c) {
+                                    mbar_wait(&b_full[sb], phb);
+                                    tc_fence_after();
+                                    if (elect_one()) {
+                                        const uint64_t ad = a_tmpl | (uint64_t)(row16 + 8u * c);
+                                        const uint64_t bd = b_tmpl | (uint64_t)((b_base + (uint32_t)sb * p.b_stage_bytes) >> 4);
+                                        umma_bf16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                        umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                                        umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                                        umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                                        umma_commit(&b_empty[sb]);
+                                        if (b == sg.kh - 1 && c == sg.kw - 1) {
+                                            umma_commit(&a_empty[sa]);
+                                            if (last_chunk && a == sg.kd - 1) umma_commit(&tfull[acc]);
+                                        }
+                                    }
+                                    __syncwarp();
+                                    first = 0;
+                                    if (++sb == SB) { sb = 0; phb ^= 1u; }
+                                }
+                            }
+                        }
+                        if (++sa == SA) { sa = 0; pha ^= 1u; }
+                    }
+                }
+            }
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else {
+        // ================================================================ epilogue (warps 2..5)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int rh = row >> 3, rw = row & 7;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles_n;
+            int mt = tile / p.n_tiles_n;
+            const int iw = mt % p.tw; mt /= p.tw;
+            const int ih = mt % p.th; mt /= p.th;
+            const int d = mt % p.Do, n = mt / p.Do;
+            const int h = ih * H_BH + rh, w = iw * H_BW + rw;
+            const bool valid = h < p.Ho && w < p.Wo;
+            const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw;
+            const long long lin = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
+            const float* embp = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * H_ACC_COLS + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(t_addr + c0, r);
+                tmem_ld_wait();
+                const int ch = nt * BN + c0;
+                if (valid && ch < p.Cout8) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int cg = ch + 8 * g;
+                        if (cg >= p.Cout8) break;
+                        float* vv = v + 8 * g;
+                        if (p.bias) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cg + 4));
+                            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+                            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+                        }
+                        if (embp) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(embp + cg));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(embp + cg + 4));
+                            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+                            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+                        }
+                        if (p.residual) {
+                            const uint4 rr = ldg_nc_u4(p.residual + lin * p.res_stride + cg);
+                            vv[0] += bf16_lo(rr.x); vv[1] += bf16_hi(rr.x); vv[2] += bf16_lo(rr.y); vv[3] += bf16_hi(rr.y);
+                            vv[4] += bf16_lo(rr.z); vv[5] += bf16_hi(rr.z); vv[6] += bf16_lo(rr.w); vv[7] += bf16_hi(rr.w);
+                        }
+                        if (p.y_is_f32) {
+                            float* yp = reinterpret_cast<float*>(p.y) + yoff + cg;
+                            *reinterpret_cast<float4*>(yp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                            *reinterpret_cast<float4*>(yp + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+                        } else {
+                            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + cg;
+                            *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16(vv[0], vv[1]), pack_bf16(vv[2], vv[3]),
+                                                                       pack_bf16(vv[4], vv[5]), pack_bf16(vv[6], vv[7]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host
+int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
+    GG_REQUIRE(a->stride == 1, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(a->nsrc >= 1 && a->nsrc <= H_MAX_SEGS, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->gn_partial == nullptr, GG_ERR_UNSUPPORTED);
+    if (!encode_fn()) return GG_ERR_DRIVER;
+    HaloParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = a->block_n > 0 ? a->block_n : gg_conv_pick_block_n(a->Cout);
+    GG_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256, GG_ERR_UNSUPPORTED);
+    p.BN = BN;
+    p.No = a->N; p.Do = a->Do; p.Ho = a->Ho; p.Wo = a->Wo;
+    p.th = (a->Ho + H_BH - 1) / H_BH; p.tw = (a->Wo + H_BW - 1) / H_BW;
+    p.n_tiles_n = (a->Cout + BN - 1) / BN;
+    const int64_t total = (int64_t)a->N * a->Do * p.th * p.tw * p.n_tiles_n;
+    GG_REQUIRE(total < (1ll << 31), GG_ERR_UNSUPPORTED);
+    p.total_tiles = (int)total;
+    p.Cout8 = (a->Cout + 7) / 8 * 8;
+    const int64_t W = a->W, H = a->H, D = a->D, N = a->N;
+    uint32_t max_a = 0;
+    int num_kb = 0;
+    for (int s = 0; s < a->nsrc; ++s) {
+        const gg_conv_src& src = a->src[s];
+        GG_REQUIRE(src.x != nullptr && src.C > 0 && src.C % 8 == 0, GG_ERR_BAD_ARG);
+        GG_REQUIRE(aligned(src.x, 16), GG_ERR_ALIGNMENT);
+        HaloSeg& sg = p.seg[s];
+        sg.nchunks = (src.C + BK - 1) / BK;
+        sg.dshift = src.d_shift;
+        if (src.centre_only) { sg.kd = sg.kh = sg.kw = 1; sg.od = sg.oh = sg.ow = 0; }
+        else { sg.kd = a->kd; sg.kh = a->kh; sg.kw = a->kw; sg.od = a->od; sg.oh = a->oh; sg.ow = a->ow; }
+        sg.pitch = H_BW + sg.kw - 1;
+        sg.plane = (H_BH + sg.kh - 1) * sg.pitch;
+        sg.a_bytes = (uint32_t)sg.plane * 128u;
+        max_a = std::max(max_a, sg.a_bytes);
+        const int64_t C = src.C;
+        const int64_t dim[4] = {W, H, D, N};
+        const int64_t str[4] = {C, W * C, H * W * C, D * H * W * C};
+        const int box[4] = {sg.pitch, H_BH + sg.kh - 1, 1, 1};
+        if (!encode_act_map(&p.amap[s], src.x, src.C, dim, str, box)) return GG_ERR_DRIVER;
+        num_kb += sg.nchunks * sg.kd * sg.kh * sg.kw;
+    }
+    p.nseg = a->nsrc;
+    if (!encode_w_map(&p.wmap, a->w_packed, (int64_t)num_kb * BK, a->Cout, BN)) return GG_ERR_DRIVER;
+    p.a_stage_bytes = (max_a + 1023u) & ~1023u;
+    p.b_tap_bytes = (uint32_t)BN * 128u;
+    const int bar_bytes = 512;
+    const int avail = H_SMEM_BUDGET - 1024 - bar_bytes;
+    int kwmax = 1;
+    for (int s = 0; s < a->nsrc; ++s) kwmax = std::max(kwmax, p.seg[s].kw);
+    // a B stage holds a whole kw row of taps when three A planes and >= 3 such B stages still fit
+    int G = kwmax;
+    if (const char* e = getenv("GG_HALO_MAXG")) G = std::min(G, std::max(1, atoi(e)));     // tuning knob
+    int SA = 3;
+    int SB = (avail - SA * (int)p.a_stage_bytes) / (G * (int)p.b_tap_bytes);
+    if (SB < 3) {
+        G = 1;
+        SB = (avail - SA * (int)p.a_stage_bytes) / (int)p.b_tap_bytes;
+    }
+    GG_REQUIRE(SB >= 2, GG_ERR_UNSUPPORTED);
+    if (SB > H_MAX_SB) {            // spare shared memory: deepen the A ring instead
+        SA = std::min(H_MAX_SA, (avail - H_MAX_SB * G * (int)p.b_tap_bytes) / (int)p.a_stage_bytes);
+        SB = H_MAX_SB;
+    }
+    p.b_stage_bytes = (uint32_t)G * p.b_tap_bytes;
+    for (int s = 0; s < a->nsrc; ++s) p.seg[s].g = (G > 1 && p.seg[s].kw == G) ? G : 1;
+    p.SA = SA; p.SB = SB;
+    const size_t smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * p.b_stage_bytes + bar_bytes + 1024;
+
+    p.bias = a->bias; p.emb = a->emb; p.emb_stride = a->emb_stride;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.res_stride = a->res_stride;
+    p.y = a->y; p.y_sn = a->y_sn; p.y_sd = a->y_sd; p.y_sh = a->y_sh; p.y_sw = a->y_sw; p.y_is_f32 = a->y_is_f32;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int grid = std::min(p.total_tiles, num_sms());
+    if (G == 3) conv_halo_kernel<3><<<grid, H_THREADS, smem, stream>>>(p);
+    else if (G == 2) conv_halo_kernel<2><<<grid, H_THREADS, smem, stream>>>(p);
+    else conv_halo_kernel<1><<<grid, H_THREADS, smem, stream>>>(p);
+    return launch_result();
+}
+
+}  // namespace gg

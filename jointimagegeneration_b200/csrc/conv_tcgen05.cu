@@ -13,14 +13,10 @@
 // * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
 //   lane), warps 2..5 = epilogue (tcgen05.ld -> +bias +emb +residual -> bf16/fp32 stores),
 //   which overlaps the next tile's main loop.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gg {
 
-constexpr int BM = 128;
-constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_MAPS = 8;
@@ -57,90 +53,10 @@ struct alignas(64) ConvParams {
     void* y;
     long long y_sn, y_sd, y_sh, y_sw;
     int y_is_f32;
+    // fused GroupNorm statistics of the (bf16-rounded) output: per (sample, M tile, epilogue warp) partial sums
+    float* gn_partial;     // [N, gn_nchunks_total, Cout8, 2] or null
+    int gn_chunk_base, gn_nchunks_total, stats_d_min;
 };
-
-// ------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                            int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0, 14)
-    d |= (uint64_t)1 << 16;                         // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset [32, 46)
-    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-        "elect.sync rx|px, %1;\n\t"
-        "@px mov.s32 %0, 1;\n\t}"
-        : "+r"(pred)
-        : "r"(0xffffffffu));
-    return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __grid_constant__ ConvParams p) {
@@ -282,15 +198,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            const bool stat_row = valid && d >= p.stats_d_min;
+            float* gnp = nullptr;
+            if (p.gn_partial) {     // bn == 1 (checked on the host): the whole tile belongs to sample `mt`
+                const long long chunk = p.gn_chunk_base + (long long)((id * p.th + ih) * p.tw + iw) * 4 + q;
+                gnp = p.gn_partial + (((long long)mt * p.gn_nchunks_total + chunk) * p.Cout8) * 2;
+            }
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(t_addr + c0, r);
                 tmem_ld_wait();
                 const int ch = nt * BN + c0;
-                if (valid && ch < p.Cout8) {
-                    float v[16];
+                float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (valid && ch < p.Cout8) {
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         const int cg = ch + 8 * g;
@@ -324,6 +246,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
                         }
                     }
                 }
+                if (gnp != nullptr && ch < p.Cout8) {      // warp-uniform
+                    // per-column (sum, sum of squares) over this warp's 32 rows of the values AS STORED (bf16):
+                    // butterfly reduce-scatter, 16 shuffles per quantity; lane l ends with column
+                    // 8*b4 + 4*b3 + 2*b2 + b1 (b_k = bit k of l), duplicated in lanes l and l^1
+                    float s1[16], s2[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float rv = (stat_row && ch + j < p.Cout8) ? (p.y_is_f32 ? v[j] : __bfloat162float(__float2bfloat16_rn(v[j]))) : 0.f;
+                        s1[j] = rv; s2[j] = rv * rv;
+                    }
+#pragma unroll
+                    for (int half = 8; half >= 1; half >>= 1) {
+                        const int m = half * 2;
+                        const bool up = (lane & m) != 0;
+#pragma unroll
+                        for (int i = 0; i < half; ++i) {
+                            const float k1 = up ? s1[i + half] : s1[i], x1 = up ? s1[i] : s1[i + half];
+                            const float k2 = up ? s2[i + half] : s2[i], x2 = up ? s2[i] : s2[i + half];
+                            s1[i] = k1 + __shfl_xor_sync(0xffffffffu, x1, m);
+                            s2[i] = k2 + __shfl_xor_sync(0xffffffffu, x2, m);
+                        }
+                    }
+                    s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+                    s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+                    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    if ((lane & 1) == 0 && ch + col < p.Cout8)
+                        *reinterpret_cast<float2*>(gnp + 2 * (ch + col)) = make_float2(s1[0], s2[0]);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -342,11 +292,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
 }
 
 // -------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = []() -> EncodeTiledFn {
         void* f = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -359,7 +305,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 5-D activation map over a (possibly strided) sub-grid of a CL tensor
-static bool encode_act_map(CUtensorMap* m, const void* base, int C, const int64_t dim[4] /*W,H,D,N extents*/,
+bool encode_act_map(CUtensorMap* m, const void* base, int C, const int64_t dim[4] /*W,H,D,N extents*/,
                            const int64_t stride_el[4] /*element strides of W,H,D,N*/, const int box[4] /*bw,bh,bd,bn*/) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
@@ -374,7 +320,7 @@ static bool encode_act_map(CUtensorMap* m, const void* base, int C, const int64_
     return r == CUDA_SUCCESS;
 }
 
-static bool encode_w_map(CUtensorMap* m, const void* base, int64_t Ktot, int rows, int BN) {
+bool encode_w_map(CUtensorMap* m, const void* base, int64_t Ktot, int rows, int BN) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
@@ -420,6 +366,16 @@ extern "C" int32_t gg_conv_pick_block_n(int32_t Cout) {
     return best;
 }
 
+extern "C" int32_t gg_conv_stats_chunks(const gg_conv_args* a) {
+    if (!a || a->Do <= 0 || a->Ho <= 0 || a->Wo <= 0) return 0;
+    int brick[4];
+    if (a->brick[0] > 0) { for (int i = 0; i < 4; ++i) brick[i] = a->brick[i]; }
+    else pick_brick(a->N, a->Do, a->Ho, a->Wo, brick);
+    if (brick[0] != 1) return 0;
+    const int td = (a->Do + brick[1] - 1) / brick[1], th = (a->Ho + brick[2] - 1) / brick[2], tw = (a->Wo + brick[3] - 1) / brick[3];
+    return td * th * tw * 4;
+}
+
 extern "C" int64_t gg_conv_packed_k(const gg_conv_args* a) {
     if (!a || a->nsrc < 1 || a->nsrc > 4) return -1;
     int64_t kb = 0;
@@ -443,6 +399,7 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
     if (a->bias) GG_REQUIRE(aligned(a->bias, 16), GG_ERR_ALIGNMENT);
     if (a->emb) GG_REQUIRE(aligned(a->emb, 16) && a->emb_stride % 4 == 0, GG_ERR_ALIGNMENT);
     if (!encode_fn()) return GG_ERR_DRIVER;
+    if (a->algo == 1) return conv_halo_fwd(a, as_stream(stream));
 
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -545,6 +502,13 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
     p.bias = a->bias; p.emb = a->emb; p.emb_stride = a->emb_stride;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.res_stride = a->res_stride;
     p.y = a->y; p.y_sn = a->y_sn; p.y_sd = a->y_sd; p.y_sh = a->y_sh; p.y_sw = a->y_sw; p.y_is_f32 = a->y_is_f32;
+    if (a->gn_partial) {
+        GG_REQUIRE(p.bn == 1, GG_ERR_UNSUPPORTED);      // a tile must not span samples (gg_conv_stats_chunks() == 0)
+        GG_REQUIRE(aligned(a->gn_partial, 8), GG_ERR_ALIGNMENT);
+        GG_REQUIRE(a->gn_chunk_base >= 0 && a->gn_chunk_base + p.td * p.th * p.tw * 4 <= a->gn_nchunks_total, GG_ERR_BAD_ARG);
+        p.gn_partial = a->gn_partial; p.gn_chunk_base = a->gn_chunk_base; p.gn_nchunks_total = a->gn_nchunks_total;
+        p.stats_d_min = a->stats_d_min;
+    }
 
     static bool attr_set = false;
     if (!attr_set) {

@@ -29,28 +29,22 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
     if (row < R) {
         const __nv_bfloat16* base = x + ((int64_t)n * S) * C + oct * 8;
         int64_t p = p0 + row;
-        // two loads in flight per thread
-        for (; p + R < p1; p += 2 * R) {
-            uint4 a = ldg_nc_u4(base + p * C);
-            uint4 b = ldg_nc_u4(base + (p + R) * C);
-            const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float f0 = bf16_lo(wa[e]), f1 = bf16_hi(wa[e]), g0 = bf16_lo(wb[e]), g1 = bf16_hi(wb[e]);
-                s[2 * e] += f0 + g0; s[2 * e + 1] += f1 + g1;
-                ss[2 * e] += f0 * f0 + g0 * g0; ss[2 * e + 1] += f1 * f1 + g1 * g1;
-            }
-        }
-        for (; p < p1; p += R) {
-            uint4 a = ldg_nc_u4(base + p * C);
+        // four loads in flight per thread
+        auto acc = [&](const uint4& a) {
             const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float f0 = bf16_lo(wa[e]), f1 = bf16_hi(wa[e]);
+                const float f0 = bf16_lo(wa[e]), f1 = bf16_hi(wa[e]);
                 s[2 * e] += f0; s[2 * e + 1] += f1;
-                ss[2 * e] += f0 * f0; ss[2 * e + 1] += f1 * f1;
+                ss[2 * e] = fmaf(f0, f0, ss[2 * e]); ss[2 * e + 1] = fmaf(f1, f1, ss[2 * e + 1]);
             }
+        };
+        for (; p + 3 * R < p1; p += 4 * R) {
+            const uint4 a = ldg_nc_u4(base + p * C), b = ldg_nc_u4(base + (p + R) * C);
+            const uint4 c = ldg_nc_u4(base + (p + 2 * R) * C), d = ldg_nc_u4(base + (p + 3 * R) * C);
+            acc(a); acc(b); acc(c); acc(d);
         }
+        for (; p < p1; p += R) acc(ldg_nc_u4(base + p * C));
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             sm[row * 2 * C + 2 * (oct * 8 + e)] = s[e];

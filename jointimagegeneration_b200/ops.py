@@ -188,7 +188,7 @@ def conv_block_n(cout):
 
 
 def pack_conv_weight(w: torch.Tensor, splits: Sequence[int], centre_only: Sequence[bool] = None,
-                     extra: Sequence[torch.Tensor] = ()) -> torch.Tensor:
+                     extra: Sequence[torch.Tensor] = (), chunk_major: bool = False) -> torch.Tensor:
     """torch conv / linear weight [Cout, Cin, *k] -> bf16 [Cout, Ktot] in the library's K order
     (source -> tap -> 64-channel chunk -> channel; include/guidegen_sm100.h).  `splits` = channels
     of each full-filter source (sum = Cin); `extra` = 1x1 weights [Cout, Ci(, 1...)] of
@@ -203,6 +203,8 @@ def pack_conv_weight(w: torch.Tensor, splits: Sequence[int], centre_only: Sequen
         nch = (cs + BLOCK_K - 1) // BLOCK_K
         ws = ws.permute(0, 2, 1)                                  # [Cout, taps, cs]
         ws = torch.nn.functional.pad(ws, (0, nch * BLOCK_K - cs))
+        if chunk_major:                                           # algo 1: source -> chunk -> tap -> channel
+            ws = ws.reshape(Cout, ws.shape[1], nch, BLOCK_K).permute(0, 2, 1, 3)
         cols.append(ws.reshape(Cout, -1))
     assert c0 == w.shape[1]
     for e in extra:
@@ -226,7 +228,7 @@ def pad_vec(v: Optional[torch.Tensor], n: int) -> Optional[torch.Tensor]:
 
 def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=None, emb=None, residual=None,
                    taps=None, offsets=None, out_spatial=None, y_strides=None, block_n=0, brick=None, d_shift=0,
-                   y_f32=False) -> _C.ConvArgs:
+                   y_f32=False, algo=0) -> _C.ConvArgs:
     """srcs: list of (CL tensor [N, D, H, W, C], centre_only).  y: CL tensor [N, Do, Ho, Wo, >= Cout8]
     (bf16 or fp32).  Returns the filled gg_conv_args (keeps nothing alive: the caller owns the tensors)."""
     a = _C.ConvArgs()
@@ -270,6 +272,7 @@ def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=Non
     a.y_sn, a.y_sd, a.y_sh, a.y_sw = y_strides
     a.y_is_f32 = int(y_f32) if isinstance(y, int) else int(y.dtype == torch.float32)
     a.Cout = cout
+    a.algo = algo
     a.block_n = block_n
     if brick is not None:
         for i in range(4):

@@ -33,6 +33,7 @@ class Act:
     lead: int = 0
     trail: int = 0
     halo_valid: bool = False
+    stats: Optional[tuple] = None      # (partial [N, n, C, 2], n): GroupNorm partial sums written by the producing conv
 
     @property
     def N(self): return self.t.shape[0]
@@ -163,6 +164,9 @@ class UNetEngine:
         self.num_heads = num_heads
         self.num_head_channels = num_head_channels
         self.fused_upsample = fused_upsample
+        self.use_halo_conv = True
+        self.fused_gn_stats = False     # GroupNorm statistics from the conv epilogue: correct, but the extra epilogue
+                                        # work costs more than the separate (cached) statistics pass saves on B200
         self.slab = None            # sharding.SlabComm: depth-slab decomposition of ONE volume over ranks
         self.plans: Dict[tuple, Plan] = {}
         self._wcache: Dict[tuple, torch.Tensor] = {}
@@ -216,14 +220,20 @@ class UNetEngine:
         C1, C2 = x1.C, (x2.C if x2 is not None else 0)
         R = self.slab.world if self.slab is not None else 1
 
+        temps = []
+
         def partial(x, Cx):
-            n = ops.gn_num_chunks(S, Cx)
-            p = ar.alloc((N, n, Cx, 2), torch.float32)
-            plan.add(lib.gg_gn_partial, x.ip, N, S, Cx, _C.ptr(p))
+            if x.stats is not None:            # written by the producing conv's epilogue
+                p, n = x.stats
+            else:
+                n = ops.gn_num_chunks(S, Cx)
+                p = ar.alloc((N, n, Cx, 2), torch.float32)
+                plan.add(lib.gg_gn_partial, x.ip, N, S, Cx, _C.ptr(p))
+                x.stats = (p, n)               # skip tensors are normalised twice: keep the sums with the activation
             if R > 1:       # every rank needs the statistics of the whole volume: gather the partials
                 g = ar.alloc((N, R * n, Cx, 2), torch.float32)
                 plan.add_py(self.slab.all_gather, g, p)
-                ar.release(p)
+                temps.append(g)
                 return g, R * n
             return p, n
 
@@ -236,13 +246,28 @@ class UNetEngine:
         plan.add(lib.gg_gn_finalize, C.byref(fa))
         y = self._new_act(ar, N, x1.sp, C1 + C2)
         plan.add(lib.gg_gn_apply, x1.ip, C1, x2.ip if x2 is not None else 0, C2, _C.ptr(ss), y.ip, N, S, int(silu))
-        ar.release(p1), ar.release(p2), ar.release(ss)
+        for tbuf in temps:
+            ar.release(tbuf)
+        ar.release(ss)
         return y
 
-    def _conv(self, plan: Plan, ar: _Arena, srcs: List[Tuple[Act, bool]], w_packed: torch.Tensor, cout: int, *, dims: int,
+    def _free(self, ar, a: Optional[Act]):
+        if a is None:
+            return
+        ar.release(a.t)
+        if a.stats is not None:
+            ar.release(a.stats[0])
+
+    def _halo_ok(self, taps, stride, out_spatial) -> bool:
+        """The halo-brick kernel (conv_halo.cu) pays off for multi-tap stride-1 filters on grids that fill its
+        16 x 8 output brick."""
+        return (self.use_halo_conv and stride == 1 and taps[0] * taps[1] * taps[2] > 1 and out_spatial[1] >= 16
+                and out_spatial[2] >= 8)
+
+    def _conv(self, plan: Plan, ar: _Arena, srcs: List[Tuple[Act, bool]], w_packed, cout: int, *, dims: int,
               ksize: int = 3, stride: int = 1, bias=None, emb=None, emb_stride=0, residual: Optional[Act] = None,
               f32_out: bool = False, taps=None, offsets=None, y_ptr: Optional[int] = None, y_strides=None,
-              out_spatial=None, out: Optional[Act] = None) -> Act:
+              out_spatial=None, out: Optional[Act] = None, stats: bool = False, stats_part=(0, 1)) -> Act:
         x0 = srcs[0][0]
         N, (D, H, W) = x0.N, x0.sp
         cout8 = (cout + 7) // 8 * 8
@@ -258,6 +283,11 @@ class UNetEngine:
                 out_spatial = (f(D, dims >= 3), f(H, dims >= 2), f(W, True))
         if out is None:
             out = self._new_act(ar, N, out_spatial, cout8, torch.float32 if f32_out else torch.bfloat16)
+        algo = 1 if (self._halo_ok(taps, stride, out_spatial) and not (stats and self.fused_gn_stats)) else 0
+        if callable(w_packed):          # packed-weight K order depends on the kernel
+            w_packed = w_packed(algo == 1)
+        else:
+            algo = 0
         lead = x0.lead
         d_shift, kernel_out_sp, y_base = lead, tuple(out_spatial), (y_ptr if y_ptr is not None else out.ip)
         if lead and taps[0] > 1:
@@ -276,10 +306,21 @@ class UNetEngine:
         a = ops.make_conv_args([(s.t, c) for s, c in srcs], w_packed, cout, y_base, dims=dims, ksize=ksize, stride=stride,
                                bias=bias, emb=None, residual=residual.ip if residual is not None else None, taps=taps,
                                offsets=offsets, out_spatial=kernel_out_sp, y_strides=y_strides, d_shift=d_shift,
-                               y_f32=f32_out)
+                               y_f32=f32_out, algo=algo)
         if emb is not None:
             a.emb = emb
             a.emb_stride = emb_stride
+        if stats and self.fused_gn_stats:
+            # GroupNorm statistics of the output come out of this conv's epilogue (no separate pass over the
+            # tensor); stats_part = (index, count) when several launches fill one output (folded upsample)
+            per = int(self.lib.gg_conv_stats_chunks(C.byref(a)))
+            if per > 0:
+                idx, cnt = stats_part
+                if out.stats is None:
+                    out.stats = (ar.alloc((N, per * cnt, cout8, 2), torch.float32), per * cnt)
+                a.gn_partial = _C.ptr(out.stats[0])
+                a.gn_chunk_base, a.gn_nchunks_total = idx * per, per * cnt
+                a.stats_d_min = 1 if kernel_out_sp != tuple(out_spatial) else 0
         kexp = ops.conv_packed_k(a)
         assert kexp == w_packed.shape[1], (kexp, tuple(w_packed.shape))
         plan.keep.append(a)
@@ -287,8 +328,8 @@ class UNetEngine:
         plan.flops += 2 * N * int(math.prod(out_spatial)) * cout * w_packed.shape[1]
         return out
 
-    def _pack(self, conv: M.ParamConv, splits, extra=()):
-        key = (id(conv.weight), tuple(splits), tuple(id(e) for e in extra))
+    def _pack(self, conv: M.ParamConv, splits, extra=(), chunk_major=False):
+        key = (id(conv.weight), tuple(splits), tuple(id(e) for e in extra), chunk_major)
 
         def make():
             w = conv.weight.detach()
@@ -296,9 +337,12 @@ class UNetEngine:
             if missing > 0:      # activation channels were zero-padded to a multiple of 8 (e.g. 13 -> 16)
                 assert len(splits) == 1
                 w = torch.cat([w, w.new_zeros((w.shape[0], missing) + tuple(w.shape[2:]))], 1)
-            return ops.pack_conv_weight(w, splits, extra=[e for e in extra])
+            return ops.pack_conv_weight(w, splits, extra=[e for e in extra], chunk_major=chunk_major)
 
         return self._cached(key, make)
+
+    def _packer(self, conv, splits):
+        return lambda cm: self._pack(conv, splits, chunk_major=cm)
 
     # ------------------------------------------------------------------------------ layers
     def _resblock(self, plan, ar, rb: M.ResBlock, x1: Act, x2: Optional[Act], emb_ptr: int, emb_stride: int) -> Act:
@@ -306,15 +350,17 @@ class UNetEngine:
         cout = rb.out_channels
         a1 = self._gn(plan, ar, x1, x2, rb.in_layers[0], True)
         c1 = rb.in_layers[2]
-        h1 = self._conv(plan, ar, [(a1, False)], self._pack(c1, [a1.C]), cout, dims=dims, emb=emb_ptr, emb_stride=emb_stride)
-        ar.release(a1.t)
+        h1 = self._conv(plan, ar, [(a1, False)], self._packer(c1, [a1.C]), cout, dims=dims, emb=emb_ptr, emb_stride=emb_stride,
+                        stats=True)
+        self._free(ar, a1)
         a2 = self._gn(plan, ar, h1, None, rb.out_layers[0], True)
-        ar.release(h1.t)
+        self._free(ar, h1)
         c2 = rb.out_layers[3]
         if isinstance(rb.skip_connection, torch.nn.Identity):
             assert x2 is None and x1.C == cout
             b2 = self._vec8((id(c2.bias), "b"), lambda: c2.bias, cout)
-            out = self._conv(plan, ar, [(a2, False)], self._pack(c2, [a2.C]), cout, dims=dims, bias=_C.ptr(b2), residual=x1)
+            out = self._conv(plan, ar, [(a2, False)], self._packer(c2, [a2.C]), cout, dims=dims, bias=_C.ptr(b2), residual=x1,
+                             stats=True)
         else:
             sk = rb.skip_connection
             if sk.kernel_size != 1:
@@ -326,10 +372,10 @@ class UNetEngine:
                 extras.append(skw[:, c0:c0 + x.C])
                 c0 += x.C
             key = (id(c2.weight), id(sk.weight), tuple(x.C for x in xs))
-            wp = self._cached(key, lambda: ops.pack_conv_weight(c2.weight, [a2.C], extra=extras))
+            wp = lambda cm: self._cached(key + (cm,), lambda: ops.pack_conv_weight(c2.weight, [a2.C], extra=extras, chunk_major=cm))  # noqa: E731
             b2 = self._vec8((id(c2.bias), id(sk.bias), "b"), lambda: c2.bias.detach() + sk.bias.detach(), cout)
-            out = self._conv(plan, ar, [(a2, False)] + [(x, True) for x in xs], wp, cout, dims=dims, bias=_C.ptr(b2))
-        ar.release(a2.t)
+            out = self._conv(plan, ar, [(a2, False)] + [(x, True) for x in xs], wp, cout, dims=dims, bias=_C.ptr(b2), stats=True)
+        self._free(ar, a2)
         return out
 
     def _heads(self, ch):
@@ -362,7 +408,8 @@ class UNetEngine:
         plan.flops += 4 * N * H * S * Tk * d
         ar.release(qkv.t), ar.release(gathered)
         bp = self._vec8((id(ab.proj_out.bias), "b"), lambda: ab.proj_out.bias, Cc)
-        out = self._conv(plan, ar, [(o, False)], self._pack(ab.proj_out, [Cc]), Cc, dims=3, ksize=1, bias=_C.ptr(bp), residual=x)
+        out = self._conv(plan, ar, [(o, False)], self._pack(ab.proj_out, [Cc]), Cc, dims=3, ksize=1, bias=_C.ptr(bp), residual=x,
+                         stats=True)
         ar.release(o.t)
         return out
 
@@ -447,7 +494,7 @@ class UNetEngine:
     def _downsample(self, plan, ar, ds: M.Downsample, x: Act) -> Act:
         b = self._vec8((id(ds.op.bias), "b"), lambda: ds.op.bias, ds.out_channels)
         return self._conv(plan, ar, [(x, False)], self._pack(ds.op, [x.C]), ds.out_channels, dims=ds.dims, stride=2,
-                          bias=_C.ptr(b))
+                          bias=_C.ptr(b), stats=True)
 
     def _upsample(self, plan, ar, up: M.Upsample, x: Act) -> Act:
         dims = up.dims
@@ -460,7 +507,8 @@ class UNetEngine:
             if not up.use_conv:
                 return y
             b = self._vec8((id(up.conv.bias), "b"), lambda: up.conv.bias, up.out_channels)
-            out = self._conv(plan, ar, [(y, False)], self._pack(up.conv, [Cc]), up.out_channels, dims=dims, bias=_C.ptr(b))
+            out = self._conv(plan, ar, [(y, False)], self._packer(up.conv, [Cc]), up.out_channels, dims=dims, bias=_C.ptr(b),
+                             stats=True)
             ar.release(y.t)
             return out
         cout = up.out_channels
@@ -474,14 +522,16 @@ class UNetEngine:
         for pd in range(fd):
             for ph in range(fh):
                 for pw in range(2):
-                    wp = self._cached((id(up.conv.weight), "up", pd, ph, pw),
-                                      lambda: ops.pack_conv_weight(_fold_upsample_weight(up.conv.weight, dims, (pd, ph, pw)), [Cc]))
+                    wp = (lambda pd=pd, ph=ph, pw=pw: lambda cm: self._cached(
+                        (id(up.conv.weight), "up", pd, ph, pw, cm),
+                        lambda: ops.pack_conv_weight(_fold_upsample_weight(up.conv.weight, dims, (pd, ph, pw)), [Cc], chunk_major=cm)))()
                     taps = (2 if dims >= 3 else 1, 2 if dims >= 2 else 1, 2)
                     offs = (pd - 1 if dims >= 3 else 0, ph - 1 if dims >= 2 else 0, pw - 1)
                     yp = out.ip + ((pd * Ho + ph) * Wo + pw) * cout * 2
                     ystr = (Do * Ho * Wo * cout, fd * Ho * Wo * cout, fh * Wo * cout, 2 * cout)
                     self._conv(plan, ar, [(x, False)], wp, cout, dims=dims, bias=_C.ptr(b), taps=taps, offsets=offs, y_ptr=yp,
-                               y_strides=ystr, out_spatial=(D, H, W), out=out)
+                               y_strides=ystr, out_spatial=(D, H, W), out=out, stats=True,
+                               stats_part=((pd * fh + ph) * 2 + pw, fd * fh * 2))
         return out
 
     # -------------------------------------------------------------------------------- plan
@@ -555,14 +605,14 @@ class UNetEngine:
                 elif isinstance(layer, M.ParamConv):
                     b = self._vec8((id(layer.bias), "b"), lambda: layer.bias, layer.out_channels)
                     h.halo_valid = False           # the sampler rewrites the input between forwards
-                    new = self._conv(plan, ar, [(h, False)], self._pack(layer, [h.C]), layer.out_channels, dims=layer.dims,
-                                     bias=_C.ptr(b))
+                    new = self._conv(plan, ar, [(h, False)], self._packer(layer, [h.C]), layer.out_channels, dims=layer.dims,
+                                     bias=_C.ptr(b), stats=True)
                 else:
                     raise NotImplementedError(type(layer).__name__)
                 if not any(h.t is p.t for p in protected):
-                    ar.release(h.t)
+                    self._free(ar, h)
                 if first and skip is not None:
-                    ar.release(skip.t)
+                    self._free(ar, skip)
                 h, first = new, False
             return h
 
@@ -577,10 +627,10 @@ class UNetEngine:
             h = run_block(block, h, skip, hs)
         # ---- head: GN -> SiLU -> conv (-> softmax fused downstream)   unet.py:715-721
         a = self._gn(plan, ar, h, None, m.out[0], True)
-        ar.release(h.t)
+        self._free(ar, h)
         oc = m.out[2]
         b = self._vec8((id(oc.bias), "b"), lambda: oc.bias, oc.out_channels)
-        head = self._conv(plan, ar, [(a, False)], self._pack(oc, [a.C]), oc.out_channels, dims=oc.dims, bias=_C.ptr(b),
+        head = self._conv(plan, ar, [(a, False)], self._packer(oc, [a.C]), oc.out_channels, dims=oc.dims, bias=_C.ptr(b),
                           f32_out=f32_head)
         ar.release(a.t)
         plan.outputs["head"] = head.interior
