@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     uint64_t* tfull = b_empty + H_MAX_SB;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bvec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512);      // [BN] bias + emb[n]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -241,7 +242,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int rh = row >> 3, rw = row & 7;
+        const int etid = threadIdx.x - 64;             // 0..127 among the epilogue warps
         uint32_t acc = 0, acc_phase = 0;
+        int cur_n = -1, cur_nt = -1;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles_n;
             int mt = tile / p.n_tiles_n;
@@ -250,55 +253,30 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             const int d = mt % p.Do, n = mt / p.Do;
             const int h = ih * H_BH + rh, w = iw * H_BW + rw;
             const bool valid = h < p.Ho && w < p.Wo;
+            if (n != cur_n || nt != cur_nt) {          // uniform over the four epilogue warps (same tile sequence)
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone is done with the previous vector
+                for (int c = etid; c < BN; c += 128) {
+                    const int ch = nt * BN + c;
+                    float v = 0.f;
+                    if (ch < p.Cout8) {
+                        if (p.bias) v += __ldg(p.bias + ch);
+                        if (p.emb) v += __ldg(p.emb + (long long)n * p.emb_stride + ch);
+                    }
+                    bvec[c] = v;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cur_n = n; cur_nt = nt;
+            }
             const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw;
             const long long lin = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
-            const float* embp = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
+            const int ncols = min(BN, p.Cout8 - nt * BN);
+            const __nv_bfloat16* res_row = p.residual ? p.residual + lin * p.res_stride + nt * BN : nullptr;
+            void* y_row = p.y_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.y) + yoff + nt * BN)
+                                     : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + nt * BN);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * H_ACC_COLS + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(t_addr + c0, r);
-                tmem_ld_wait();
-                const int ch = nt * BN + c0;
-                if (valid && ch < p.Cout8) {
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const int cg = ch + 8 * g;
-                        if (cg >= p.Cout8) break;
-                        float* vv = v + 8 * g;
-                        if (p.bias) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cg + 4));
-                            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-                            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-                        }
-                        if (embp) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(embp + cg));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(embp + cg + 4));
-                            vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-                            vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-                        }
-                        if (p.residual) {
-                            const uint4 rr = ldg_nc_u4(p.residual + lin * p.res_stride + cg);
-                            vv[0] += bf16_lo(rr.x); vv[1] += bf16_hi(rr.x); vv[2] += bf16_lo(rr.y); vv[3] += bf16_hi(rr.y);
-                            vv[4] += bf16_lo(rr.z); vv[5] += bf16_hi(rr.z); vv[6] += bf16_lo(rr.w); vv[7] += bf16_hi(rr.w);
-                        }
-                        if (p.y_is_f32) {
-                            float* yp = reinterpret_cast<float*>(p.y) + yoff + cg;
-                            *reinterpret_cast<float4*>(yp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                            *reinterpret_cast<float4*>(yp + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
-                        } else {
-                            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + cg;
-                            *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16(vv[0], vv[1]), pack_bf16(vv[2], vv[3]),
-                                                                       pack_bf16(vv[4], vv[5]), pack_bf16(vv[6], vv[7]));
-                        }
-                    }
-                }
-            }
+            epilogue_row(t_addr, BN, ncols, bvec, res_row, y_row, p.y_is_f32, valid);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -360,7 +338,7 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     if (!encode_w_map(&p.wmap, a->w_packed, (int64_t)num_kb * BK, a->Cout, BN)) return GG_ERR_DRIVER;
     p.a_stage_bytes = (max_a + 1023u) & ~1023u;
     p.b_tap_bytes = (uint32_t)BN * 128u;
-    const int bar_bytes = 512;
+    const int bar_bytes = 512 + 1024;        // barriers + the epilogue's [BN] additive vector
     const int avail = H_SMEM_BUDGET - 1024 - bar_bytes;
     int kwmax = 1;
     for (int s = 0; s < a->nsrc; ++s) kwmax = std::max(kwmax, p.seg[s].kw);

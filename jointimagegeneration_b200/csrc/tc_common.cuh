@@ -93,6 +93,65 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// Epilogue of one accumulator row (this thread's TMEM lane): 32 columns per step -- two tcgen05.ld in flight,
+// the per-column additive vector (bias + timestep embedding) read from shared memory (broadcast), the residual
+// row software-prefetched one step ahead.  Every lane of the warp must call this (tcgen05.ld is warp-collective);
+// lanes whose output position is out of range pass valid = false.
+__device__ __forceinline__ void epilogue_row(uint32_t t_addr, int BN, int ncols, const float* __restrict__ bvec,
+                                             const __nv_bfloat16* __restrict__ res_row, void* y_row, int y_is_f32, bool valid) {
+    uint4 rn[4];
+    auto load_res = [&](int c0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            rn[g] = (res_row != nullptr && valid && c0 + 8 * g < ncols) ? ldg_nc_u4(res_row + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+    };
+    load_res(0);
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld16_nowait(t_addr + c0, r);
+        if (c0 + 16 < BN) tmem_ld16_nowait(t_addr + c0 + 16, r + 16);
+        uint4 rc[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rc[g] = rn[g];
+        if (c0 + 32 < BN) load_res(c0 + 32);
+        tmem_ld_wait();
+        if (!valid) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int c = c0 + 8 * g;
+            if (c >= ncols) break;
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bvec + c), b1 = *reinterpret_cast<const float4*>(bvec + c + 4);
+            v[0] = __uint_as_float(r[8 * g + 0]) + b0.x; v[1] = __uint_as_float(r[8 * g + 1]) + b0.y;
+            v[2] = __uint_as_float(r[8 * g + 2]) + b0.z; v[3] = __uint_as_float(r[8 * g + 3]) + b0.w;
+            v[4] = __uint_as_float(r[8 * g + 4]) + b1.x; v[5] = __uint_as_float(r[8 * g + 5]) + b1.y;
+            v[6] = __uint_as_float(r[8 * g + 6]) + b1.z; v[7] = __uint_as_float(r[8 * g + 7]) + b1.w;
+            if (res_row != nullptr) {
+                const uint4 rr = rc[g];
+                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+            }
+            if (y_is_f32) {
+                float* yp = reinterpret_cast<float*>(y_row) + c;
+                *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y_row) + c;
+                *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                                           pack_bf16(v[6], v[7]));
+            }
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
