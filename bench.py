@@ -336,7 +336,21 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def instrument_plan(plan, extra=None, reps=2):
+def describe_launch(name, fargs, ms):
+    import ctypes
+    from jointimagegeneration_b200 import _C
+    if name != "gg_conv_fwd":
+        return "%s : %.3f ms" % (name, ms)
+    ca = fargs[0]._obj
+    cin = sum(ca.src[i].C for i in range(ca.nsrc))
+    kk = _C.lib().gg_conv_packed_k(ctypes.byref(ca))
+    fl = 2.0 * ca.N * ca.Do * ca.Ho * ca.Wo * ca.Cout * kk
+    return ("conv N%d in %dx%dx%d out %dx%dx%d Cin %d(nsrc %d) Cout %d taps %dx%dx%d s%d algo%d K %d : %.3f ms %.0f TF/s"
+            % (ca.N, ca.D, ca.H, ca.W, ca.Do, ca.Ho, ca.Wo, cin, ca.nsrc, ca.Cout, ca.kd, ca.kh, ca.kw, ca.stride, ca.algo, kk, ms,
+               fl / ms / 1e9))
+
+
+def instrument_plan(plan, extra=None, reps=2, detail_path=None):
     """CUDA-event time of every launch of one planned forward (eager, current stream) -> {name: [ms, count]}."""
     import torch
     from jointimagegeneration_b200 import _C
@@ -362,6 +376,10 @@ def instrument_plan(plan, extra=None, reps=2):
             d = kinds.setdefault(name, [0.0, 0])
             d[0] += a.elapsed_time(b) / reps
             d[1] += 1
+    if detail_path:
+        with open(detail_path, "w") as f:
+            for (fn, fargs), (name, a, b) in zip(plan.steps, evs):
+                f.write(describe_launch(name, fargs, a.elapsed_time(b)) + "\n")
     return {k: (v[0], v[1] // reps) for k, v in kinds.items()}
 
 
@@ -442,14 +460,14 @@ def run_ours_ldm(args):
             "slices_per_sec": value * B / S}
     if rank == 0:
         peaks = load_peaks()
-        kinds = instrument_plan(plan)
+        kinds = instrument_plan(plan, detail_path=os.path.join(ROOT, "gpurun_out", "bench_detail_ldm.txt") if args.detail else None)
         conv_ms, n_conv = kinds["gg_conv_fwd"]
         ach = wl["flop_per_sample"] * B / (conv_ms / 1e3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "conv_tcgen05_kernel (all %d launches of one step)" % n_conv, "achieved": ach,
                             "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": None,
                             "algorithmic_flop": wl["flop_per_sample"] * B, "issued_flop": plan.flops,
                             "peak_source": peaks["source"] + " (bf16 sustained)",
-                            "whole_step_frac": wl["flop_per_sample"] * B * share / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
+                            "whole_step_frac": wl["flop_per_sample"] * B / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
         line["kernel_ms"] = {k: round(v[0], 4) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
         print(json.dumps(line), flush=True)
     if world > 1:

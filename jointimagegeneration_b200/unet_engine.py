@@ -564,8 +564,10 @@ class UNetEngine:
         plan.add(self.lib.gg_small_linear, _C.ptr(temb), _C.ptr(self._f32(te0.weight)), _C.ptr(self._f32(te0.bias)), _C.ptr(e1),
                  N, E, mc, 0, 1)
         emb = ar.alloc((N, E), torch.float32)
+        # emb is only ever consumed through SiLU (every ResBlock's emb_layers = SiLU -> Linear, unet.py:205-211):
+        # apply it once here instead of once per output row of the big projection below
         plan.add(self.lib.gg_small_linear, _C.ptr(e1), _C.ptr(self._f32(te2.weight)), _C.ptr(self._f32(te2.bias)), _C.ptr(emb),
-                 N, E, E, 0, 0)
+                 N, E, E, 0, 1)
         rbs = [mod for mod in m.modules() if isinstance(mod, M.ResBlock)]
         offs, tot = {}, 0
         for rb in rbs:
@@ -586,7 +588,7 @@ class UNetEngine:
 
         W_all, b_all = self._cached(("emb_all",), make_emb_w)
         emb_all = ar.alloc((N, tot), torch.float32)
-        plan.add(self.lib.gg_small_linear, _C.ptr(emb), _C.ptr(W_all), _C.ptr(b_all), _C.ptr(emb_all), N, tot, E, 1, 0)
+        plan.add(self.lib.gg_small_linear, _C.ptr(emb), _C.ptr(W_all), _C.ptr(b_all), _C.ptr(emb_all), N, tot, E, 0, 0)
 
         def run_block(block, h: Act, skip: Optional[Act], protected) -> Act:
             first = True
