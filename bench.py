@@ -42,9 +42,15 @@ WORKLOADS = {
                      desc="LDM conditional CT slice generator (ruijin-ldm_from_controlnet_ae.yaml UNet), latent 4x64x64, "
                           "concat mask/prev-slice context, DDIM 50 steps eta 0, batch 16, bf16"),
 }
+LDM_PIXEL_NET = dict(dims=2, image_size=512, in_channels=3, out_channels=1, model_channels=128, attention_resolutions=[32, 16, 8],
+                     num_res_blocks=2, channel_mult=[1, 2, 4, 4, 5], num_head_channels=32)      # ruijin-ldm_from_controlnet.yaml:17-40
 LDM_AE_NET = dict(dims=2, image_size=512, in_channels=8, out_channels=4, model_channels=160, attention_resolutions=[8, 4, 2],
                   num_res_blocks=2, channel_mult=[1, 2, 4, 4, 5], num_head_channels=32)      # ruijin-ldm_from_controlnet_ae.yaml:17-40
 LDM_SCHEDULE = dict(timesteps=1000, linear_start=0.0015, linear_end=0.0195)
+WORKLOADS["ldm_cfg3"]["net"] = LDM_AE_NET
+WORKLOADS["ldm_cfg4"] = dict(spatial=(512, 512), C=1, batch=2, T=50, flop_per_sample=4.63e12, kind="ldm", net=LDM_PIXEL_NET,
+                             desc="stage 2 of the full GuideGen pipeline: pixel-space LDM (ruijin-ldm_from_controlnet.yaml UNet), one CT slice "
+                                  "512x512 conditioned on (previous slice | mask slice), DDIM 50 steps, n_samples 2; slices are sequential")
 
 
 def load_peaks():
@@ -401,14 +407,16 @@ def run_ours_ldm(args):
     B, S = args.batch or wl["batch"], wl["T"]
     hw = wl["spatial"]
     torch.manual_seed(4321 + rank)
-    unet = UNetModel(**LDM_AE_NET)
+    net = wl["net"]
+    xc, cc = net["out_channels"], net["in_channels"] - net["out_channels"]
+    unet = UNetModel(**net)
     randomize_zero_modules(unet, 7)
     ld = LatentDiffusion(unet, conditioning_key="concat", **LDM_SCHEDULE).to(dev).eval()
     unet.use_cuda_graph = True
     sampler = DDIMSampler(ld)
     sampler.make_schedule(S, ddim_eta=0.0, verbose=False)
-    x = torch.randn((B, 4) + hw, device=dev)
-    c = torch.randn((B, 4) + hw, device=dev)
+    x = torch.randn((B, xc) + hw, device=dev)
+    c = torch.randn((B, cc) + hw, device=dev)
     steps_t = [int(v) for v in sampler.ddim_timesteps[::-1]]
     ts = [torch.full((B,), v, device=dev, dtype=torch.long) for v in steps_t]
     state = {"x": x}
@@ -441,10 +449,10 @@ def run_ours_ldm(args):
     plan = unet.plan_for(B, hw)
     # e2e: the public call sample_cond makes (sample_diffusion.py:212), host conditioning in, host samples out
     c_host = c.cpu().pin_memory()
-    out_host = torch.empty((B, 4) + hw).pin_memory()
+    out_host = torch.empty((B, xc) + hw).pin_memory()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    smp, _ = sampler.sample(S=S, batch_size=B, shape=(4,) + hw, conditioning=c_host.to(dev, non_blocking=True), eta=0.0, verbose=False, dims=2)
+    smp, _ = sampler.sample(S=S, batch_size=B, shape=(xc,) + hw, conditioning=c_host.to(dev, non_blocking=True), eta=0.0, verbose=False, dims=2)
     out_host.copy_(smp)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0

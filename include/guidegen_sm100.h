@@ -150,6 +150,19 @@ typedef struct {
 int gg_ddpm_update(const gg_ddpm_args* a, gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Stage bridge of the autoregressive CT generator     latentdiffusion/sample_diffusion.py:196-224
+ *   :199-201  label volume -> nearest-neighbour zoom (order 0) -> / 255  (whole-mask conditioning)
+ *   :221-222  samples[:, :, m] = (ds - ds.min()) / (ds.max() - ds.min())   (min / max over the whole slice batch)
+ * ---------------------------------------------------------------------------------------- */
+/* mask[d, h, w] = labels[d, h / fh, w / fw] / divisor   (uint8 [D, H, W] -> fp32 [D, H*fh, W*fw]) */
+int gg_labels_to_mask(const uint8_t* labels, float* mask, int32_t D, int32_t H, int32_t W, int32_t fh, int32_t fw, float divisor,
+                      gg_stream_t stream);
+/* y[b, 0:per_sample] = (x[b] - min(x)) / (max(x) - min(x)); x dense fp32 [B, per_sample]; row b of y starts at
+ * y + b * y_batch_stride (a slice of a [B, 1, D, H, W] volume); scratch: fp32 [1024] device workspace */
+int gg_minmax_normalize(const float* x, float* y, float* scratch, int32_t B, int64_t per_sample, int64_t y_batch_stride,
+                        gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Layout bridges at the drop-in boundary (fp32 NC* <-> CL bf16)
  *   unet.py:775 th.cat([x, input_condition], 1); ddpm.py:1419 torch.cat([x] + c_concat, 1)
  * ---------------------------------------------------------------------------------------- */

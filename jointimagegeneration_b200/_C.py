@@ -105,6 +105,8 @@ SYMBOLS = {
     "gg_cat_step_cl": (C.c_int, [C.POINTER(CatStepCLArgs), _vp]),
     "gg_ddim_update": (C.c_int, [C.POINTER(DdimArgs), _vp]),
     "gg_ddpm_update": (C.c_int, [C.POINTER(DdpmArgs), _vp]),
+    "gg_labels_to_mask": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "gg_minmax_normalize": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _vp]),
     "gg_nchw_to_cl": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i64, _vp]),
     "gg_cl_to_nchw": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i32, _vp]),
     "gg_gn_num_chunks": (_i32, [_i64, _i32]),

@@ -460,6 +460,57 @@ __global__ void __launch_bounds__(256) ddpm_kernel(const gg_ddpm_args a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// stage bridge of the autoregressive CT generator (sample_diffusion.py:196-224)
+//   labels -> nearest-neighbour zoomed float mask (label / 255);  per-slice-batch min-max normalise
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) labels_to_mask_kernel(const uint8_t* __restrict__ lab, float* __restrict__ out, int D, int H,
+                                                             int W, int fh, int fw, float divisor) {
+    const int Ho = H * fh, Wo = W * fw;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)D * Ho * Wo) return;
+    const int w = (int)(i % Wo), h = (int)((i / Wo) % Ho), d = (int)(i / ((int64_t)Wo * Ho));
+    out[i] = __fdiv_rn((float)lab[((int64_t)d * H + h / fh) * W + w / fw], divisor);
+}
+
+__device__ __forceinline__ void block_minmax(float& mn, float& mx) {
+    __shared__ float smn[8], smx[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    mn = smn[0]; mx = smx[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { mn = fminf(mn, smn[k]); mx = fmaxf(mx, smx[k]); }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ part) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(x + i);
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    block_minmax(mn, mx);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = mn; part[2 * blockIdx.x + 1] = mx; }
+}
+
+// y[b, :] (row stride y_bs) = (x[b, :] - min) / (max - min) with min / max over ALL of x (ds.min(), ds.max())
+__global__ void __launch_bounds__(256) minmax_normalize_kernel(const float* __restrict__ x, const float* __restrict__ part, int nparts,
+                                                               float* __restrict__ y, int64_t per, int64_t y_bs, int B) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (int k = threadIdx.x; k < nparts; k += blockDim.x) { mn = fminf(mn, part[2 * k]); mx = fmaxf(mx, part[2 * k + 1]); }
+    block_minmax(mn, mx);
+    const float den = __fsub_rn(mx, mn);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per * B; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / per, r = i - b * per;
+        y[b * y_bs + r] = __fdiv_rn(__fsub_rn(__ldg(x + i), mn), den);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // layout bridges
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_cl_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
@@ -570,6 +621,27 @@ extern "C" int gg_ddpm_update(const gg_ddpm_args* a, gg_stream_t stream) {
     GG_REQUIRE(a->B <= 65535, GG_ERR_UNSUPPORTED);
     const dim3 grid((unsigned)((a->per_sample + 255) / 256), (unsigned)a->B);
     ddpm_kernel<<<grid, 256, 0, as_stream(stream)>>>(*a);
+    return launch_result();
+}
+
+extern "C" int gg_labels_to_mask(const uint8_t* labels, float* mask, int32_t D, int32_t H, int32_t W, int32_t fh, int32_t fw,
+                                 float divisor, gg_stream_t stream) {
+    GG_REQUIRE(labels && mask && D > 0 && H > 0 && W > 0 && fh > 0 && fw > 0 && divisor != 0.f, GG_ERR_BAD_ARG);
+    const int64_t n = (int64_t)D * H * fh * W * fw;
+    labels_to_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(labels, mask, D, H, W, fh, fw, divisor);
+    return launch_result();
+}
+
+extern "C" int gg_minmax_normalize(const float* x, float* y, float* scratch, int32_t B, int64_t per_sample, int64_t y_batch_stride,
+                                   gg_stream_t stream) {
+    GG_REQUIRE(x && y && scratch && B > 0 && per_sample > 0 && y_batch_stride >= per_sample, GG_ERR_BAD_ARG);
+    const int64_t n = (int64_t)B * per_sample;
+    const int nparts = (int)std::min<int64_t>(512, (n + 255) / 256);
+    minmax_partial_kernel<<<nparts, 256, 0, as_stream(stream)>>>(x, n, scratch);
+    int st = launch_result();
+    if (st != GG_OK) return st;
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8);
+    minmax_normalize_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, scratch, nparts, y, per_sample, y_batch_stride, B);
     return launch_result();
 }
 

@@ -95,6 +95,27 @@ def ddpm_update(x, e_t, coef, noise=None, temperature=1.0, clip_denoised=False, 
     return x_prev, x0
 
 
+def labels_to_mask(labels, fh, fw, divisor=255.0, out=None):
+    """uint8 labels [D, H, W] -> fp32 mask [D, H*fh, W*fw] (nearest zoom, / divisor)."""
+    _chk(labels, torch.uint8)
+    D, H, W = labels.shape
+    if out is None:
+        out = torch.empty((D, H * fh, W * fw), dtype=torch.float32, device=labels.device)
+    _C.check(_C.lib().gg_labels_to_mask(_C.ptr(labels), _C.ptr(out), D, H, W, fh, fw, float(divisor), _C.stream()), "gg_labels_to_mask")
+    return out
+
+
+def minmax_normalize(x, y_view, scratch):
+    """y_view[b] = (x[b] - x.min()) / (x.max() - x.min()); y_view: [B, ...] whose rows are contiguous blocks."""
+    _chk(x, torch.float32)
+    B = x.shape[0]
+    per = x[0].numel()
+    assert y_view.dtype == torch.float32 and y_view[0].is_contiguous() and y_view[0].numel() == per
+    _C.check(_C.lib().gg_minmax_normalize(_C.ptr(x), _C.ptr(y_view), _C.ptr(scratch), B, per, y_view.stride(0), _C.stream()),
+             "gg_minmax_normalize")
+    return y_view
+
+
 def nchw_to_cl(x1, x2=None, c_pad=None, out=None):
     """fp32 [N, C1, *sp] (+ [N, C2, *sp]) -> CL bf16 [N, *sp3, Cpad] with zero-filled padding."""
     _chk(x1, torch.float32)

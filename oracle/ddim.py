@@ -120,3 +120,19 @@ def ddpm_update(x, e_t, tab, t: int, noise, temperature=1.0, clip=False):
     sd = f32(nz * np.exp(f32(0.5) * tab["logvar"][t], dtype=f32))
     n = (noise.astype(f32) * f32(temperature)).astype(f32)
     return (mean + (sd * n).astype(f32)).astype(f32), x0
+
+
+def sample_cond(eps_fn, acp_f32, wholemask: np.ndarray, n_samples: int, S: int, x_T_fn, eta: float = 0.0) -> np.ndarray:
+    """latentdiffusion/sample_diffusion.py:196-224 restated (numpy + ddim_sample above).
+    eps_fn(x [n,1,H,W], t, cond [n,2,H,W]) -> eps; wholemask [1,1,D,H,W]; returns [n,2,D,H,W]."""
+    _, _, D, H, W = wholemask.shape
+    nz = np.where(wholemask.sum((0, 1, 3, 4)))[0]
+    start, end = int(nz[0]), int(nz[-1])
+    samples = np.zeros((n_samples, 1, D, H, W), dtype=f32)
+    gen_mask = np.repeat(wholemask.astype(f32), n_samples, axis=0)
+    for m in range(start - 1, end + 1):
+        cond = np.concatenate([samples[:, :, max(0, m - 1)], gen_mask[:, :, m]], axis=1)
+        ct = torch.from_numpy(cond)
+        s = ddim_sample(lambda x, t: eps_fn(x, t, ct), acp_f32, x_T_fn(m), S, eta).numpy()
+        samples[:, 0, m] = ((s - s.min()) / (s.max() - s.min())).astype(f32)[:, 0]
+    return np.concatenate([samples, gen_mask], axis=1)

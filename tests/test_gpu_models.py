@@ -360,3 +360,37 @@ def test_ancestral_sampler_runs_and_matches_oracle_update():
         assert np.abs(got[b].cpu().numpy() - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
     out = model.p_sample_loop(cc, (2, 4, 16, 16), timesteps=3)
     assert tuple(out.shape) == (2, 4, 16, 16) and torch.isfinite(out).all()
+
+
+def test_two_stage_pipeline_vs_oracle():
+    """BASELINE config 4 at toy size: labels -> whole-mask bridge -> autoregressive slice loop
+    (previous slice | mask slice conditioning, DDIM, per-slice min-max) vs the oracle restatement of
+    sample_diffusion.py:196-224 driving the oracle network on the same weights / initial noise."""
+    from jointimagegeneration_b200.ldm import LatentDiffusion, UNetModel
+    from jointimagegeneration_b200.pipeline import GuideGenPipeline
+    from oracle import configs, ddim, nets, weights
+    params = dict(dims=2, image_size=32, in_channels=3, out_channels=1, model_channels=32, attention_resolutions=[2],
+                  num_res_blocks=1, channel_mult=[1, 2], num_head_channels=32)
+    unet = UNetModel(**params)
+    sd = _load_synth(unet, 17)
+    ld = LatentDiffusion(unet, conditioning_key="concat", **configs.LDM_SCHEDULE).cuda().eval()
+    pipe = GuideGenPipeline(ld, ddim_steps=4, ddim_eta=0.0)   # S must divide 1000 (reference quirk: util.py:46-60)
+    rs = np.random.RandomState(0)
+    labels = np.zeros((6, 8, 8), dtype=np.uint8)
+    labels[1:5] = rs.randint(0, 12, size=(4, 8, 8))
+    mask = pipe.mask_to_ct_grid(torch.from_numpy(labels).cuda(), size=(32, 32))
+    want_mask = np.repeat(np.repeat(labels, 4, 1), 4, 2).astype(np.float32) / 255.0
+    assert np.array_equal(mask[0, 0].cpu().numpy(), want_mask.astype(np.float32))
+    n = 2
+    noise = {m: weights.normal(300 + m, (n, 1, 32, 32)) for m in range(0, 6)}
+    got = pipe.sample_cond(mask, n_samples=n, x_T_fn=lambda m: noise[m].cuda()).cpu().numpy()
+    acp = ld.alphas_cumprod.cpu().numpy()
+    want = ddim.sample_cond(lambda x, t, c: nets.unet_forward(sd, torch.cat([x, c], 1), t, num_head_channels=32), acp,
+                            mask.cpu().numpy(), n, 4, lambda m: noise[m])
+    assert got.shape == want.shape == (n, 2, 6, 32, 32)
+    assert np.array_equal(got[:, 1], want[:, 1])
+    # slices outside [start-1, end] stay zero; generated slices are min-max normalised to [0, 1]
+    assert np.all(got[:, 0, 5] == 0) and got[:, 0, 1:5].min() >= 0 and got[:, 0, 1:5].max() <= 1
+    p = psnr(got[:, 0], want[:, 0])
+    print("pipeline PSNR vs oracle", p, "rel", rel(got[:, 0], want[:, 0]))
+    assert p >= 30.0
