@@ -1,14 +1,15 @@
 // attention.cu -- flash-style attention (no T x T buffer), bf16 in/out, fp32 online softmax.
 //   QKVAttentionLegacy (unet.py:343-360) and CrossAttention (ldm/modules/attention.py:170-193)
 // Generic strided heads: element (b, t, h, i) of q sits at q[b*q_bs + t*q_rs + h*q_hs + i].
-// One CTA = 64 query rows of one (batch, head); 4 warps x 16 rows; K/V streamed in 64-key
-// tiles through shared memory; S = QK^T and O += PV on mma.sync.m16n8k16 (bf16, fp32 acc).
+// One CTA = 128 query rows of one (batch, head); 8 warps x 16 rows; K/V streamed in 64-key tiles through
+// double-buffered shared memory (cp.async); S = QK^T and O += PV on mma.sync.m16n8k16 (bf16, fp32 acc).
 // Attention is ~0.3 % of the step's FLOPs at the reference shapes.
 #include "common.cuh"
 
 namespace gg {
 
 constexpr int ATT_BM = 64, ATT_BN = 64;
+constexpr int ATT_THREADS = 256;      // 8 warps x 16 query rows = 2 * ATT_BM rows per CTA
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -24,28 +25,48 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float ex2_fast(float x) {      // ex2.approx: 2 ulp, ex2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool pred) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int bytes = pred ? 16 : 0;      // src-size 0 -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// 128 query rows per CTA (8 warps x 16 rows); K/V tiles of 64 keys double-buffered with cp.async so the next
+// tile streams in while the current one is multiplied; rows past the sequence end are zero-filled.
 template <int D>
-__global__ void __launch_bounds__(128) attention_kernel(const gg_attn_args a) {
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const gg_attn_args a) {
     constexpr int LD = D + 8;  // padded row (elements): conflict-free ldmatrix
-    __shared__ __align__(16) __nv_bfloat16 sQ[ATT_BM * LD];
-    __shared__ __align__(16) __nv_bfloat16 sK[ATT_BN * LD];
-    __shared__ __align__(16) __nv_bfloat16 sV[ATT_BN * LD];
+    constexpr int NT = ATT_THREADS;
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
+    __nv_bfloat16* sKb = sQ + 2 * ATT_BM * LD;
+    __nv_bfloat16* sVb = sKb + 2 * ATT_BN * LD;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * ATT_BM, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * (2 * ATT_BM), h = blockIdx.y, b = blockIdx.z;
     const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + (int64_t)b * a.q_bs + (int64_t)h * a.q_hs;
     const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)b * a.k_bs + (int64_t)h * a.k_hs;
     const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)b * a.v_bs + (int64_t)h * a.v_hs;
     constexpr int CPR = D / 8;  // 16-byte chunks per row
 
-    auto load_tile = [&](__nv_bfloat16* dst, const __nv_bfloat16* src, int row0, int nrows, int rs) {
-        for (int i = tid; i < 64 * CPR; i += 128) {
+    auto load_tile = [&](__nv_bfloat16* dst, const __nv_bfloat16* src, int row0, int rows, int nrows, int rs) {
+        for (int i = tid; i < rows * CPR; i += NT) {
             const int r = i / CPR, c = i - r * CPR;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (row0 + r < nrows) v = *reinterpret_cast<const uint4*>(src + (int64_t)(row0 + r) * rs + c * 8);
-            *reinterpret_cast<uint4*>(dst + r * LD + c * 8) = v;
+            const bool ok = row0 + r < nrows;
+            cp_async16(dst + r * LD + c * 8, src + (int64_t)(ok ? row0 + r : 0) * rs + c * 8, ok);
         }
     };
-    load_tile(sQ, qg, q0, a.Tq, a.q_rs);
+    load_tile(sQ, qg, q0, 2 * ATT_BM, a.Tq, a.q_rs);
+    load_tile(sKb, kg, 0, ATT_BN, a.Tk, a.k_rs);
+    load_tile(sVb, vg, 0, ATT_BN, a.Tk, a.v_rs);
+    cp_async_commit();
+    cp_async_wait_all();
     __syncthreads();
 
     // Q fragments for this warp's 16 rows, all of D
@@ -64,11 +85,20 @@ __global__ void __launch_bounds__(128) attention_kernel(const gg_attn_args a) {
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     const float sl2 = a.scale * 1.4426950408889634f;
 
+    int buf = 0;
     for (int k0 = 0; k0 < a.Tk; k0 += ATT_BN) {
-        __syncthreads();  // previous tile fully consumed
-        load_tile(sK, kg, k0, a.Tk, a.k_rs);
-        load_tile(sV, vg, k0, a.Tk, a.v_rs);
-        __syncthreads();
+        if (k0 > 0) {
+            cp_async_wait_all();   // this tile's K/V have landed ...
+            __syncthreads();       // ... for every thread, and everyone is done with the buffer refilled next
+        }
+        const __nv_bfloat16* sK = sKb + buf * ATT_BN * LD;
+        const __nv_bfloat16* sV = sVb + buf * ATT_BN * LD;
+        if (k0 + ATT_BN < a.Tk) {
+            load_tile(sKb + (buf ^ 1) * ATT_BN * LD, kg, k0 + ATT_BN, ATT_BN, a.Tk, a.k_rs);
+            load_tile(sVb + (buf ^ 1) * ATT_BN * LD, vg, k0 + ATT_BN, ATT_BN, a.Tk, a.v_rs);
+            cp_async_commit();
+        }
+        buf ^= 1;
         // ---- S = Q K^T  (16 x 64 per warp)
         float s[ATT_BN / 8][4];
 #pragma unroll
@@ -99,14 +129,14 @@ __global__ void __launch_bounds__(128) attention_kernel(const gg_attn_args a) {
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const float c0 = exp2f((m0 - mn0) * sl2), c1 = exp2f((m1 - mn1) * sl2);
+        const float c0 = ex2_fast((m0 - mn0) * sl2), c1 = ex2_fast((m1 - mn1) * sl2);
         m0 = mn0; m1 = mn1;
         float rs0 = 0.f, rs1 = 0.f;
         uint32_t pf[ATT_BN / 16][4];
 #pragma unroll
         for (int j = 0; j < ATT_BN / 8; ++j) {
-            const float p0 = exp2f((s[j][0] - mn0) * sl2), p1 = exp2f((s[j][1] - mn0) * sl2);
-            const float p2 = exp2f((s[j][2] - mn1) * sl2), p3 = exp2f((s[j][3] - mn1) * sl2);
+            const float p0 = ex2_fast((s[j][0] - mn0) * sl2), p1 = ex2_fast((s[j][1] - mn0) * sl2);
+            const float p2 = ex2_fast((s[j][2] - mn1) * sl2), p3 = ex2_fast((s[j][3] - mn1) * sl2);
             rs0 += p0 + p1; rs1 += p2 + p3;
             pf[j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
             pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
@@ -155,8 +185,15 @@ extern "C" int gg_attention_fwd(const gg_attn_args* a, gg_stream_t stream) {
     GG_REQUIRE(a->q_hs % 8 == 0 && a->k_hs % 8 == 0 && a->v_hs % 8 == 0 && a->o_hs % 2 == 0, GG_ERR_ALIGNMENT);
     GG_REQUIRE(a->q_bs % 8 == 0 && a->k_bs % 8 == 0 && a->v_bs % 8 == 0 && a->o_bs % 2 == 0, GG_ERR_ALIGNMENT);
     GG_REQUIRE(a->H <= 65535 && a->B <= 65535, GG_ERR_UNSUPPORTED);
-    dim3 grid((a->Tq + ATT_BM - 1) / ATT_BM, a->H, a->B);
-    if (a->d == 32) attention_kernel<32><<<grid, 128, 0, as_stream(stream)>>>(*a);
-    else attention_kernel<64><<<grid, 128, 0, as_stream(stream)>>>(*a);
+    dim3 grid((a->Tq + 2 * ATT_BM - 1) / (2 * ATT_BM), a->H, a->B);
+    auto smem_for = [](int D) { return (size_t)(2 * ATT_BM + 4 * ATT_BN) * (D + 8) * sizeof(__nv_bfloat16); };
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(64));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    if (a->d == 32) attention_kernel<32><<<grid, ATT_THREADS, smem_for(32), as_stream(stream)>>>(*a);
+    else attention_kernel<64><<<grid, ATT_THREADS, smem_for(64), as_stream(stream)>>>(*a);
     return launch_result();
 }
