@@ -259,26 +259,36 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
     if ((dim & 1) && j == 0) emb[(int64_t)b * dim + dim - 1] = 0.f;
 }
 
-template <int MT>
+// one warp per output feature n: the weight row is read once (128-bit when K % 4 == 0), up to MT rows of x per pass
+template <int MT, bool VEC>
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ y, int M, int N,
                                                            int K, int act_in, int act_out) {
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
+    auto act = [&](float v) { return act_in ? v / (1.0f + expf(-v)) : v; };
     for (int m0 = 0; m0 < M; m0 += MT) {
         float acc[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) acc[m] = 0.f;
-        for (int k = lane; k < K; k += 32) {
-            const float wv = __ldg(w + (int64_t)n * K + k);
+        if (VEC) {
+            for (int k = lane * 4; k < K; k += 128) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (int64_t)n * K + k));
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                if (m0 + m < M) {
-                    float xv = __ldg(x + (int64_t)(m0 + m) * K + k);
-                    if (act_in) xv = xv / (1.0f + expf(-xv));
-                    acc[m] += xv * wv;
+                for (int m = 0; m < MT; ++m) {
+                    if (m0 + m < M) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (int64_t)(m0 + m) * K + k));
+                        acc[m] += act(xv.x) * wv.x + act(xv.y) * wv.y + act(xv.z) * wv.z + act(xv.w) * wv.w;
+                    }
                 }
+            }
+        } else {
+            for (int k = lane; k < K; k += 32) {
+                const float wv = __ldg(w + (int64_t)n * K + k);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    if (m0 + m < M) acc[m] += act(__ldg(x + (int64_t)(m0 + m) * K + k)) * wv;
             }
         }
 #pragma unroll
@@ -400,7 +410,14 @@ extern "C" int gg_small_linear(const float* x, const float* w, const float* b, f
                                int32_t act_in, int32_t act_out, gg_stream_t stream) {
     GG_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0, GG_ERR_BAD_ARG);
     const unsigned blocks = (unsigned)((N + 7) / 8);
-    if (M <= 4) small_linear_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(x, w, b, y, M, N, K, act_in, act_out);
-    else small_linear_kernel<16><<<blocks, 256, 0, as_stream(stream)>>>(x, w, b, y, M, N, K, act_in, act_out);
+    const bool vec = (K % 4 == 0) && aligned(x, 16) && aligned(w, 16);
+    cudaStream_t s = as_stream(stream);
+    if (M <= 4) {
+        if (vec) small_linear_kernel<4, true><<<blocks, 256, 0, s>>>(x, w, b, y, M, N, K, act_in, act_out);
+        else small_linear_kernel<4, false><<<blocks, 256, 0, s>>>(x, w, b, y, M, N, K, act_in, act_out);
+    } else {
+        if (vec) small_linear_kernel<16, true><<<blocks, 256, 0, s>>>(x, w, b, y, M, N, K, act_in, act_out);
+        else small_linear_kernel<16, false><<<blocks, 256, 0, s>>>(x, w, b, y, M, N, K, act_in, act_out);
+    }
     return launch_result();
 }

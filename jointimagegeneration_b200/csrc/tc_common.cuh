@@ -106,7 +106,8 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 // row software-prefetched one step ahead.  Every lane of the warp must call this (tcgen05.ld is warp-collective);
 // lanes whose output position is out of range pass valid = false.
 __device__ __forceinline__ void epilogue_row(uint32_t t_addr, int BN, int ncols, const float* __restrict__ bvec,
-                                             const __nv_bfloat16* __restrict__ res_row, void* y_row, int y_is_f32, bool valid) {
+                                             const __nv_bfloat16* __restrict__ res_row, void* y_row, int y_is_f32, bool valid,
+                                             const float* __restrict__ emb_row = nullptr) {
     uint4 rn[4];
     auto load_res = [&](int c0) {
 #pragma unroll
@@ -134,6 +135,10 @@ __device__ __forceinline__ void epilogue_row(uint32_t t_addr, int BN, int ncols,
             v[2] = __uint_as_float(r[8 * g + 2]) + b0.z; v[3] = __uint_as_float(r[8 * g + 3]) + b0.w;
             v[4] = __uint_as_float(r[8 * g + 4]) + b1.x; v[5] = __uint_as_float(r[8 * g + 5]) + b1.y;
             v[6] = __uint_as_float(r[8 * g + 6]) + b1.z; v[7] = __uint_as_float(r[8 * g + 7]) + b1.w;
+            if (emb_row != nullptr) {       // per-row additive vector (tiles that span samples): global, rare
+                const float4 e0 = __ldg(reinterpret_cast<const float4*>(emb_row + c)), e1 = __ldg(reinterpret_cast<const float4*>(emb_row + c + 4));
+                v[0] += e0.x; v[1] += e0.y; v[2] += e0.z; v[3] += e0.w; v[4] += e1.x; v[5] += e1.y; v[6] += e1.z; v[7] += e1.w;
+            }
             if (res_row != nullptr) {
                 const uint4 rr = rc[g];
                 v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
