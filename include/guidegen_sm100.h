@@ -259,10 +259,18 @@ typedef struct {
      * (shifted UMMA descriptors) -- 6x fewer A-operand bytes through shared memory.  Packed-weight K order for
      * algo 1 is  source -> 64-channel chunk -> tap -> channel. */
     int32_t algo;
+    /* Split-K (algo 0): layers whose output has fewer tiles than the GPU has SMs but a long reduction (the
+     * low-resolution 3^d convs) are cut into split_k K ranges; each (tile, range) work item writes raw fp32
+     * partial sums into workspace [split_k, N*Do*Ho*Wo, Cout8] (caller-owned) and a second launch sums them
+     * and applies bias / emb / residual.  split_k <= 1: off. */
+    int32_t split_k;
+    float* workspace;
 } gg_conv_args;
 
 /* N tile (accumulator columns) the kernel uses for a given Cout */
 int32_t gg_conv_pick_block_n(int32_t Cout);
+/* output tiles (128 positions x N tile) algo 0 will process for `a`: what split-K decisions are based on */
+int32_t gg_conv_num_tiles(const gg_conv_args* a);
 /* rows of gn_partial one launch of `a` fills per sample (4 per M tile), 0 if fused statistics are unsupported */
 int32_t gg_conv_stats_chunks(const gg_conv_args* a);
 /* K extent (columns) of the packed weight matrix for the sources / taps in `a` */

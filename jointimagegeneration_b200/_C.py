@@ -81,7 +81,7 @@ class ConvArgs(C.Structure):
                 ("y_sn", C.c_int64), ("y_sd", C.c_int64), ("y_sh", C.c_int64), ("y_sw", C.c_int64),
                 ("y_is_f32", C.c_int32), ("Cout", C.c_int32), ("block_n", C.c_int32), ("brick", C.c_int32 * 4),
                 ("gn_partial", C.c_void_p), ("gn_chunk_base", C.c_int32), ("gn_nchunks_total", C.c_int32),
-                ("stats_d_min", C.c_int32), ("algo", C.c_int32)]
+                ("stats_d_min", C.c_int32), ("algo", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p)]
 
 
 class AttnArgs(C.Structure):
@@ -116,6 +116,7 @@ SYMBOLS = {
     "gg_conv_pick_block_n": (_i32, [_i32]),
     "gg_conv_packed_k": (_i64, [C.POINTER(ConvArgs)]),
     "gg_conv_stats_chunks": (_i32, [C.POINTER(ConvArgs)]),
+    "gg_conv_num_tiles": (_i32, [C.POINTER(ConvArgs)]),
     "gg_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "gg_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "gg_attention_fwd": (C.c_int, [C.POINTER(AttnArgs), _vp]),

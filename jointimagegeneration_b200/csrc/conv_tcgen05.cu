@@ -56,6 +56,10 @@ struct alignas(64) ConvParams {
     // fused GroupNorm statistics of the (bf16-rounded) output: per (sample, M tile, epilogue warp) partial sums
     float* gn_partial;     // [N, gn_nchunks_total, Cout8, 2] or null
     int gn_chunk_base, gn_nchunks_total, stats_d_min;
+    // split-K: work item = (tile, split); each split accumulates a K range and writes raw fp32 partials
+    int split_k;
+    float* workspace;      // [split_k, No*Do*Ho*Wo, Cout8]
+    long long ws_split_stride;
 };
 
 // ------------------------------------------------------------------------------------ kernel
@@ -102,7 +106,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
         // the whole warp runs the loop (uniform control flow); one elected lane issues the copies
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < p.total_tiles * p.split_k; item += gridDim.x) {
+            const int tile = item / p.split_k, split = item - tile * p.split_k;
+            const int kb_lo = (int)((long long)p.num_kb * split / p.split_k), kb_hi = (int)((long long)p.num_kb * (split + 1) / p.split_k);
             const int nt = tile % p.n_tiles_n;
             int mt = tile / p.n_tiles_n;
             const int iw = mt % p.tw; mt /= p.tw;
@@ -128,6 +134,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
                                 od = sg.od + a; oh = sg.oh + b; ow = sg.ow + c;
                             }
                             for (int j = 0; j < sg.nchunks; ++j) {
+                                if (kb < kb_lo || kb >= kb_hi) { ++kb; continue; }      // another split's K block
                                 mbar_wait(&empty[stage], phase ^ 1u);
                                 if (elect_one()) {
                                     mbar_expect_tx(&full[stage], stage_bytes);
@@ -151,23 +158,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
         const uint32_t smem_base = smem_u32(smem);
         int stage = 0;
         uint32_t phase = 0, acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < p.total_tiles * p.split_k; item += gridDim.x) {
+            const int split = item % p.split_k;
+            const int kb_lo = (int)((long long)p.num_kb * split / p.split_k), kb_hi = (int)((long long)p.num_kb * (split + 1) / p.split_k);
             mbar_wait(&tempty[acc], acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                     const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + A_BYTES);
                     // +32 bytes per K=16 step inside the 128-byte swizzle atom (encoded >> 4)
-                    umma_bf16(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+                    umma_bf16(d_tmem, adesc, bdesc, idesc, kb != kb_lo ? 1u : 0u);
                     umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
                     umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
                     umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
                     umma_commit(&empty[stage]);
-                    if (kb == p.num_kb - 1) umma_commit(&tfull[acc]);
+                    if (kb == kb_hi - 1) umma_commit(&tfull[acc]);
                 }
                 __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -182,7 +191,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
         uint32_t acc = 0, acc_phase = 0;
         int cur_n = -1, cur_nt = -1;
         const int bvol = p.bd * p.bh * p.bw, bhw = p.bh * p.bw;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < p.total_tiles * p.split_k; item += gridDim.x) {
+            const int tile = item / p.split_k, split = item - tile * p.split_k;
             const int nt = tile % p.n_tiles_n;
             int mt = tile / p.n_tiles_n;
             const int iw = mt % p.tw; mt /= p.tw;
@@ -197,6 +207,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
             const long long lin = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
             const float* embp = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
 
+            if (p.split_k > 1) {
+                // raw fp32 partial sums of this K range -> workspace[split][position][channel]; bias / emb / residual
+                // are applied by splitk_reduce_kernel
+                if (cur_nt != -3) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    for (int c = (int)threadIdx.x - 64; c < BN; c += 128) bvec[c] = 0.f;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    cur_nt = -3;
+                }
+                const int ncols = min(BN, p.Cout8 - nt * BN);
+                float* w_row = p.workspace + (long long)split * p.ws_split_stride + lin * p.Cout8 + nt * BN;
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                epilogue_row(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16), BN, ncols, bvec, nullptr, w_row, 1, valid);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                acc ^= 1u;
+                if (acc == 0) acc_phase ^= 1u;
+                continue;
+            }
             if (p.gn_partial == nullptr) {
                 // fast path: additive vector staged in smem, residual prefetched, paired TMEM loads
                 const int vn = (p.bn == 1) ? mt : -2;              // sample whose emb is folded into bvec (-2: none)
@@ -326,6 +357,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
     }
 }
 
+// sum of the split-K partials + bias + emb + residual -> output (8 channels per thread)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const ConvParams p, long long npos) {
+    const int P8 = p.Cout8 >> 3;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npos * P8) return;
+    const long long lin = i / P8;
+    const int cg = (int)(i - lin * P8) * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < p.split_k; ++s) {
+        const float* wp = p.workspace + (long long)s * p.ws_split_stride + lin * p.Cout8 + cg;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(wp)), b = __ldg(reinterpret_cast<const float4*>(wp + 4));
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    long long t = lin;
+    const int w = (int)(t % p.Wo); t /= p.Wo;
+    const int h = (int)(t % p.Ho); t /= p.Ho;
+    const int d = (int)(t % p.Do); t /= p.Do;
+    const int n = (int)t;
+    if (p.bias) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += __ldg(p.bias + cg + e);
+    }
+    if (p.emb) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += __ldg(p.emb + (long long)n * p.emb_stride + cg + e);
+    }
+    if (p.residual) {
+        const uint4 rr = ldg_nc_u4(p.residual + lin * p.res_stride + cg);
+        v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+        v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+    }
+    const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw + cg;
+    if (p.y_is_f32) {
+        float* yp = reinterpret_cast<float*>(p.y) + yoff;
+        *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+}
+
 // -------------------------------------------------------------------------------- host side
 EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = []() -> EncodeTiledFn {
@@ -399,6 +472,17 @@ extern "C" int32_t gg_conv_pick_block_n(int32_t Cout) {
         if (waste < best_waste) { best_waste = waste; best = bn; }
     }
     return best;
+}
+
+extern "C" int32_t gg_conv_num_tiles(const gg_conv_args* a) {
+    if (!a || a->Do <= 0 || a->Ho <= 0 || a->Wo <= 0 || a->Cout <= 0) return 0;
+    int brick[4];
+    if (a->brick[0] > 0) { for (int i = 0; i < 4; ++i) brick[i] = a->brick[i]; }
+    else pick_brick(a->N, a->Do, a->Ho, a->Wo, brick);
+    const int BN = a->block_n > 0 ? a->block_n : gg_conv_pick_block_n(a->Cout);
+    const int64_t t = (int64_t)((a->N + brick[0] - 1) / brick[0]) * ((a->Do + brick[1] - 1) / brick[1]) * ((a->Ho + brick[2] - 1) / brick[2]) *
+                      ((a->Wo + brick[3] - 1) / brick[3]) * ((a->Cout + BN - 1) / BN);
+    return (int32_t)std::min<int64_t>(t, 1 << 30);
 }
 
 extern "C" int32_t gg_conv_stats_chunks(const gg_conv_args* a) {
@@ -551,7 +635,20 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    const int grid = std::min(p.total_tiles, num_sms());
+    p.split_k = 1;
+    if (a->split_k > 1) {
+        GG_REQUIRE(a->workspace != nullptr && aligned(a->workspace, 16) && a->gn_partial == nullptr, GG_ERR_BAD_ARG);
+        GG_REQUIRE(a->split_k <= num_kb, GG_ERR_BAD_ARG);
+        p.split_k = a->split_k;
+        p.workspace = a->workspace;
+        p.ws_split_stride = (long long)a->N * a->Do * a->Ho * a->Wo * p.Cout8;
+    }
+    const int grid = (int)std::min<int64_t>((int64_t)p.total_tiles * p.split_k, num_sms());
     conv_tcgen05_kernel<<<grid, NUM_THREADS, smem, as_stream(stream)>>>(p);
+    int st = launch_result();
+    if (st != GG_OK || p.split_k == 1) return st;
+    const long long npos = (long long)a->N * a->Do * a->Ho * a->Wo;
+    const long long nthr = npos * (p.Cout8 / 8);
+    splitk_reduce_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, as_stream(stream)>>>(p, npos);
     return launch_result();
 }

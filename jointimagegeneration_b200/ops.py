@@ -249,7 +249,7 @@ def pad_vec(v: Optional[torch.Tensor], n: int) -> Optional[torch.Tensor]:
 
 def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=None, emb=None, residual=None,
                    taps=None, offsets=None, out_spatial=None, y_strides=None, block_n=0, brick=None, d_shift=0,
-                   y_f32=False, algo=0) -> _C.ConvArgs:
+                   y_f32=False, algo=0, split_k=0, workspace=None) -> _C.ConvArgs:
     """srcs: list of (CL tensor [N, D, H, W, C], centre_only).  y: CL tensor [N, Do, Ho, Wo, >= Cout8]
     (bf16 or fp32).  Returns the filled gg_conv_args (keeps nothing alive: the caller owns the tensors)."""
     a = _C.ConvArgs()
@@ -294,6 +294,8 @@ def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=Non
     a.y_is_f32 = int(y_f32) if isinstance(y, int) else int(y.dtype == torch.float32)
     a.Cout = cout
     a.algo = algo
+    a.split_k = split_k
+    a.workspace = _C.ptr(workspace)
     a.block_n = block_n
     if brick is not None:
         for i in range(4):

@@ -165,6 +165,9 @@ class UNetEngine:
         self.num_head_channels = num_head_channels
         self.fused_upsample = fused_upsample
         self.use_halo_conv = True
+        self.use_split_k = True
+        self.num_sms = torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count \
+            if next(model.parameters()).is_cuda else 148
         self.fused_gn_stats = False     # GroupNorm statistics from the conv epilogue: correct, but the extra epilogue
                                         # work costs more than the separate (cached) statistics pass saves on B200
         self.slab = None            # sharding.SlabComm: depth-slab decomposition of ONE volume over ranks
@@ -323,6 +326,15 @@ class UNetEngine:
                 a.stats_d_min = 1 if kernel_out_sp != tuple(out_spatial) else 0
         kexp = ops.conv_packed_k(a)
         assert kexp == w_packed.shape[1], (kexp, tuple(w_packed.shape))
+        if algo == 0 and self.use_split_k and a.gn_partial is None:
+            # few output tiles, long reduction (low-resolution layers): spread K ranges over the idle SMs
+            tiles, nkb = int(self.lib.gg_conv_num_tiles(C.byref(a))), kexp // ops.BLOCK_K
+            S = min(16, self.num_sms // max(tiles, 1), nkb // 6)
+            if tiles * 2 <= self.num_sms and S >= 2:
+                ws = ar.alloc((S, N * int(math.prod(kernel_out_sp)), cout8), torch.float32)
+                a.split_k, a.workspace = S, _C.ptr(ws)
+                plan.keep.append(ws)
+                ar.release(ws)          # stream order: the reduce launch of this conv is done before any later kernel
         plan.keep.append(a)
         plan.add(self.lib.gg_conv_fwd, C.byref(a))
         plan.flops += 2 * N * int(math.prod(out_spatial)) * cout * w_packed.shape[1]

@@ -232,7 +232,7 @@ def test_group_norm_silu(ops, N, sp, C1, C2, silu, eps):
 
 # ------------------------------------------------------------------------------ convolution
 def _conv_case(ops, N, sp, Cs, Cout, dims, k=3, stride=1, bias=True, emb=False, residual=False, extra_C=0, f32_out=False,
-               seed=0, block_n=0, brick=None, algo=0):
+               seed=0, block_n=0, brick=None, algo=0, split_k=0):
     no_tf32()
     rs = np.random.RandomState(seed)
     sp3 = (1,) * (3 - len(sp)) + tuple(sp)
@@ -257,8 +257,9 @@ def _conv_case(ops, N, sp, Cs, Cout, dims, k=3, stride=1, bias=True, emb=False, 
     e = torch.from_numpy(rs.standard_normal((N, Cout8)).astype(np.float32)).cuda() if emb else None
     r = torch.from_numpy(rs.standard_normal((N,) + osp + (Cout8,)).astype(np.float32)).cuda().to(torch.bfloat16) if residual else None
     y = torch.full((N,) + osp + (Cout8,), float("nan"), dtype=torch.float32 if f32_out else torch.bfloat16, device="cuda")
+    ws = torch.full((max(split_k, 1), N * osp[0] * osp[1] * osp[2], Cout8), float("nan"), device="cuda") if split_k > 1 else None
     a = ops.make_conv_args(srcs, wp, Cout, y, dims=dims, ksize=k, stride=stride, bias=ops.pad_vec(b, Cout), emb=e,
-                           residual=r, block_n=block_n, brick=brick, algo=algo)
+                           residual=r, block_n=block_n, brick=brick, algo=algo, split_k=split_k, workspace=ws)
     assert ops.conv_packed_k(a) == wp.shape[1]
     ops.conv_fwd(a)
     torch.cuda.synchronize()
@@ -284,6 +285,11 @@ CONV_CASES = {
     "conv3d_many_tiles": dict(N=2, sp=(16, 32, 32), Cs=[128], Cout=128, dims=3, residual=True),
     "conv3d_tiny_spatial": dict(N=3, sp=(2, 2, 2), Cs=[320, 320], Cout=320, dims=3, emb=True),
     "conv2d_bn64_brick": dict(N=1, sp=(32, 32), Cs=[64], Cout=64, dims=2, block_n=64, brick=(1, 1, 8, 16)),
+    # split-K (general kernel)
+    "splitk_tiny_spatial": dict(N=3, sp=(2, 2, 2), Cs=[320, 320], Cout=320, dims=3, emb=True, residual=True, split_k=5),
+    "splitk_2d_4x4": dict(N=16, sp=(4, 4), Cs=[800], Cout=800, dims=2, emb=True, split_k=8),
+    "splitk_stride2": dict(N=1, sp=(8, 8, 8), Cs=[128], Cout=128, dims=3, stride=2, split_k=3),
+    "splitk_f32": dict(N=1, sp=(8, 8), Cs=[64], Cout=12, dims=2, f32_out=True, split_k=2),
     # halo-brick kernel (algo 1)
     "halo3d_64": dict(N=1, sp=(4, 16, 16), Cs=[64], Cout=64, dims=3, algo=1),
     "halo3d_all": dict(N=2, sp=(3, 32, 24), Cs=[128, 64], Cout=64, dims=3, extra_C=192, emb=True, algo=1),
