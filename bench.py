@@ -35,6 +35,10 @@ WORKLOADS = {
                       desc="CCDM mask sampler 128x128x64 (tensor [8,12,64,128,128]), 12 classes, 1000-step chain, batch 8, bf16"),
     "ccdm_cfg1": dict(spatial=(32, 32, 32), C=12, batch=1, T=10, flop_per_sample=1.97e11,
                       desc="CCDM mask sampler 32x32x32, 12 classes, 10 steps, batch 1"),
+    "ccdm_cfg2_text": dict(spatial=(64, 128, 128), C=12, batch=8, T=1000, flop_per_sample=6.324e12, text=True,
+                           desc="CCDM TEXT-CONDITIONED mask sampler 128x128x64, 12 classes, batch 8, bf16: attention sites are "
+                                "SpatialTransformer blocks (self-attn + cross-attn to a [8,512,768] BERT-like context + GEGLU FF); the "
+                                "reference declares but cannot construct this network (SURVEY.md D1/D2), so there is no reference arm"),
     "ccdm_cfg5": dict(spatial=(128, 256, 256), C=12, batch=1, T=1000, flop_per_sample=5.182e13, attn_flop=1.41e12, slab=True,
                       desc="CCDM mask sampler, ONE 256x256x128 volume (tensor [1,12,128,256,256]) split into depth slabs over the "
                            "GPUs: halo exchange per 3x3x3 conv, GroupNorm partial-sum gather, attention K/V gather (NCCL)"),
@@ -155,7 +159,11 @@ def run_ours(args):
     V = sp[0] * sp[1] * sp[2]
 
     torch.manual_seed(1234 + rank)
-    model = build_model(T, "cosine", {"s": 0.008}, [(1,) + sp, (Cc,) + sp], None, "unet_openai", dict(CCDM_NET), "synthetic",
+    net = dict(CCDM_NET)
+    context = None
+    if wl.get("text"):
+        net.update(use_spatial_transformer=True, transformer_depth=1, context_dim=768)
+    model = build_model(T, "cosine", {"s": 0.008}, [(1,) + sp, (Cc,) + sp], None, "unet_openai", net, "synthetic",
                         "majority", dims=3)
     randomize_zero_modules(model.unet, 7)
     model = model.to(dev).eval()
@@ -177,7 +185,9 @@ def run_ours(args):
     cond = torch.zeros((B, 1) + sp, dtype=torch.float32, device=dev)          # ruijin.py:181-182: zeros
     t_values = list(range(T, 0, -1))
     coefs = model.diffusion.step_coef_tensor(torch.tensor(t_values)).to(dev)[:, None, :].expand(-1, B, -1).contiguous()
-    st = model.resident_begin(x_T, cond)
+    if wl.get("text"):
+        context = torch.randn((B, 512, 768), device=dev)
+    st = model.resident_begin(x_T, cond, context)
     plan = st["plan"]
 
     def step(i):
@@ -215,7 +225,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    res = model(x_host, c_host, t=torch.tensor(10000 + Ke))["diffusion_out"]   # reference's own K-step knob (:190-197)
+    res = model(x_host, c_host, t=torch.tensor(10000 + Ke), context=context)["diffusion_out"]   # reference's own K-step knob (:190-197)
     out_host.copy_(res, non_blocking=False)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
