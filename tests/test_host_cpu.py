@@ -196,6 +196,27 @@ back = sharding.gather_batch(mine * 2, 5)
 assert torch.equal(back, full * 2)
 mn, mx = sharding.global_minmax(mine)
 assert (mn, mx) == (0.0, 14.0)
+# depth-slab communication (config 5): halo planes from the neighbours, zeros at the ends of the volume
+comm = sharding.SlabComm()
+lead, D = 2, 3
+t = torch.full((1, lead + D + 1, 2, 2, 4), -7.0)
+t[0, lead:lead + D] = torch.arange(D, dtype=torch.float32).reshape(D, 1, 1, 1) + 10 * (r + 1)
+comm.exchange_halo(t, lead, D)
+lo, hi = t[0, lead - 1], t[0, lead + D]
+if r == 0:
+    assert torch.all(lo == 0) and torch.all(hi == 20.0)          # rank 1's first interior plane
+else:
+    assert torch.all(lo == 12.0) and torch.all(hi == 0)          # rank 0's last interior plane
+assert torch.all(t[0, 0] == -7.0)                                # spare plane untouched
+t2 = torch.full_like(t, -7.0)
+t2[0, lead:lead + D] = t[0, lead:lead + D]
+comm.exchange_halo(t2, lead, D, need_lo=True, need_hi=False)     # what a stride-2 conv asks for
+assert torch.all(t2[0, lead + D] == -7.0) and torch.all(t2[0, lead - 1] == (0.0 if r == 0 else 12.0))
+part = torch.full((1, 2, 4, 2), float(r + 1))
+g = torch.empty((1, 4, 4, 2))
+comm.all_gather(g, part)
+assert torch.all(g[0, :2] == 1.0) and torch.all(g[0, 2:] == 2.0)
+assert comm.n_exchanges == 2 and comm.n_gathers == 1
 dist.barrier()
 dist.destroy_process_group()
 print("ok", r)
