@@ -348,6 +348,9 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
+        model.unet.invalidate()           # drop plans (and any CUDA graph holding NCCL work) before the communicator
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -181,7 +181,7 @@ class DenoisingModel(nn.Module):
             step0 = 0
         unet = self.unet
         plan = unet.plan_for(B, spatial, context)
-        if self.use_cuda_graph and plan.graph is None and not plan.has_py:
+        if self.use_cuda_graph and plan.graph is None:
             plan.capture()
         if "context" in plan.inputs:
             plan.inputs["context"].copy_(unet._ctx_cl(context, B))
@@ -240,7 +240,7 @@ class DenoisingModel(nn.Module):
         if "context" in plan.inputs:
             plan.inputs["context"].copy_(unet._ctx_cl(context, B))
         xin = plan.inputs["x"]
-        if self.use_cuda_graph and plan.graph is None and not plan.has_py:
+        if self.use_cuda_graph and plan.graph is None:
             plan.capture()
         ops.nchw_to_cl(xt, cond, c_pad=unet.in_channels_padded, out=xin)
         lab_a = torch.empty((B * V,), dtype=torch.uint8, device=dev)
