@@ -316,7 +316,7 @@ def run_ours(args):
         cat_ms = kinds["gg_cat_step_cl"][0]
         alg_b = 50.0 * B * V
         act_b = (64 + 1 + 1 + 2 * plan.inputs["x"].shape[-1] + 2) * B * V
-        line["roofline_hbm_resident"] = {"bound": "hbm", "kernel": "cat_step_cl_kernel (softmax + posterior + clamp + Philox draw + next input)",
+        line["roofline_hbm_resident"] = {"bound": "hbm", "kernel": "cat_step_cl_fast_kernel (softmax + posterior + clamp + Philox inverse-CDF draw + next input)",
                                          "achieved": alg_b / (cat_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                          "frac": alg_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
                                          "algorithmic_bytes": alg_b, "moved_bytes": act_b,

@@ -99,8 +99,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int tiles_per_n = p.td * p.th * p.tw;
-
     if (warp == 0) {
         // ================================================================ TMA producer
         // the whole warp runs the loop (uniform control flow); one elected lane issues the copies
@@ -441,7 +439,6 @@ bool encode_w_map(CUtensorMap* m, const void* base, int64_t Ktot, int rows, int 
     return r == CUDA_SUCCESS;
 }
 
-static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 static int pow2_ceil(int v) { int r = 1; while (r < v) r *= 2; return r; }
 
 // brick of 128 output positions: as much W as possible, then H, D, N (powers of two)

@@ -394,6 +394,107 @@ __global__ void __launch_bounds__(256) cat_step_cl_kernel(const gg_cat_step_cl_a
     }
 }
 
+// Production form of the same step (noise from the in-kernel generator, no probs_out): HBM-bound.
+//  * a quad of lanes owns FOUR consecutive voxels: one Philox4x32-10 call yields their four uniforms, the
+//    uint8 labels move as one 32-bit word, index math / coefficient loads are amortised 4x;
+//  * x_t is one-hot, so the posterior has only two distinct denominators per voxel (class == label or not):
+//    two reciprocals replace C divisions, and the softmax normaliser cancels in the draw;
+//  * the draw is an inverse-CDF categorical sample with ONE uniform per voxel (scan over the class axis by
+//    warp shuffles) instead of the C-variate exponential race torch.multinomial uses -- same distribution,
+//    1/12 of the random numbers and no logarithms.  (The injected-noise path above keeps the race so that
+//    labels can be compared with the reference draw for draw.)
+__global__ void __launch_bounds__(256) cat_step_cl_fast_kernel(const gg_cat_step_cl_args a) {
+    const int b = blockIdx.y;
+    const int sub = threadIdx.x & 3;
+    const int64_t v0 = ((int64_t)blockIdx.x * 64 + (threadIdx.x >> 2)) * 4;     // first of this quad's 4 voxels
+    const bool live = v0 < a.V;
+    const int64_t vb = (int64_t)b * a.V + (live ? v0 : 0);
+    const int C = a.C;
+    float4 lg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lg[j] = ldg_nc_f4(a.logits + (vb + j) * 16 + 4 * sub);
+    const uint32_t labs = __ldg(reinterpret_cast<const uint32_t*>(a.labels_in + vb));
+    const float al = __ldg(a.coef + 2 * b), g = __ldg(a.coef + 2 * b + 1);
+    const float k = (1.0f - al) / (float)C, h = (1.0f - g) / (float)C;
+    const float hU = h * (al + (float)C * k);
+    const float inv_lab = __fdividef(1.0f, fmaf(g, al + k, hU)), inv_oth = __fdividef(1.0f, fmaf(g, k, hU));
+    const uint64_t gq = ((uint64_t)vb + (uint64_t)a.vox_base) >> 2;             // global index of this group of 4 voxels
+    const uint4 rr = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), (uint32_t)a.offset, (uint32_t)(a.offset >> 32)),
+                                   make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+    const uint32_t rbits[4] = {rr.x, rr.y, rr.z, rr.w};
+    const bool pad[4] = {4 * sub + 0 >= C, 4 * sub + 1 >= C, 4 * sub + 2 >= C, 4 * sub + 3 >= C};
+    uint32_t lab_out = 0;
+    const uint16_t* cond = reinterpret_cast<const uint16_t*>(a.cond);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float l[4] = {lg[j].x, lg[j].y, lg[j].z, lg[j].w};
+        float m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { if (pad[e]) l[e] = -INFINITY; m = fmaxf(m, l[e]); }
+        m = quad_max(m);
+        const int lab = (int)((labs >> (8 * j)) & 255u);
+        float ex[4], r[4], u[4], se = 0.f, R = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool is_lab = (4 * sub + e) == lab;
+            ex[e] = __expf(l[e] - m);                       // 0 for padding classes
+            se += ex[e];
+            u[e] = (is_lab ? al : 0.f) + k;
+            r[e] = ex[e] * (is_lab ? inv_lab : inv_oth);    // un-normalised softmax: 1/sum(ex) is a common factor
+            R += r[e];
+        }
+        se = quad_sum(se);
+        R = quad_sum(R);
+        const float hR = h * R, floor_p = a.clamp_min * se; // clamp(p / se, min) == max(p, min * se) / se
+        float cum[4], run = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float pe = pad[e] ? 0.f : fmaxf(u[e] * fmaf(g, r[e], hR), floor_p);
+            run += pe;
+            cum[e] = run;
+        }
+        // inclusive scan of the lane totals over the quad, then the voxel total
+        float inc = run;
+        float t = __shfl_up_sync(0xffffffffu, inc, 1, 4); if (sub >= 1) inc += t;
+        t = __shfl_up_sync(0xffffffffu, inc, 2, 4); if (sub >= 2) inc += t;
+        const float excl = inc - run;
+        const float P = __shfl_sync(0xffffffffu, inc, 3, 4);
+        const float target = ((float)(rbits[j] >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f)) * P;
+        int cand = 99;
+#pragma unroll
+        for (int e = 3; e >= 0; --e)
+            if (!pad[e] && excl + cum[e] >= target) cand = 4 * sub + e;
+        cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, 1));
+        cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, 2));
+        const int bi = cand == 99 ? C - 1 : cand;           // target rounded above the last partial sum
+        lab_out |= (uint32_t)bi << (8 * j);
+    }
+    if (live && a.next_x != nullptr) {
+        // next UNet input rows: one-hot(C) | cond | zero pad (bf16).  Lane `sub` writes the whole row of voxel
+        // v0 + sub (every lane of the quad holds all four labels), 16-byte stores, 128 contiguous bytes per quad
+        const int bi = (int)((lab_out >> (8 * sub)) & 255u);
+        uint16_t* row = reinterpret_cast<uint16_t*>(a.next_x) + (vb + sub) * a.Cin_pad;
+        for (int c0 = 0; c0 < a.Cin_pad; c0 += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = c0 + 2 * e;
+                uint32_t bits = (c == (bi & ~1)) ? ((bi & 1) ? 0x3F800000u : 0x3F80u) : 0u;
+                if (c + 1 >= C && cond != nullptr) {       // pair touches the condition channels
+#pragma unroll
+                    for (int z = 0; z < 2; ++z) {
+                        const int cc = c + z - C;
+                        if (cc >= 0 && cc < a.n_cond) bits |= (uint32_t)cond[(vb + sub) * a.n_cond + cc] << (16 * z);
+                    }
+                }
+                w[e] = bits;
+            }
+            *reinterpret_cast<uint4*>(row + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    if (live && sub == 0) *reinterpret_cast<uint32_t*>(a.labels_out + vb) = lab_out;
+}
+
 // ------------------------------------------------------------------------------------------
 // K14  DDIM update
 // ------------------------------------------------------------------------------------------
@@ -596,6 +697,12 @@ extern "C" int gg_cat_step_cl(const gg_cat_step_cl_args* a, gg_stream_t stream) 
         GG_REQUIRE(aligned(a->next_x, 16), GG_ERR_ALIGNMENT);
     }
     GG_REQUIRE(a->B <= 65535, GG_ERR_UNSUPPORTED);
+    if (a->q == nullptr && a->probs_out == nullptr && a->mode == GG_CAT_SAMPLE && a->V % 4 == 0 && aligned(a->labels_in, 4) &&
+        aligned(a->labels_out, 4)) {
+        const dim3 fblocks((unsigned)((a->V / 4 + 63) / 64), (unsigned)a->B);
+        cat_step_cl_fast_kernel<<<fblocks, 256, 0, as_stream(stream)>>>(*a);
+        return launch_result();
+    }
     const dim3 blocks((unsigned)((a->V + 63) / 64), (unsigned)a->B);
     cat_step_cl_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*a);
     return launch_result();

@@ -377,3 +377,43 @@ def test_layernorm_geglu_upsample(ops):
     got2 = ops.upsample2x(u[:, :1].contiguous(), 2)
     want2 = torch.nn.functional.interpolate(nchw_from_cl(u[:, :1])[:, :, 0], scale_factor=2, mode="nearest")
     assert torch.equal(nchw_from_cl(got2)[:, :, 0], want2)
+
+
+def test_cat_step_cl_fast_path_distribution_and_slab_invariance(ops):
+    """Production per-voxel kernel (in-kernel Philox, inverse-CDF draw): (i) the empirical label
+    distribution over 2^20 identical voxels matches the oracle posterior, (ii) labels depend only on
+    (seed, offset, GLOBAL voxel index): a half-volume call with vox_base reproduces the full call,
+    (iii) the next-input row is the one-hot of the drawn label plus the condition channel."""
+    from oracle import diffusion
+    C, V, t = 12, 1 << 20, 300
+    _, alphas, cumalphas = diffusion.cosine_schedule(1000)
+    a, g = diffusion.step_coefficients(alphas, cumalphas, t)
+    rs = np.random.RandomState(8)
+    row = (rs.standard_normal(16) * 1.5).astype(np.float32)
+    logits = torch.from_numpy(np.tile(row, (V, 1))).cuda()
+    lab_in = torch.full((V,), 5, dtype=torch.uint8, device="cuda")
+    coef = torch.tensor([[a, g]], dtype=torch.float32).cuda()
+    cond = torch.full((V, 1), 0.25, dtype=torch.bfloat16, device="cuda")
+    out = torch.empty(V, dtype=torch.uint8, device="cuda")
+    nx = torch.empty((V, 16), dtype=torch.bfloat16, device="cuda")
+    ops.cat_step_cl(logits, lab_in, coef, out, 1, V, C, cond=cond, n_cond=1, next_x=nx, seed=3, offset=17)
+    x0 = torch.softmax(torch.from_numpy(row[:C]), 0).numpy().reshape(C, 1)
+    xt = np.eye(C, dtype=np.float32)[5].reshape(C, 1)
+    p = np.maximum(diffusion.theta_post_prob_closed(a, g, xt, x0)[:, 0], 1e-12)
+    p = p / p.sum()
+    hist = torch.bincount(out.long(), minlength=C).cpu().numpy() / V
+    # binomial standard error at 2^20 draws is <= 5e-4; allow 5 sigma
+    assert np.abs(hist - p).max() <= 2.5e-3, (hist, p)
+    nxf = nx.float().cpu().numpy()
+    assert np.array_equal(nxf[:, :C].argmax(1), out.cpu().numpy()) and np.all(nxf[:, :C].sum(1) == 1)
+    assert np.all(nxf[:, C] == 0.25) and np.all(nxf[:, C + 1:] == 0)
+    # determinism and dependence on the global voxel index only
+    out2 = torch.empty_like(out)
+    ops.cat_step_cl(logits, lab_in, coef, out2, 1, V, C, cond=cond, n_cond=1, seed=3, offset=17)
+    assert torch.equal(out, out2)
+    half = V // 2
+    out3 = torch.empty(half, dtype=torch.uint8, device="cuda")
+    ops.cat_step_cl(logits[half:], lab_in[half:], coef, out3, 1, half, C, cond=cond[half:], n_cond=1, seed=3, offset=17, vox_base=half)
+    assert torch.equal(out3, out[half:])
+    ops.cat_step_cl(logits, lab_in, coef, out2, 1, V, C, seed=3, offset=18)
+    assert not torch.equal(out, out2)
