@@ -62,7 +62,64 @@ struct alignas(64) HaloParams {
     void* y;
     long long y_sn, y_sd, y_sh, y_sw;
     int y_is_f32;
+    float* gn_partial;             // fused GroupNorm statistics (BN == Cout8 == 64): [N, gn_nchunks_total, 64, 2]
+    int gn_chunk_base, gn_nchunks_total;
 };
+
+// Epilogue of one row for the BN = 64 statistics variant: as epilogue_row, plus per-thread running sums of the
+// stored (bf16-rounded) values per column, kept in registers across all tiles of a sample.
+__device__ __forceinline__ void epilogue_row_stats64(uint32_t t_addr, const float* __restrict__ bvec,
+                                                     const __nv_bfloat16* __restrict__ res_row, __nv_bfloat16* y_row, bool valid,
+                                                     float (&s1)[64], float (&s2)[64]) {
+    uint32_t r[64];
+    tmem_ld16_nowait(t_addr, r);
+    tmem_ld16_nowait(t_addr + 16, r + 16);
+    tmem_ld16_nowait(t_addr + 32, r + 32);
+    tmem_ld16_nowait(t_addr + 48, r + 48);
+    uint4 rr[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) rr[g] = (res_row != nullptr && valid) ? ldg_nc_u4(res_row + 8 * g) : make_uint4(0, 0, 0, 0);
+    tmem_ld_wait();
+    if (!valid) return;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bvec + 8 * g), b1 = *reinterpret_cast<const float4*>(bvec + 8 * g + 4);
+        float v[8];
+        v[0] = __uint_as_float(r[8 * g + 0]) + b0.x + bf16_lo(rr[g].x); v[1] = __uint_as_float(r[8 * g + 1]) + b0.y + bf16_hi(rr[g].x);
+        v[2] = __uint_as_float(r[8 * g + 2]) + b0.z + bf16_lo(rr[g].y); v[3] = __uint_as_float(r[8 * g + 3]) + b0.w + bf16_hi(rr[g].y);
+        v[4] = __uint_as_float(r[8 * g + 4]) + b1.x + bf16_lo(rr[g].z); v[5] = __uint_as_float(r[8 * g + 5]) + b1.y + bf16_hi(rr[g].z);
+        v[6] = __uint_as_float(r[8 * g + 6]) + b1.z + bf16_lo(rr[g].w); v[7] = __uint_as_float(r[8 * g + 7]) + b1.w + bf16_hi(rr[g].w);
+        const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        *reinterpret_cast<uint4*>(y_row + 8 * g) = pk;
+        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+            s1[8 * g + 2 * e] += lo; s2[8 * g + 2 * e] = fmaf(lo, lo, s2[8 * g + 2 * e]);
+            s1[8 * g + 2 * e + 1] += hi; s2[8 * g + 2 * e + 1] = fmaf(hi, hi, s2[8 * g + 2 * e + 1]);
+        }
+    }
+}
+
+// sum the 64 per-thread column sums over the 32 lanes of a warp (butterfly reduce-scatter: 62 shuffles per
+// quantity, once per (CTA, sample)); lane l ends with columns 2l, 2l+1 and writes them to the partial row
+__device__ __forceinline__ void flush_stats64(float (&s1)[64], float (&s2)[64], float* __restrict__ dst, int lane) {
+#pragma unroll
+    for (int half = 32; half >= 2; half >>= 1) {
+        const int m = half >> 1;          // lane mask 16, 8, 4, 2, 1
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float k1 = up ? s1[i + half] : s1[i], x1 = up ? s1[i] : s1[i + half];
+            const float k2 = up ? s2[i + half] : s2[i], x2 = up ? s2[i] : s2[i + half];
+            s1[i] = k1 + __shfl_xor_sync(0xffffffffu, x1, m);
+            s2[i] = k2 + __shfl_xor_sync(0xffffffffu, x2, m);
+        }
+    }
+    *reinterpret_cast<float4*>(dst + 4 * lane) = make_float4(s1[0], s2[0], s1[1], s2[1]);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+}
 
 __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -74,7 +131,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t
     return d;
 }
 
-template <int G>
+template <int G, bool STATS>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -245,6 +302,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         const int etid = threadIdx.x - 64;             // 0..127 among the epilogue warps
         uint32_t acc = 0, acc_phase = 0;
         int cur_n = -1, cur_nt = -1;
+        float s1[STATS ? 64 : 1], s2[STATS ? 64 : 1];
+        int stat_n = -1;
+        if (STATS) {
+#pragma unroll
+            for (int i = 0; i < (STATS ? 64 : 1); ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        }
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles_n;
             int mt = tile / p.n_tiles_n;
@@ -276,12 +339,27 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * H_ACC_COLS + ((uint32_t)(q * 32) << 16);
-            epilogue_row(t_addr, BN, ncols, bvec, res_row, y_row, p.y_is_f32, valid);
+            if constexpr (STATS) {
+                if (n != stat_n) {         // tiles are ordered by sample: flush the finished sample's sums
+                    if (stat_n >= 0)
+                        flush_stats64(s1, s2, p.gn_partial + (((long long)stat_n * p.gn_nchunks_total + p.gn_chunk_base +
+                                                                (long long)blockIdx.x * 4 + q) * 64) * 2, lane);
+                    stat_n = n;
+                }
+                epilogue_row_stats64(t_addr, bvec, res_row, reinterpret_cast<__nv_bfloat16*>(y_row), valid, s1, s2);
+            } else {
+                epilogue_row(t_addr, BN, ncols, bvec, res_row, y_row, p.y_is_f32, valid);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;
+        }
+        if constexpr (STATS) {
+            if (stat_n >= 0)
+                flush_stats64(s1, s2, p.gn_partial + (((long long)stat_n * p.gn_nchunks_total + p.gn_chunk_base +
+                                                        (long long)blockIdx.x * 4 + q) * 64) * 2, lane);
         }
     }
 
@@ -297,7 +375,6 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
 int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     GG_REQUIRE(a->stride == 1, GG_ERR_UNSUPPORTED);
     GG_REQUIRE(a->nsrc >= 1 && a->nsrc <= H_MAX_SEGS, GG_ERR_BAD_ARG);
-    GG_REQUIRE(a->gn_partial == nullptr, GG_ERR_UNSUPPORTED);
     if (!encode_fn()) return GG_ERR_DRIVER;
     HaloParams p;
     memset(&p, 0, sizeof(p));
@@ -367,16 +444,33 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
+        cudaError_t e = cudaSuccess;
+        auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET); };
+        set((const void*)conv_halo_kernel<1, false>); set((const void*)conv_halo_kernel<2, false>); set((const void*)conv_halo_kernel<3, false>);
+        set((const void*)conv_halo_kernel<1, true>); set((const void*)conv_halo_kernel<2, true>); set((const void*)conv_halo_kernel<3, true>);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     const int grid = std::min(p.total_tiles, num_sms());
-    if (G == 3) conv_halo_kernel<3><<<grid, H_THREADS, smem, stream>>>(p);
-    else if (G == 2) conv_halo_kernel<2><<<grid, H_THREADS, smem, stream>>>(p);
-    else conv_halo_kernel<1><<<grid, H_THREADS, smem, stream>>>(p);
+    if (a->gn_partial != nullptr) {
+        // fused GroupNorm statistics: one partial row per (CTA, epilogue warp) and sample; CTAs that never touch a
+        // sample leave zeros, so the rows are cleared first (a memset node under graph capture)
+        GG_REQUIRE(BN == 64 && p.Cout8 == 64 && p.n_tiles_n == 1 && !a->y_is_f32, GG_ERR_UNSUPPORTED);
+        GG_REQUIRE(aligned(a->gn_partial, 16) && a->gn_chunk_base >= 0 && a->gn_chunk_base + grid * 4 <= a->gn_nchunks_total, GG_ERR_BAD_ARG);
+        p.gn_partial = a->gn_partial; p.gn_chunk_base = a->gn_chunk_base; p.gn_nchunks_total = a->gn_nchunks_total;
+        for (int n = 0; n < a->N; ++n) {
+            cudaError_t e = cudaMemsetAsync(a->gn_partial + ((size_t)n * a->gn_nchunks_total + a->gn_chunk_base) * 128, 0,
+                                            (size_t)grid * 4 * 128 * sizeof(float), stream);
+            if (e != cudaSuccess) return (int)e;
+        }
+        if (G == 3) conv_halo_kernel<3, true><<<grid, H_THREADS, smem, stream>>>(p);
+        else if (G == 2) conv_halo_kernel<2, true><<<grid, H_THREADS, smem, stream>>>(p);
+        else conv_halo_kernel<1, true><<<grid, H_THREADS, smem, stream>>>(p);
+        return launch_result();
+    }
+    if (G == 3) conv_halo_kernel<3, false><<<grid, H_THREADS, smem, stream>>>(p);
+    else if (G == 2) conv_halo_kernel<2, false><<<grid, H_THREADS, smem, stream>>>(p);
+    else conv_halo_kernel<1, false><<<grid, H_THREADS, smem, stream>>>(p);
     return launch_result();
 }
 

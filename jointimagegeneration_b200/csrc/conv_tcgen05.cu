@@ -484,6 +484,13 @@ extern "C" int32_t gg_conv_num_tiles(const gg_conv_args* a) {
 
 extern "C" int32_t gg_conv_stats_chunks(const gg_conv_args* a) {
     if (!a || a->Do <= 0 || a->Ho <= 0 || a->Wo <= 0) return 0;
+    if (a->algo == 1) {
+        // halo kernel: register-resident column sums, one row per (CTA, epilogue warp); 64-channel outputs only
+        const int BNh = a->block_n > 0 ? a->block_n : gg_conv_pick_block_n(a->Cout);
+        if (BNh != 64 || (a->Cout + 7) / 8 * 8 != 64 || a->y_is_f32) return 0;
+        const int64_t tiles = (int64_t)a->N * a->Do * ((a->Ho + 15) / 16) * ((a->Wo + 7) / 8);
+        return (int32_t)std::min<int64_t>(tiles, num_sms()) * 4;
+    }
     int brick[4];
     if (a->brick[0] > 0) { for (int i = 0; i < 4; ++i) brick[i] = a->brick[i]; }
     else pick_brick(a->N, a->Do, a->Ho, a->Wo, brick);

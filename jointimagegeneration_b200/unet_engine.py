@@ -173,6 +173,7 @@ class UNetEngine:
         self.use_split_k = True
         self.num_sms = torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count \
             if next(model.parameters()).is_cuda else 148
+        self.halo_gn_stats = True       # ... except in the halo kernel's 64-channel layers, where they are register sums
         self.fused_gn_stats = False     # GroupNorm statistics from the conv epilogue: correct, but the extra epilogue
                                         # work costs more than the separate (cached) statistics pass saves on B200
         self.slab = None            # sharding.SlabComm: depth-slab decomposition of ONE volume over ranks
@@ -291,7 +292,10 @@ class UNetEngine:
                 out_spatial = (f(D, dims >= 3), f(H, dims >= 2), f(W, True))
         if out is None:
             out = self._new_act(ar, N, out_spatial, cout8, torch.float32 if f32_out else torch.bfloat16)
-        algo = 1 if (self._halo_ok(taps, stride, out_spatial) and not (stats and self.fused_gn_stats)) else 0
+        halo = self._halo_ok(taps, stride, out_spatial) and callable(w_packed)
+        # the halo kernel keeps GroupNorm column sums in registers when one 64-wide tile covers all output channels
+        halo_stats = halo and stats and self.halo_gn_stats and cout8 == 64 and not f32_out
+        algo = 1 if halo and (halo_stats or not (stats and self.fused_gn_stats)) else 0
         if callable(w_packed):          # packed-weight K order depends on the kernel
             w_packed = w_packed(algo == 1)
         else:
@@ -318,7 +322,7 @@ class UNetEngine:
         if emb is not None:
             a.emb = emb
             a.emb_stride = emb_stride
-        if stats and self.fused_gn_stats:
+        if stats and (self.fused_gn_stats or halo_stats):
             # GroupNorm statistics of the output come out of this conv's epilogue (no separate pass over the
             # tensor); stats_part = (index, count) when several launches fill one output (folded upsample)
             per = int(self.lib.gg_conv_stats_chunks(C.byref(a)))

@@ -232,7 +232,7 @@ def test_group_norm_silu(ops, N, sp, C1, C2, silu, eps):
 
 # ------------------------------------------------------------------------------ convolution
 def _conv_case(ops, N, sp, Cs, Cout, dims, k=3, stride=1, bias=True, emb=False, residual=False, extra_C=0, f32_out=False,
-               seed=0, block_n=0, brick=None, algo=0, split_k=0):
+               seed=0, block_n=0, brick=None, algo=0, split_k=0, stats=False):
     no_tf32()
     rs = np.random.RandomState(seed)
     sp3 = (1,) * (3 - len(sp)) + tuple(sp)
@@ -258,11 +258,26 @@ def _conv_case(ops, N, sp, Cs, Cout, dims, k=3, stride=1, bias=True, emb=False, 
     r = torch.from_numpy(rs.standard_normal((N,) + osp + (Cout8,)).astype(np.float32)).cuda().to(torch.bfloat16) if residual else None
     y = torch.full((N,) + osp + (Cout8,), float("nan"), dtype=torch.float32 if f32_out else torch.bfloat16, device="cuda")
     ws = torch.full((max(split_k, 1), N * osp[0] * osp[1] * osp[2], Cout8), float("nan"), device="cuda") if split_k > 1 else None
-    a = ops.make_conv_args(srcs, wp, Cout, y, dims=dims, ksize=k, stride=stride, bias=ops.pad_vec(b, Cout), emb=e,
+    b_pad = ops.pad_vec(b, Cout)       # the args struct holds raw pointers: keep the padded copy alive
+    a = ops.make_conv_args(srcs, wp, Cout, y, dims=dims, ksize=k, stride=stride, bias=b_pad, emb=e,
                            residual=r, block_n=block_n, brick=brick, algo=algo, split_k=split_k, workspace=ws)
     assert ops.conv_packed_k(a) == wp.shape[1]
+    part = None
+    if stats:       # GroupNorm column sums from the conv epilogue; poisoned first: the launch must define every row
+        import ctypes as C
+        from jointimagegeneration_b200 import _C
+        per = int(_C.lib().gg_conv_stats_chunks(C.byref(a)))
+        assert per > 0
+        part = torch.full((N, per + 3, Cout8, 2), float("nan"), device="cuda")
+        a.gn_partial, a.gn_chunk_base, a.gn_nchunks_total = _C.ptr(part), 2, per + 3
     ops.conv_fwd(a)
     torch.cuda.synchronize()
+    if stats:
+        assert torch.isnan(part[:, :2]).all() and torch.isnan(part[:, -1:]).all()      # stays inside its chunk range
+        got_s = part[:, 2:-1].double().sum(1)
+        yd = y.double().reshape(N, -1, Cout8)
+        want_s = torch.stack([yd.sum(1), (yd * yd).sum(1)], -1)
+        assert torch.allclose(got_s, want_s, rtol=1e-4, atol=1e-2), float((got_s - want_s).abs().max())
     want = conv_ref(xs, w, b, dims, stride, e, r, extra)
     got = nchw_from_cl(y, Cout)
     assert got.shape == want.shape, (got.shape, want.shape)
@@ -298,6 +313,10 @@ CONV_CASES = {
     "halo2d_160_320": dict(N=2, sp=(32, 32), Cs=[160], Cout=320, dims=2, emb=True, algo=1),
     "halo3d_head_f32": dict(N=1, sp=(4, 16, 16), Cs=[64], Cout=12, dims=3, f32_out=True, algo=1),
     "halo3d_many_tiles": dict(N=2, sp=(16, 64, 64), Cs=[64], Cout=64, dims=3, residual=True, algo=1),
+    # halo-brick kernel with GroupNorm statistics accumulated in registers (64-channel outputs)
+    "halo3d_stats": dict(N=2, sp=(16, 64, 64), Cs=[64], Cout=64, dims=3, residual=True, algo=1, stats=True),
+    "halo3d_stats_ragged": dict(N=3, sp=(5, 20, 13), Cs=[16], Cout=64, dims=3, emb=True, algo=1, stats=True),
+    "halo3d_stats_few_tiles": dict(N=5, sp=(1, 16, 8), Cs=[128, 64], Cout=60, dims=3, algo=1, stats=True),
 }
 
 
