@@ -257,7 +257,10 @@ typedef struct {
     /* 0: one A tile per (tap, chunk) (any stride / shape).  1: "halo brick" kernel for stride-1 filters: the
      * 16 x 8 output brick's input window is loaded ONCE per 64-channel chunk and every tap reads it in place
      * (shifted UMMA descriptors) -- 6x fewer A-operand bytes through shared memory.  Packed-weight K order for
-     * algo 1 is  source -> 64-channel chunk -> tap -> channel. */
+     * algo 1 is  source -> 64-channel chunk -> tap -> channel.  Algo 1 runs as CTA PAIRS (cta_group::2, one
+     * M = 256 MMA stream over two w-adjacent bricks, each CTA holding half of the weight rows) when the brick
+     * count along w is even; 2 = halo kernel, single CTAs only; 3 = halo kernel, pairs forced (tests).
+     * With algo 1..3 and a 64-channel output, gn_partial rows are per (CTA, epilogue warp) register sums. */
     int32_t algo;
     /* Split-K (algo 0): layers whose output has fewer tiles than the GPU has SMs but a long reduction (the
      * low-resolution 3^d convs) are cut into split_k K ranges; each (tile, range) work item writes raw fp32

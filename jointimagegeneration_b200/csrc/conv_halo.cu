@@ -131,7 +131,57 @@ __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t
     return d;
 }
 
-template <int G, bool STATS>
+// ------------------------------------------------------------------------------ CTA-pair (cta_group::2) helpers
+// PAIR mode (protocol probed on B200: tools/umma2_probe.cu): a cluster of two CTAs computes two w-adjacent bricks
+// with ONE M = 256 MMA stream issued by the leader (rank 0).  Each CTA keeps its own halo planes and HALF of the
+// weight rows in its own shared memory, so weight traffic (L2 -> smem and smem -> tensor core) per brick halves.
+// TMA loads of both CTAs count bytes on the leader's "full" barrier; tcgen05.commit multicasts to the same-offset
+// "empty"/"accumulator full" barriers of both CTAs; both epilogues arrive on the leader's "accumulator empty".
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t leader_addr(const void* smem_ptr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(smem_ptr)), "r"(0u));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_bf16_t(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (PAIR) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_t(uint64_t* bar) {
+    if constexpr (PAIR) {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    } else {
+        umma_commit(bar);
+    }
+}
+
+template <int G, bool STATS, bool PAIR>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -148,6 +198,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     float* bvec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512);      // [BN] bias + emb[n]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    // persistent schedule: in PAIR mode a "tile" is a pair of w-adjacent bricks and the two CTAs of a cluster walk
+    // the same tile sequence (p.tw = pairs along w); CTA `rank` owns brick 2 iw + rank
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < p.nseg; ++i) prefetch_tmap(&p.amap[i]);
         prefetch_tmap(&p.wmap);
@@ -156,16 +210,23 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         if (lane == 0) {
             for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
             for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 8 : 4); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();       // the peer's barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -173,9 +234,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         // ================================================================ A (halo brick) producer
         int sa = 0;
         uint32_t pha = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
             int mt = tile / p.n_tiles_n;
-            const int iw = mt % p.tw; mt /= p.tw;
+            const int iw = (PAIR ? 2 : 1) * (mt % p.tw) + rank; mt /= p.tw;
             const int ih = mt % p.th; mt /= p.th;
             const int d0 = mt % p.Do, n0 = mt / p.Do;
             const int h0 = ih * H_BH, w0 = iw * H_BW;
@@ -185,9 +246,15 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
                     for (int a = 0; a < sg.kd; ++a) {
                         mbar_wait(&a_empty[sa], pha ^ 1u);
                         if (elect_one()) {
-                            mbar_expect_tx(&a_full[sa], sg.a_bytes);
-                            tma_load_5d(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], &a_full[sa], j * BK, w0 + sg.ow, h0 + sg.oh,
-                                        d0 + sg.od + sg.dshift + a, n0);
+                            if constexpr (PAIR) {
+                                if (rank == 0) mbar_expect_tx(&a_full[sa], 2u * sg.a_bytes);
+                                tma_load_5d_pair(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], leader_addr(&a_full[sa]), j * BK,
+                                                 w0 + sg.ow, h0 + sg.oh, d0 + sg.od + sg.dshift + a, n0);
+                            } else {
+                                mbar_expect_tx(&a_full[sa], sg.a_bytes);
+                                tma_load_5d(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], &a_full[sa], j * BK, w0 + sg.ow, h0 + sg.oh,
+                                            d0 + sg.od + sg.dshift + a, n0);
+                            }
                         }
                         __syncwarp();
                         if (++sa == SA) { sa = 0; pha ^= 1u; }
@@ -198,7 +265,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         // ================================================================ B (weights) producer
         int sb = 0;
         uint32_t phb = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
             const int nt = tile % p.n_tiles_n;
             int kb = 0;
             for (int s = 0; s < p.nseg; ++s) {
@@ -207,10 +274,18 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
                 for (int i = 0; i < nk; ++i) {
                     mbar_wait(&b_empty[sb], phb ^ 1u);
                     if (elect_one()) {
-                        mbar_expect_tx(&b_full[sb], p.b_tap_bytes * (uint32_t)sg.g);
-                        for (int t = 0; t < sg.g; ++t)
-                            tma_load_2d(smem_b + (size_t)sb * p.b_stage_bytes + (size_t)t * p.b_tap_bytes, &p.wmap, &b_full[sb],
-                                        (kb + t) * BK, nt * BN);
+                        if constexpr (PAIR) {       // this CTA's half of the weight rows
+                            if (rank == 0) mbar_expect_tx(&b_full[sb], 2u * p.b_tap_bytes * (uint32_t)sg.g);
+                            const uint32_t bar = leader_addr(&b_full[sb]);
+                            for (int t = 0; t < sg.g; ++t)
+                                tma_load_2d_pair(smem_b + (size_t)sb * p.b_stage_bytes + (size_t)t * p.b_tap_bytes, &p.wmap, bar,
+                                                 (kb + t) * BK, nt * BN + rank * (BN >> 1));
+                        } else {
+                            mbar_expect_tx(&b_full[sb], p.b_tap_bytes * (uint32_t)sg.g);
+                            for (int t = 0; t < sg.g; ++t)
+                                tma_load_2d(smem_b + (size_t)sb * p.b_stage_bytes + (size_t)t * p.b_tap_bytes, &p.wmap, &b_full[sb],
+                                            (kb + t) * BK, nt * BN);
+                        }
                     }
                     __syncwarp();
                     kb += sg.g;
@@ -219,12 +294,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        // ================================================================ MMA issuer
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // ================================================================ MMA issuer (PAIR: the leader CTA only)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
         const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem_b);
         int sa = 0, sb = 0;
         uint32_t pha = 0, phb = 0, acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < (rank == 0 ? p.total_tiles : 0); tile += tstep) {
             mbar_wait(&tempty[acc], acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * H_ACC_COLS;
@@ -250,15 +326,15 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
 #pragma unroll
                                     for (int t = 0; t < G; ++t) {
                                         const uint64_t ad = a_tmpl | (uint64_t)(row16 + 8u * t), bd = b_tmpl | (uint64_t)(b16 + b_tap16 * t);
-                                        umma_bf16(d_tmem, ad, bd, idesc, (t == 0 && first) ? 0u : 1u);
-                                        umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                                        umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                                        umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                                        umma_bf16_t<PAIR>(d_tmem, ad, bd, idesc, (t == 0 && first) ? 0u : 1u);
+                                        umma_bf16_t<PAIR>(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                                        umma_bf16_t<PAIR>(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                                        umma_bf16_t<PAIR>(d_tmem, ad + 6, bd + 6, idesc, 1u);
                                     }
-                                    umma_commit(&b_empty[sb]);
+                                    umma_commit_t<PAIR>(&b_empty[sb]);
                                     if (b == sg.kh - 1) {
-                                        umma_commit(&a_empty[sa]);
-                                        if (last_chunk && a == sg.kd - 1) umma_commit(&tfull[acc]);
+                                        umma_commit_t<PAIR>(&a_empty[sa]);
+                                        if (last_chunk && a == sg.kd - 1) umma_commit_t<PAIR>(&tfull[acc]);
                                     }
                                 }
                                 __syncwarp();
@@ -271,14 +347,14 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
                                     if (elect_one()) {
                                         const uint64_t ad = a_tmpl | (uint64_t)(row16 + 8u * c);
                                         const uint64_t bd = b_tmpl | (uint64_t)((b_base + (uint32_t)sb * p.b_stage_bytes) >> 4);
-                                        umma_bf16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
-                                        umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                                        umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                                        umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
-                                        umma_commit(&b_empty[sb]);
+                                        umma_bf16_t<PAIR>(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                        umma_bf16_t<PAIR>(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                                        umma_bf16_t<PAIR>(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                                        umma_bf16_t<PAIR>(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                                        umma_commit_t<PAIR>(&b_empty[sb]);
                                         if (b == sg.kh - 1 && c == sg.kw - 1) {
-                                            umma_commit(&a_empty[sa]);
-                                            if (last_chunk && a == sg.kd - 1) umma_commit(&tfull[acc]);
+                                            umma_commit_t<PAIR>(&a_empty[sa]);
+                                            if (last_chunk && a == sg.kd - 1) umma_commit_t<PAIR>(&tfull[acc]);
                                         }
                                     }
                                     __syncwarp();
@@ -308,10 +384,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
 #pragma unroll
             for (int i = 0; i < (STATS ? 64 : 1); ++i) { s1[i] = 0.f; s2[i] = 0.f; }
         }
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const uint32_t tempty_r0 = PAIR ? leader_addr(&tempty[0]) : 0u, tempty_r1 = PAIR ? leader_addr(&tempty[1]) : 0u;
+        for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
             const int nt = tile % p.n_tiles_n;
             int mt = tile / p.n_tiles_n;
-            const int iw = mt % p.tw; mt /= p.tw;
+            const int iw = (PAIR ? 2 : 1) * (mt % p.tw) + rank; mt /= p.tw;
             const int ih = mt % p.th; mt /= p.th;
             const int d = mt % p.Do, n = mt / p.Do;
             const int h = ih * H_BH + rh, w = iw * H_BW + rw;
@@ -352,7 +429,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_remote(acc ? tempty_r1 : tempty_r0);
+                else mbar_arrive(&tempty[acc]);
+            }
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -365,13 +445,54 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();       // the leader's MMAs / multicast commits no longer touch the peer
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
+template <int G, bool STATS, bool PAIR>
+static int launch_halo(const HaloParams& p, int grid, size_t smem, cudaStream_t stream) {
+    auto* fn = conv_halo_kernel<G, STATS, PAIR>;
+    static bool attr_set = false;      // one flag per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(H_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
+    if (e != cudaSuccess) return (int)e;
+    return launch_result();
+}
+template <bool STATS, bool PAIR>
+static int launch_halo_g(int G, const HaloParams& p, int grid, size_t smem, cudaStream_t stream) {
+    if (G == 3) return launch_halo<3, STATS, PAIR>(p, grid, smem, stream);
+    if (G == 2) return launch_halo<2, STATS, PAIR>(p, grid, smem, stream);
+    return launch_halo<1, STATS, PAIR>(p, grid, smem, stream);
+}
+
 // ---------------------------------------------------------------------------------------- host
+// launch geometry shared with gg_conv_stats_chunks: CTA pairs (algo 3 forces, algo 2 forbids) take two w-adjacent
+// bricks per cluster; an odd brick count along w would idle one CTA of the last pair, so auto mode wants it even
+int conv_halo_grid(const gg_conv_args* a, bool* pair_out) {
+    const int BN = a->block_n > 0 ? a->block_n : gg_conv_pick_block_n(a->Cout);
+    const int th = (a->Ho + H_BH - 1) / H_BH, tw = (a->Wo + H_BW - 1) / H_BW;
+    bool pair = a->algo == 3 || (a->algo == 1 && tw % 2 == 0);
+    if (const char* e = getenv("GG_HALO_PAIR")) { if (a->algo == 1) pair = pair && atoi(e) != 0; }     // tuning knob
+    const int64_t tiles = (int64_t)a->N * a->Do * th * (pair ? (tw + 1) / 2 : tw) * ((a->Cout + BN - 1) / BN);
+    if (pair_out) *pair_out = pair;
+    return pair ? 2 * (int)std::min<int64_t>(tiles, num_sms() / 2) : (int)std::min<int64_t>(tiles, num_sms());
+}
+
 int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     GG_REQUIRE(a->stride == 1, GG_ERR_UNSUPPORTED);
     GG_REQUIRE(a->nsrc >= 1 && a->nsrc <= H_MAX_SEGS, GG_ERR_BAD_ARG);
@@ -383,6 +504,10 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     p.BN = BN;
     p.No = a->N; p.Do = a->Do; p.Ho = a->Ho; p.Wo = a->Wo;
     p.th = (a->Ho + H_BH - 1) / H_BH; p.tw = (a->Wo + H_BW - 1) / H_BW;
+    bool pair = false;
+    const int grid = conv_halo_grid(a, &pair);
+    GG_REQUIRE(!pair || BN % 16 == 0, GG_ERR_UNSUPPORTED);
+    if (pair) p.tw = (p.tw + 1) / 2;
     p.n_tiles_n = (a->Cout + BN - 1) / BN;
     const int64_t total = (int64_t)a->N * a->Do * p.th * p.tw * p.n_tiles_n;
     GG_REQUIRE(total < (1ll << 31), GG_ERR_UNSUPPORTED);
@@ -412,9 +537,10 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
         num_kb += sg.nchunks * sg.kd * sg.kh * sg.kw;
     }
     p.nseg = a->nsrc;
-    if (!encode_w_map(&p.wmap, a->w_packed, (int64_t)num_kb * BK, a->Cout, BN)) return GG_ERR_DRIVER;
+    const int b_rows = pair ? BN / 2 : BN;          // weight rows per CTA and tap
+    if (!encode_w_map(&p.wmap, a->w_packed, (int64_t)num_kb * BK, a->Cout, b_rows)) return GG_ERR_DRIVER;
     p.a_stage_bytes = (max_a + 1023u) & ~1023u;
-    p.b_tap_bytes = (uint32_t)BN * 128u;
+    p.b_tap_bytes = (uint32_t)b_rows * 128u;
     const int bar_bytes = 512 + 1024;        // barriers + the epilogue's [BN] additive vector
     const int avail = H_SMEM_BUDGET - 1024 - bar_bytes;
     int kwmax = 1;
@@ -442,16 +568,6 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.res_stride = a->res_stride;
     p.y = a->y; p.y_sn = a->y_sn; p.y_sd = a->y_sd; p.y_sh = a->y_sh; p.y_sw = a->y_sw; p.y_is_f32 = a->y_is_f32;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaSuccess;
-        auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET); };
-        set((const void*)conv_halo_kernel<1, false>); set((const void*)conv_halo_kernel<2, false>); set((const void*)conv_halo_kernel<3, false>);
-        set((const void*)conv_halo_kernel<1, true>); set((const void*)conv_halo_kernel<2, true>); set((const void*)conv_halo_kernel<3, true>);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    const int grid = std::min(p.total_tiles, num_sms());
     if (a->gn_partial != nullptr) {
         // fused GroupNorm statistics: one partial row per (CTA, epilogue warp) and sample; CTAs that never touch a
         // sample leave zeros, so the rows are cleared first (a memset node under graph capture)
@@ -463,15 +579,9 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
                                             (size_t)grid * 4 * 128 * sizeof(float), stream);
             if (e != cudaSuccess) return (int)e;
         }
-        if (G == 3) conv_halo_kernel<3, true><<<grid, H_THREADS, smem, stream>>>(p);
-        else if (G == 2) conv_halo_kernel<2, true><<<grid, H_THREADS, smem, stream>>>(p);
-        else conv_halo_kernel<1, true><<<grid, H_THREADS, smem, stream>>>(p);
-        return launch_result();
+        return pair ? launch_halo_g<true, true>(G, p, grid, smem, stream) : launch_halo_g<true, false>(G, p, grid, smem, stream);
     }
-    if (G == 3) conv_halo_kernel<3, false><<<grid, H_THREADS, smem, stream>>>(p);
-    else if (G == 2) conv_halo_kernel<2, false><<<grid, H_THREADS, smem, stream>>>(p);
-    else conv_halo_kernel<1, false><<<grid, H_THREADS, smem, stream>>>(p);
-    return launch_result();
+    return pair ? launch_halo_g<false, true>(G, p, grid, smem, stream) : launch_halo_g<false, false>(G, p, grid, smem, stream);
 }
 
 }  // namespace gg

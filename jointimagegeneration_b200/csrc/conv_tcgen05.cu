@@ -484,12 +484,11 @@ extern "C" int32_t gg_conv_num_tiles(const gg_conv_args* a) {
 
 extern "C" int32_t gg_conv_stats_chunks(const gg_conv_args* a) {
     if (!a || a->Do <= 0 || a->Ho <= 0 || a->Wo <= 0) return 0;
-    if (a->algo == 1) {
+    if (a->algo >= 1 && a->algo <= 3) {
         // halo kernel: register-resident column sums, one row per (CTA, epilogue warp); 64-channel outputs only
         const int BNh = a->block_n > 0 ? a->block_n : gg_conv_pick_block_n(a->Cout);
         if (BNh != 64 || (a->Cout + 7) / 8 * 8 != 64 || a->y_is_f32) return 0;
-        const int64_t tiles = (int64_t)a->N * a->Do * ((a->Ho + 15) / 16) * ((a->Wo + 7) / 8);
-        return (int32_t)std::min<int64_t>(tiles, num_sms()) * 4;
+        return conv_halo_grid(a, nullptr) * 4;
     }
     int brick[4];
     if (a->brick[0] > 0) { for (int i = 0; i < 4; ++i) brick[i] = a->brick[i]; }
@@ -522,7 +521,7 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
     if (a->bias) GG_REQUIRE(aligned(a->bias, 16), GG_ERR_ALIGNMENT);
     if (a->emb) GG_REQUIRE(aligned(a->emb, 16) && a->emb_stride % 4 == 0, GG_ERR_ALIGNMENT);
     if (!encode_fn()) return GG_ERR_DRIVER;
-    if (a->algo == 1) return conv_halo_fwd(a, as_stream(stream));
+    if (a->algo >= 1 && a->algo <= 3) return conv_halo_fwd(a, as_stream(stream));
 
     ConvParams p;
     memset(&p, 0, sizeof(p));

@@ -23,7 +23,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t ok;
+    uint32_t ok, spins = 0;
+    uint64_t t0 = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -32,6 +33,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(addr), "r"(parity)
             : "memory");
+        // watchdog (failed polls only): a pipeline-protocol bug must surface as a launch error, not hang the GPU
+        if (!ok && (++spins & 0xFFFu) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
     } while (!ok);
 }
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
@@ -165,5 +173,6 @@ EncodeTiledFn encode_fn();
 bool encode_act_map(CUtensorMap* m, const void* base, int C, const int64_t dim[4], const int64_t stride_el[4], const int box[4]);
 bool encode_w_map(CUtensorMap* m, const void* base, int64_t Ktot, int rows, int BN);
 int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream);   // conv_halo.cu
+int conv_halo_grid(const gg_conv_args* a, bool* pair_out);       // CTAs conv_halo_fwd launches for `a`
 
 }  // namespace gg

@@ -247,7 +247,7 @@ def _conv_case(ops, N, sp, Cs, Cout, dims, k=3, stride=1, bias=True, emb=False, 
         extra.append((xe, we))
         extra_w.append(we)
         srcs.append((xe, True))
-    wp = ops.pack_conv_weight(w, Cs, extra=extra_w, chunk_major=(algo == 1))
+    wp = ops.pack_conv_weight(w, Cs, extra=extra_w, chunk_major=(algo >= 1))
     Cout8 = (Cout + 7) // 8 * 8
     if stride == 1:
         osp = sp3
@@ -317,6 +317,17 @@ CONV_CASES = {
     "halo3d_stats": dict(N=2, sp=(16, 64, 64), Cs=[64], Cout=64, dims=3, residual=True, algo=1, stats=True),
     "halo3d_stats_ragged": dict(N=3, sp=(5, 20, 13), Cs=[16], Cout=64, dims=3, emb=True, algo=1, stats=True),
     "halo3d_stats_few_tiles": dict(N=5, sp=(1, 16, 8), Cs=[128, 64], Cout=60, dims=3, algo=1, stats=True),
+    # halo-brick kernel, single CTAs forced (algo 2) / CTA pairs forced (algo 3; odd brick counts along w included)
+    "halo_single_64": dict(N=2, sp=(4, 32, 32), Cs=[64], Cout=64, dims=3, residual=True, algo=2),
+    "halo_pair_64": dict(N=1, sp=(4, 16, 16), Cs=[64], Cout=64, dims=3, algo=3),
+    "halo_pair_all": dict(N=2, sp=(3, 32, 24), Cs=[128, 64], Cout=64, dims=3, extra_C=192, emb=True, algo=3),
+    "halo_pair_res_128": dict(N=2, sp=(8, 32, 32), Cs=[128], Cout=128, dims=3, residual=True, algo=3),
+    "halo_pair_ragged_odd": dict(N=3, sp=(5, 20, 21), Cs=[16], Cout=64, dims=3, emb=True, algo=3, stats=True),
+    "halo_pair_one_brick": dict(N=2, sp=(2, 16, 8), Cs=[64], Cout=128, dims=3, algo=3),
+    "halo_pair_2d_160_320": dict(N=2, sp=(32, 32), Cs=[160], Cout=320, dims=2, emb=True, algo=3),
+    "halo_pair_head_f32": dict(N=1, sp=(4, 16, 16), Cs=[64], Cout=12, dims=3, f32_out=True, algo=3),
+    "halo_pair_many_tiles": dict(N=2, sp=(16, 64, 64), Cs=[64], Cout=64, dims=3, residual=True, algo=3, stats=True),
+    "halo_pair_cout_192": dict(N=1, sp=(2, 32, 16), Cs=[128], Cout=192, dims=3, algo=3),
 }
 
 
