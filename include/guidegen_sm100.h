@@ -260,7 +260,10 @@ typedef struct {
      * algo 1 is  source -> 64-channel chunk -> tap -> channel.  Algo 1 runs as CTA PAIRS (cta_group::2, one
      * M = 256 MMA stream over two w-adjacent bricks, each CTA holding half of the weight rows) when the brick
      * count along w is even; 2 = halo kernel, single CTAs only; 3 = halo kernel, pairs forced (tests).
-     * With algo 1..3 and a 64-channel output, gn_partial rows are per (CTA, epilogue warp) register sums. */
+     * 4 = "depth-rolling" kernel for 3x3x3 stride-1 filters with 3 * Cout <= 256 (conv_roll.cu): walks input
+     * depth planes and stacks the three depth taps along N, so each plane is loaded once and each A slice feeds
+     * 3 Cout accumulator columns (same packed-weight K order as algo 1; always CTA pairs).
+     * With algo 1..4 and a 64-channel output, gn_partial rows are per (CTA, epilogue warp) register sums. */
     int32_t algo;
     /* Split-K (algo 0): layers whose output has fewer tiles than the GPU has SMs but a long reduction (the
      * low-resolution 3^d convs) are cut into split_k K ranges; each (tile, range) work item writes raw fp32

@@ -1,0 +1,605 @@
+// conv_roll.cu -- "depth-rolling" 3x3x3 convolution for narrow outputs (3 * Cout <= 256), CTA pairs only
+//
+// With Cout = 64 the halo-brick kernel issues 128 x 64 x 16 MMAs: every MMA re-reads its 4 KB A slice from
+// shared memory to fill only 64 accumulator columns, and the A reads alone (128 B/clk) are the SM's whole
+// shared-memory bandwidth.  This kernel walks the INPUT depth planes of a brick column instead of the output
+// planes.  Input plane z feeds output planes z+1, z, z-1 through the depth taps kd = 0, 1, 2, so the three
+// tap-weight tiles are stacked along N and ONE MMA stream (N = 3 Cout) updates three accumulator slots:
+//
+//     step t (input plane z = d0 - 1 + t):   slot (t+1-kd) mod 3  +=  X[z] (shifted by kh, kw) * W[kd, kh, kw]
+//
+// Each halo plane is loaded once (not three times) and each A slice read from shared memory feeds 3x the
+// columns.  After step t the slot of output plane z-1 is complete: the epilogue stores it, ZEROES the slot
+// (tcgen05.st; every MMA accumulates) and hands it back; it becomes the kd = 0 target of step t+1.  So that
+// the tensor core never waits for that hand-over, a CTA interleaves two bricks (h-adjacent, `wi` = 0/1) with
+// their own slot triples: X(t), Y(t), X(t+1), ...  A depth segment of L output planes costs L + 2 steps (the
+// first/last step feed one real output plane each); the host picks the segment length that balances that
+// overhead against the number of work items per CTA pair.
+//
+// CTA pair (cta_group::2, M = 256): two w-adjacent bricks per cluster, each CTA holds its own planes and half
+// of the stacked weight rows (N/2 = 1.5 slots).  Sources flagged centre_only (the fused 1x1x1 skip) are
+// N = Cout MMAs into the slot of output plane z.  K order of the packed weights: as conv_halo.cu (algo 1).
+//
+// Roles (224 threads): warp 0 = A (plane) producer, warp 6 = B (weights) producer, warp 1 = MMA issuer
+// (leader CTA), warps 2..5 = epilogue.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "halo_common.cuh"
+
+namespace gg {
+
+constexpr int R_MAX_SA = 4, R_MAX_SB = 6;
+constexpr int R_THREADS = 352;      // warps 0, 1, 6 = producers / MMA; warps 2..5 drain brick 0, warps 7..10 drain brick 1
+
+struct RollSeg {
+    int nchunks, centre;
+    int kh, kw, oh, ow, dshift;
+    int pitch;
+    uint32_t a_bytes;
+    int g;           // kw taps per B stage (kw or 1)
+    int kb_base;     // first 64-wide K block of this source in the packed weights
+    int taps;        // K blocks per chunk: 3 kh kw, or 1 (centre_only)
+};
+
+struct alignas(64) RollParams {
+    CUtensorMap amap[H_MAX_SEGS];
+    CUtensorMap wmap;              // box = 64 k x (BNs / 2) weight rows: one "unit" = half a slot
+    RollSeg seg[H_MAX_SEGS];
+    int nseg, BNs, SA, SB;
+    uint32_t a_stage_bytes, b_stage_bytes, b_unit_bytes;
+    int No, Do, Ho, Wo;
+    int thp, twp, nsd, Lseg, total_items;      // brick pairs along h / w, depth segments and their length
+    int Cout8;
+    const float* bias;
+    const float* emb;
+    int emb_stride;
+    const __nv_bfloat16* residual;
+    int res_stride;
+    void* y;
+    long long y_sn, y_sd, y_sh, y_sw;
+    int y_is_f32;
+    float* gn_partial;
+    int gn_chunk_base, gn_nchunks_total;
+    unsigned long long* dbg;       // tuning aid (GG_ROLL_DBG=1): per leader CTA, clocks the MMA issuer spent in each wait
+};
+
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// accumulator slot -> registers (the slot is handed back to the tensor core BEFORE the row is finished and stored)
+template <int BNS>
+__device__ __forceinline__ void load_slot(uint32_t t_addr, uint32_t (&r)[BNS]) {
+#pragma unroll
+    for (int c = 0; c < BNS; c += 16) tmem_ld16_nowait(t_addr + c, r + c);
+    tmem_ld_wait();
+}
+// bias / embedding / residual / rounding / store of one output row from registers.  STATS: r[] is left holding the
+// stored (bf16-rounded) values as floats, zeros for rows outside the tensor, for warp_colsum64.
+template <int BNS, bool STATS>
+__device__ __forceinline__ void finish_row(uint32_t (&r)[BNS], const uint4 (&rr)[BNS / 8], int ncols, const float* __restrict__ bvec,
+                                           void* y_row, int y_is_f32, bool valid) {
+#pragma unroll
+    for (int g = 0; g < BNS / 8; ++g) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bvec + 8 * g), b1 = *reinterpret_cast<const float4*>(bvec + 8 * g + 4);
+        float v[8];
+        v[0] = __uint_as_float(r[8 * g + 0]) + b0.x + bf16_lo(rr[g].x); v[1] = __uint_as_float(r[8 * g + 1]) + b0.y + bf16_hi(rr[g].x);
+        v[2] = __uint_as_float(r[8 * g + 2]) + b0.z + bf16_lo(rr[g].y); v[3] = __uint_as_float(r[8 * g + 3]) + b0.w + bf16_hi(rr[g].y);
+        v[4] = __uint_as_float(r[8 * g + 4]) + b1.x + bf16_lo(rr[g].z); v[5] = __uint_as_float(r[8 * g + 5]) + b1.y + bf16_hi(rr[g].z);
+        v[6] = __uint_as_float(r[8 * g + 6]) + b1.z + bf16_lo(rr[g].w); v[7] = __uint_as_float(r[8 * g + 7]) + b1.w + bf16_hi(rr[g].w);
+        if (y_is_f32) {
+            if (valid && 8 * g < ncols) {
+                float* yp = reinterpret_cast<float*>(y_row) + 8 * g;
+                *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        } else {
+            const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            if (valid && 8 * g < ncols) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_row) + 8 * g) = pk;
+            if constexpr (STATS) {
+                const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    r[8 * g + 2 * e] = valid ? __float_as_uint(bf16_lo(w[e])) : 0u;
+                    r[8 * g + 2 * e + 1] = valid ? __float_as_uint(bf16_hi(w[e])) : 0u;
+                }
+            }
+        }
+    }
+}
+// column sums over the 32 rows a warp holds (one row of 64 values per lane): butterfly reduce-scatter, 62 shuffles;
+// lane l returns the sums of columns 2l and 2l+1.  Destroys a[].
+__device__ __forceinline__ float2 warp_colsum64(float (&a)[64], int lane) {
+#pragma unroll
+    for (int half = 32; half >= 2; half >>= 1) {
+        const int m = half >> 1;
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = up ? a[i + half] : a[i], send = up ? a[i] : a[i + half];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    return make_float2(a[0], a[1]);
+}
+
+struct RollItem { int n, d0, L, ihp, iwp; };
+__device__ __forceinline__ RollItem roll_item(const RollParams& p, int item) {
+    RollItem it;
+    it.iwp = item % p.twp; item /= p.twp;
+    it.ihp = item % p.thp; item /= p.thp;
+    const int sd = item % p.nsd;
+    it.n = item / p.nsd;
+    it.d0 = sd * p.Lseg;
+    it.L = min(p.Do, it.d0 + p.Lseg) - it.d0;
+    return it;
+}
+
+template <int G, bool STATS, int BNS>
+__global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_constant__ RollParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const int SA = p.SA, SB = p.SB;
+    constexpr int BNs = BNS;
+    uint8_t* smem_b = smem + (size_t)SA * p.a_stage_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)SB * p.b_stage_bytes);
+    uint64_t* a_empty = a_full + R_MAX_SA;
+    uint64_t* b_full = a_empty + R_MAX_SA;
+    uint64_t* b_empty = b_full + R_MAX_SB;
+    uint64_t* step_done = b_empty + R_MAX_SB;       // [wi]: the MMAs of one step of brick wi have completed
+    uint64_t* slot_free = step_done + 2;            // [wi] (leader's): finished slot of brick wi drained and zeroed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_free + 2);
+    float* bvec_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512);  // [2][BNs] bias + emb[n], per epilogue group
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int item0 = (int)(blockIdx.x >> 1), istep = (int)(gridDim.x >> 1);
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < p.nseg; ++i) prefetch_tmap(&p.amap[i]);
+        prefetch_tmap(&p.wmap);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&step_done[i], 1); mbar_init(&slot_free[i], 8); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================ A (halo plane) producer
+        int sa = 0;
+        uint32_t pha = 0;
+        for (int item = item0; item < p.total_items; item += istep) {
+            const RollItem it = roll_item(p, item);
+            const int w0 = (2 * it.iwp + rank) * H_BW;
+            for (int t = 0; t < it.L + 2; ++t)
+                for (int wi = 0; wi < 2; ++wi) {
+                    const int h0 = (2 * it.ihp + wi) * H_BH, z = it.d0 - 1 + t;
+                    for (int s = 0; s < p.nseg; ++s) {
+                        const RollSeg sg = p.seg[s];
+                        if (sg.centre && (t == 0 || t == it.L + 1)) continue;     // would only feed planes outside the segment
+                        for (int j = 0; j < sg.nchunks; ++j) {
+                            mbar_wait(&a_empty[sa], pha ^ 1u);
+                            if (elect_one()) {
+                                if (rank == 0) mbar_expect_tx(&a_full[sa], 2u * sg.a_bytes);
+                                tma_load_5d_pair(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], leader_addr(&a_full[sa]), j * BK,
+                                                 w0 + sg.ow, h0 + sg.oh, z + sg.dshift, it.n);
+                            }
+                            __syncwarp();
+                            if (++sa == SA) { sa = 0; pha ^= 1u; }
+                        }
+                    }
+                }
+        }
+    } else if (warp == 6) {
+        // ================================================================ B (stacked weights) producer
+        int sb = 0;
+        uint32_t phb = 0;
+        const int half_rows = BNs >> 1;
+        for (int item = item0; item < p.total_items; item += istep) {
+            const RollItem it = roll_item(p, item);
+            for (int t = 0; t < it.L + 2; ++t)
+                for (int wi = 0; wi < 2; ++wi)
+                    for (int s = 0; s < p.nseg; ++s) {
+                        const RollSeg sg = p.seg[s];
+                        if (sg.centre && (t == 0 || t == it.L + 1)) continue;
+                        for (int j = 0; j < sg.nchunks; ++j) {
+                            const int kb0 = sg.kb_base + j * sg.taps;
+                            if (sg.centre) {
+                                mbar_wait(&b_empty[sb], phb ^ 1u);
+                                if (elect_one()) {
+                                    if (rank == 0) mbar_expect_tx(&b_full[sb], 2u * p.b_unit_bytes);
+                                    tma_load_2d_pair(smem_b + (size_t)sb * p.b_stage_bytes, &p.wmap, leader_addr(&b_full[sb]), kb0 * BK,
+                                                     rank * half_rows);
+                                }
+                                __syncwarp();
+                                if (++sb == SB) { sb = 0; phb ^= 1u; }
+                                continue;
+                            }
+                            const int khw = sg.kh * sg.kw;
+                            for (int b = 0; b < sg.kh; ++b)
+                                for (int cg = 0; cg < sg.kw / sg.g; ++cg) {
+                                    mbar_wait(&b_empty[sb], phb ^ 1u);
+                                    if (elect_one()) {
+                                        if (rank == 0) mbar_expect_tx(&b_full[sb], 2u * 3u * p.b_unit_bytes * (uint32_t)sg.g);
+                                        const uint32_t bar = leader_addr(&b_full[sb]);
+                                        uint8_t* dst = smem_b + (size_t)sb * p.b_stage_bytes;
+                                        for (int tt = 0; tt < sg.g; ++tt)
+                                            for (int ul = 0; ul < 3; ++ul) {
+                                                // this CTA's rows of the stacked tile: units 3 rank .. 3 rank + 2 of six half-slots
+                                                const int u = 3 * rank + ul, slot = u >> 1, half = u & 1;
+                                                const int kd = (t + 4 - slot) % 3;
+                                                const int kb = kb0 + kd * khw + b * sg.kw + cg * sg.g + tt;
+                                                tma_load_2d_pair(dst + (size_t)(tt * 3 + ul) * p.b_unit_bytes, &p.wmap, bar, kb * BK,
+                                                                 half * half_rows);
+                                            }
+                                    }
+                                    __syncwarp();
+                                    if (++sb == SB) { sb = 0; phb ^= 1u; }
+                                }
+                        }
+                    }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer (leader CTA only)
+        if (rank == 0) {
+            const uint32_t idesc_full = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * BNs) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t idesc_one = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNs >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem_b);
+            const uint64_t b_tmpl = make_sw128_desc_sbo(0, 1024u);
+            const uint32_t tap16 = (3u * p.b_unit_bytes) >> 4;
+            int sa = 0, sb = 0;
+            uint32_t pha = 0, phb = 0, phf[2] = {0, 0};
+            long long w_slot = 0, w_a = 0, w_b = 0, t_begin = clock64(), tq;
+            for (int item = item0; item < p.total_items; item += istep) {
+                const RollItem it = roll_item(p, item);
+                for (int t = 0; t < it.L + 2; ++t)
+                    for (int wi = 0; wi < 2; ++wi) {
+                        tq = clock64();
+                        mbar_wait(&slot_free[wi], phf[wi]);
+                        w_slot += clock64() - tq;
+                        phf[wi] ^= 1u;
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(wi * 3 * BNs);
+                        for (int s = 0; s < p.nseg; ++s) {
+                            const RollSeg sg = p.seg[s];
+                            if (sg.centre && (t == 0 || t == it.L + 1)) continue;
+                            const uint64_t a_tmpl = make_sw128_desc_sbo(0, (uint32_t)sg.pitch * 128u);
+                            for (int j = 0; j < sg.nchunks; ++j) {
+                                tq = clock64();
+                                mbar_wait(&a_full[sa], pha);
+                                w_a += clock64() - tq;
+                                const uint32_t a_stage16 = (a_base + (uint32_t)sa * p.a_stage_bytes) >> 4;
+                                if (sg.centre) {
+                                    mbar_wait(&b_full[sb], phb);
+                                    tc_fence_after();
+                                    if (elect_one()) {
+                                        const uint64_t ad = a_tmpl | (uint64_t)a_stage16;
+                                        const uint64_t bd = b_tmpl | (uint64_t)((b_base + (uint32_t)sb * p.b_stage_bytes) >> 4);
+                                        const uint32_t dc = d_tmem + (uint32_t)((t % 3) * BNs);      // slot of output plane z
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) umma_bf16_t<true>(dc, ad + 2 * k, bd + 2 * k, idesc_one, 1u);
+                                        umma_commit_t<true>(&b_empty[sb]);
+                                        umma_commit_t<true>(&a_empty[sa]);
+                                    }
+                                    __syncwarp();
+                                    if (++sb == SB) { sb = 0; phb ^= 1u; }
+                                } else {
+                                    for (int b = 0; b < sg.kh; ++b) {
+                                        const uint32_t row16 = a_stage16 + (uint32_t)(b * sg.pitch) * 8u;
+                                        for (int cg = 0; cg < sg.kw / sg.g; ++cg) {
+                                            tq = clock64();
+                                            mbar_wait(&b_full[sb], phb);
+                                            w_b += clock64() - tq;
+                                            tc_fence_after();
+                                            if (elect_one()) {
+                                                const uint32_t b16 = (b_base + (uint32_t)sb * p.b_stage_bytes) >> 4;
+                                                if (G > 1 && sg.g == G) {
+#pragma unroll
+                                                    for (int tt = 0; tt < G; ++tt) {
+                                                        const uint64_t ad = a_tmpl | (uint64_t)(row16 + 8u * tt), bd = b_tmpl | (uint64_t)(b16 + tap16 * tt);
+#pragma unroll
+                                                        for (int k = 0; k < 4; ++k) umma_bf16_t<true>(d_tmem, ad + 2 * k, bd + 2 * k, idesc_full, 1u);
+                                                    }
+                                                } else {
+                                                    const uint64_t ad = a_tmpl | (uint64_t)(row16 + 8u * cg), bd = b_tmpl | (uint64_t)b16;
+#pragma unroll
+                                                    for (int k = 0; k < 4; ++k) umma_bf16_t<true>(d_tmem, ad + 2 * k, bd + 2 * k, idesc_full, 1u);
+                                                }
+                                                umma_commit_t<true>(&b_empty[sb]);
+                                                if (b == sg.kh - 1 && cg == sg.kw / sg.g - 1) umma_commit_t<true>(&a_empty[sa]);
+                                            }
+                                            __syncwarp();
+                                            if (++sb == SB) { sb = 0; phb ^= 1u; }
+                                        }
+                                    }
+                                }
+                                if (++sa == SA) { sa = 0; pha ^= 1u; }
+                            }
+                        }
+                        if (elect_one()) umma_commit_t<true>(&step_done[wi]);
+                        __syncwarp();
+                    }
+            }
+            if (p.dbg != nullptr && elect_one()) {
+                unsigned long long* o = p.dbg + (size_t)(blockIdx.x >> 1) * 4;
+                o[0] = (unsigned long long)(clock64() - t_begin); o[1] = (unsigned long long)w_slot;
+                o[2] = (unsigned long long)w_a; o[3] = (unsigned long long)w_b;
+            }
+        }
+    } else {
+        // ================================================================ epilogue: warps 2..5 drain brick 0, warps 7..10 brick 1
+        const int wi = warp >= 7 ? 1 : 0;
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int rh = row >> 3, rw = row & 7;
+        const int etid = ((warp - (wi ? 7 : 2)) << 5) + lane;       // 0..127 within the group
+        float* bvec = bvec_all + wi * BNs;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t free_r = leader_addr(&slot_free[wi]);
+        // every MMA accumulates: the three slots of this group's brick start as zeros
+        for (int c = 0; c < 3 * BNs; c += 16) tmem_zero16(lane_base + (uint32_t)(wi * 3 * BNs + c));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(free_r);
+        uint32_t phd = 0;
+        int cur_n = -1;
+        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);       // STATS: (sum, sum sq) of columns 2 lane, 2 lane + 1 over this warp's rows
+        int stat_n = -1;
+        auto flush = [&](int n) {
+            *reinterpret_cast<float4*>(p.gn_partial + (((long long)n * p.gn_nchunks_total + p.gn_chunk_base + (long long)blockIdx.x * 8 + wi * 4 + q) * 64) * 2 +
+                                       4 * lane) = st;
+            st = make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        for (int item = item0; item < p.total_items; item += istep) {
+            const RollItem it = roll_item(p, item);
+            const int n = it.n;
+            if (n != cur_n) {          // uniform over the four warps of the group (same item sequence)
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + wi) : "memory");
+                for (int c = etid; c < BNs; c += 128) {
+                    float v = 0.f;
+                    if (c < p.Cout8) {
+                        if (p.bias) v += __ldg(p.bias + c);
+                        if (p.emb) v += __ldg(p.emb + (long long)n * p.emb_stride + c);
+                    }
+                    bvec[c] = v;
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + wi) : "memory");
+                cur_n = n;
+            }
+            if constexpr (STATS) {
+                if (n != stat_n) {
+                    if (stat_n >= 0) flush(stat_n);
+                    stat_n = n;
+                }
+            }
+            const int w = (2 * it.iwp + rank) * H_BW + rw;
+            for (int t = 0; t < it.L + 2; ++t) {
+                {
+                    const int slot = (t + 2) % 3, d = it.d0 - 2 + t;
+                    const uint32_t t_addr = lane_base + (uint32_t)((wi * 3 + slot) * BNs);
+                    const bool store = d >= it.d0 && d < it.d0 + it.L;
+                    const int h = (2 * it.ihp + wi) * H_BH + rh;
+                    const bool valid = store && h < p.Ho && w < p.Wo;
+                    const long long lin = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
+                    // the residual row is requested before waiting for the accumulator: its latency hides behind the MMAs
+                    uint4 rr[BNS / 8];
+#pragma unroll
+                    for (int g = 0; g < BNS / 8; ++g)
+                        rr[g] = (p.residual != nullptr && valid && 8 * g < p.Cout8) ? ldg_nc_u4(p.residual + lin * p.res_stride + 8 * g)
+                                                                                    : make_uint4(0, 0, 0, 0);
+                    mbar_wait(&step_done[wi], phd);
+                    phd ^= 1u;
+                    tc_fence_after();
+                    uint32_t r[BNS];
+                    if (store) load_slot<BNS>(t_addr, r);
+                    // hand the slot back first: zero it (and, at the end of the segment, the two slots holding partial
+                    // sums of planes outside it); the global-memory half of the epilogue is off the MMA's critical path
+                    if (t == it.L + 1) {
+                        for (int c = 0; c < 3 * BNs; c += 16) tmem_zero16(lane_base + (uint32_t)(wi * 3 * BNs + c));
+                    } else {
+                        for (int c = 0; c < BNs; c += 16) tmem_zero16(t_addr + c);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(free_r);
+                    if (store) {
+                        const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw;
+                        void* y_row = p.y_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.y) + yoff)
+                                                 : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff);
+                        finish_row<BNS, STATS>(r, rr, p.Cout8, bvec, y_row, p.y_is_f32, valid);
+                        if constexpr (STATS) {       // squares first: the reduction destroys its input
+                            float b[64];
+#pragma unroll
+                            for (int i = 0; i < 64; ++i) b[i] = __uint_as_float(r[i]) * __uint_as_float(r[i]);
+                            const float2 sb = warp_colsum64(b, lane);
+#pragma unroll
+                            for (int i = 0; i < 64; ++i) b[i] = __uint_as_float(r[i]);
+                            const float2 sa = warp_colsum64(b, lane);
+                            st.x += sa.x; st.y += sb.x; st.z += sa.y; st.w += sb.y;
+                        }
+                    }
+                }
+            }
+        }
+        if constexpr (STATS) {
+            if (stat_n >= 0) flush(stat_n);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host
+template <int G, bool STATS, int BNS>
+static int launch_roll(const RollParams& p, int grid, size_t smem, cudaStream_t stream) {
+    auto* fn = conv_roll_kernel<G, STATS, BNS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(R_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
+    if (e != cudaSuccess) return (int)e;
+    return launch_result();
+}
+
+// geometry shared with gg_conv_stats_chunks: brick pairs, depth segmentation, grid
+struct RollGeom { int BNs, thp, twp, nsd, Lseg, items, grid; };
+static RollGeom roll_geom(const gg_conv_args* a) {
+    RollGeom g;
+    g.BNs = (a->Cout + 15) / 16 * 16;
+    const int th = (a->Ho + H_BH - 1) / H_BH, tw = (a->Wo + H_BW - 1) / H_BW;
+    g.thp = (th + 1) / 2; g.twp = (tw + 1) / 2;
+    const int npairs = std::max(1, num_sms() / 2);
+    const int64_t cols = (int64_t)a->N * g.thp * g.twp;
+    // a segment of L output planes costs L + 2 steps; pick the segmentation with the shortest critical path
+    int64_t best = -1;
+    g.nsd = 1; g.Lseg = a->Do;
+    for (int nsd = 1; nsd <= a->Do; ++nsd) {
+        const int L = (a->Do + nsd - 1) / nsd;
+        const int real = (a->Do + L - 1) / L;
+        const int64_t rounds = (cols * real + npairs - 1) / npairs;
+        const int64_t cost = rounds * (L + 2);
+        if (best < 0 || cost < best) { best = cost; g.nsd = real; g.Lseg = L; }
+    }
+    const int64_t items = cols * g.nsd;
+    g.items = (int)std::min<int64_t>(items, INT32_MAX);
+    g.grid = 2 * (int)std::min<int64_t>(items, npairs);
+    return g;
+}
+int conv_roll_grid(const gg_conv_args* a) { return roll_geom(a).grid; }
+
+int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
+    GG_REQUIRE(a->stride == 1 && a->dims == 3, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(a->kd == 3 && a->od == -1, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(a->nsrc >= 1 && a->nsrc <= H_MAX_SEGS && !a->src[0].centre_only, GG_ERR_BAD_ARG);
+    if (!encode_fn()) return GG_ERR_DRIVER;
+    RollParams p;
+    memset(&p, 0, sizeof(p));
+    const RollGeom g = roll_geom(a);
+    GG_REQUIRE(g.BNs == 16 || g.BNs == 64, GG_ERR_UNSUPPORTED);      // instantiated slot widths (3 BNs <= 256)
+    GG_REQUIRE((int64_t)a->N * g.thp * g.twp * g.nsd < (1ll << 31), GG_ERR_UNSUPPORTED);
+    p.BNs = g.BNs;
+    p.No = a->N; p.Do = a->Do; p.Ho = a->Ho; p.Wo = a->Wo;
+    p.thp = g.thp; p.twp = g.twp; p.nsd = g.nsd; p.Lseg = g.Lseg; p.total_items = g.items;
+    p.Cout8 = (a->Cout + 7) / 8 * 8;
+    const int64_t W = a->W, H = a->H, D = a->D, N = a->N;
+    uint32_t max_a = 0;
+    int num_kb = 0, kwmax = 1;
+    for (int s = 0; s < a->nsrc; ++s) {
+        const gg_conv_src& src = a->src[s];
+        GG_REQUIRE(src.x != nullptr && src.C > 0 && src.C % 8 == 0, GG_ERR_BAD_ARG);
+        GG_REQUIRE(aligned(src.x, 16), GG_ERR_ALIGNMENT);
+        RollSeg& sg = p.seg[s];
+        sg.nchunks = (src.C + BK - 1) / BK;
+        sg.dshift = src.d_shift;
+        sg.centre = src.centre_only ? 1 : 0;
+        if (src.centre_only) { sg.kh = sg.kw = 1; sg.oh = sg.ow = 0; sg.taps = 1; }
+        else { sg.kh = a->kh; sg.kw = a->kw; sg.oh = a->oh; sg.ow = a->ow; sg.taps = 3 * a->kh * a->kw; }
+        sg.pitch = H_BW + sg.kw - 1;
+        sg.a_bytes = (uint32_t)((H_BH + sg.kh - 1) * sg.pitch) * 128u;
+        max_a = std::max(max_a, sg.a_bytes);
+        kwmax = std::max(kwmax, sg.kw);
+        sg.kb_base = num_kb;
+        const int64_t C = src.C;
+        const int64_t dim[4] = {W, H, D, N};
+        const int64_t str[4] = {C, W * C, H * W * C, D * H * W * C};
+        const int box[4] = {sg.pitch, H_BH + sg.kh - 1, 1, 1};
+        if (!encode_act_map(&p.amap[s], src.x, src.C, dim, str, box)) return GG_ERR_DRIVER;
+        num_kb += sg.nchunks * sg.taps;
+    }
+    p.nseg = a->nsrc;
+    if (!encode_w_map(&p.wmap, a->w_packed, (int64_t)num_kb * BK, a->Cout, g.BNs / 2)) return GG_ERR_DRIVER;
+    p.a_stage_bytes = (max_a + 1023u) & ~1023u;
+    p.b_unit_bytes = (uint32_t)(g.BNs / 2) * 128u;
+    const int bar_bytes = 512 + 1024;        // barriers + two [BNs] additive vectors
+    const int avail = H_SMEM_BUDGET - 1024 - bar_bytes;
+    int G = kwmax, SA = 3;
+    const int tap_bytes = 3 * (int)p.b_unit_bytes;
+    int SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes);
+    if (SB < 3) { G = 1; SB = (avail - SA * (int)p.a_stage_bytes) / tap_bytes; }
+    GG_REQUIRE(SB >= 2, GG_ERR_UNSUPPORTED);
+    if (SB > R_MAX_SB) {
+        SA = std::min(R_MAX_SA, (avail - R_MAX_SB * G * tap_bytes) / (int)p.a_stage_bytes);
+        SB = R_MAX_SB;
+    }
+    GG_REQUIRE(G == 1 || G == 3, GG_ERR_UNSUPPORTED);
+    p.b_stage_bytes = (uint32_t)(G * tap_bytes);
+    for (int s = 0; s < a->nsrc; ++s) p.seg[s].g = (G > 1 && p.seg[s].kw == G) ? G : 1;
+    p.SA = SA; p.SB = SB;
+    const size_t smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * p.b_stage_bytes + bar_bytes + 1024;
+
+    p.bias = a->bias; p.emb = a->emb; p.emb_stride = a->emb_stride;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.res_stride = a->res_stride;
+    p.y = a->y; p.y_sn = a->y_sn; p.y_sd = a->y_sd; p.y_sh = a->y_sh; p.y_sw = a->y_sw; p.y_is_f32 = a->y_is_f32;
+
+    static unsigned long long* dbg_buf = nullptr;
+    const bool dbg = getenv("GG_ROLL_DBG") != nullptr;
+    if (dbg) {
+        if (!dbg_buf && cudaMalloc(&dbg_buf, 4096 * sizeof(unsigned long long)) != cudaSuccess) return GG_ERR_DRIVER;
+        cudaMemsetAsync(dbg_buf, 0, 4096 * sizeof(unsigned long long), stream);
+        p.dbg = dbg_buf;
+    }
+    struct DbgPrint {
+        bool on; int pairs; cudaStream_t st; unsigned long long* buf;
+        ~DbgPrint() {
+            if (!on) return;
+            cudaStreamSynchronize(st);
+            std::vector<unsigned long long> h((size_t)pairs * 4);
+            cudaMemcpy(h.data(), buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            double s[4] = {0, 0, 0, 0};
+            for (int i = 0; i < pairs; ++i) for (int k = 0; k < 4; ++k) s[k] += (double)h[(size_t)i * 4 + k] / pairs;
+            fprintf(stderr, "[conv_roll] MMA issuer clocks: total %.0f, waiting slot_free %.0f, a_full %.0f, b_full %.0f (avg of %d pairs)\n",
+                    s[0], s[1], s[2], s[3], pairs);
+        }
+    } dbg_print{dbg, g.grid / 2, stream, dbg_buf};
+    if (a->gn_partial != nullptr) {
+        GG_REQUIRE(g.BNs == 64 && p.Cout8 == 64 && !a->y_is_f32, GG_ERR_UNSUPPORTED);
+        GG_REQUIRE(aligned(a->gn_partial, 16) && a->gn_chunk_base >= 0 && a->gn_chunk_base + g.grid * 8 <= a->gn_nchunks_total, GG_ERR_BAD_ARG);
+        p.gn_partial = a->gn_partial; p.gn_chunk_base = a->gn_chunk_base; p.gn_nchunks_total = a->gn_nchunks_total;
+        for (int n = 0; n < a->N; ++n) {
+            cudaError_t e = cudaMemsetAsync(a->gn_partial + ((size_t)n * a->gn_nchunks_total + a->gn_chunk_base) * 128, 0,
+                                            (size_t)g.grid * 8 * 128 * sizeof(float), stream);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return G == 3 ? launch_roll<3, true, 64>(p, g.grid, smem, stream) : launch_roll<1, true, 64>(p, g.grid, smem, stream);
+    }
+    if (g.BNs == 16) return G == 3 ? launch_roll<3, false, 16>(p, g.grid, smem, stream) : launch_roll<1, false, 16>(p, g.grid, smem, stream);
+    return G == 3 ? launch_roll<3, false, 64>(p, g.grid, smem, stream) : launch_roll<1, false, 64>(p, g.grid, smem, stream);
+}
+
+}  // namespace gg

@@ -490,6 +490,10 @@ extern "C" int32_t gg_conv_stats_chunks(const gg_conv_args* a) {
         if (BNh != 64 || (a->Cout + 7) / 8 * 8 != 64 || a->y_is_f32) return 0;
         return conv_halo_grid(a, nullptr) * 4;
     }
+    if (a->algo == 4) {
+        if ((a->Cout + 7) / 8 * 8 != 64 || a->y_is_f32) return 0;
+        return conv_roll_grid(a) * 8;      // one row per (CTA, epilogue warp): two groups of four warps
+    }
     int brick[4];
     if (a->brick[0] > 0) { for (int i = 0; i < 4; ++i) brick[i] = a->brick[i]; }
     else pick_brick(a->N, a->Do, a->Ho, a->Wo, brick);
@@ -522,6 +526,7 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
     if (a->emb) GG_REQUIRE(aligned(a->emb, 16) && a->emb_stride % 4 == 0, GG_ERR_ALIGNMENT);
     if (!encode_fn()) return GG_ERR_DRIVER;
     if (a->algo >= 1 && a->algo <= 3) return conv_halo_fwd(a, as_stream(stream));
+    if (a->algo == 4) return conv_roll_fwd(a, as_stream(stream));
 
     ConvParams p;
     memset(&p, 0, sizeof(p));

@@ -174,5 +174,7 @@ bool encode_act_map(CUtensorMap* m, const void* base, int C, const int64_t dim[4
 bool encode_w_map(CUtensorMap* m, const void* base, int64_t Ktot, int rows, int BN);
 int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream);   // conv_halo.cu
 int conv_halo_grid(const gg_conv_args* a, bool* pair_out);       // CTAs conv_halo_fwd launches for `a`
+int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream);   // conv_roll.cu (algo 4)
+int conv_roll_grid(const gg_conv_args* a);
 
 }  // namespace gg

@@ -170,6 +170,7 @@ class UNetEngine:
         self.num_head_channels = num_head_channels
         self.fused_upsample = fused_upsample
         self.use_halo_conv = True
+        self.use_roll_conv = True
         self.use_split_k = True
         self.num_sms = torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count \
             if next(model.parameters()).is_cuda else 148
@@ -296,8 +297,11 @@ class UNetEngine:
         # the halo kernel keeps GroupNorm column sums in registers when one 64-wide tile covers all output channels
         halo_stats = halo and stats and self.halo_gn_stats and cout8 == 64 and not f32_out
         algo = 1 if halo and (halo_stats or not (stats and self.fused_gn_stats)) else 0
+        if (algo == 1 and self.use_roll_conv and dims == 3 and tuple(taps) == (3, 3, 3) and tuple(offsets) == (-1, -1, -1)
+                and (cout + 15) // 16 * 16 in (16, 64) and out_spatial[1] >= 32 and out_spatial[2] >= 16 and y_strides is None):
+            algo = 4        # narrow outputs: depth-rolling kernel (three depth taps stacked along N)
         if callable(w_packed):          # packed-weight K order depends on the kernel
-            w_packed = w_packed(algo == 1)
+            w_packed = w_packed(algo >= 1)
         else:
             algo = 0
         lead = x0.lead

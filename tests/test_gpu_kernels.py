@@ -328,6 +328,15 @@ CONV_CASES = {
     "halo_pair_head_f32": dict(N=1, sp=(4, 16, 16), Cs=[64], Cout=12, dims=3, f32_out=True, algo=3),
     "halo_pair_many_tiles": dict(N=2, sp=(16, 64, 64), Cs=[64], Cout=64, dims=3, residual=True, algo=3, stats=True),
     "halo_pair_cout_192": dict(N=1, sp=(2, 32, 16), Cs=[128], Cout=192, dims=3, algo=3),
+    # depth-rolling kernel (algo 4): three depth taps stacked along N, two interleaved bricks per CTA, CTA pairs
+    "roll_64": dict(N=1, sp=(4, 32, 16), Cs=[64], Cout=64, dims=3, algo=4),
+    "roll_one_plane": dict(N=2, sp=(1, 32, 16), Cs=[64], Cout=64, dims=3, algo=4),
+    "roll_all": dict(N=2, sp=(5, 32, 32), Cs=[128, 64], Cout=64, dims=3, extra_C=192, emb=True, residual=True, algo=4, stats=True),
+    "roll_ragged_odd": dict(N=3, sp=(7, 20, 21), Cs=[16], Cout=64, dims=3, emb=True, algo=4, stats=True),
+    "roll_head_f32": dict(N=1, sp=(6, 32, 16), Cs=[64], Cout=12, dims=3, f32_out=True, algo=4),
+    "roll_cout_60": dict(N=1, sp=(3, 16, 16), Cs=[192], Cout=60, dims=3, residual=True, algo=4),
+    "roll_many_items": dict(N=2, sp=(16, 64, 64), Cs=[64], Cout=64, dims=3, residual=True, algo=4, stats=True),
+    "roll_deep": dict(N=1, sp=(40, 32, 16), Cs=[64], Cout=64, dims=3, algo=4),
 }
 
 

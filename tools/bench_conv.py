@@ -1,0 +1,62 @@
+"""Micro-benchmark of the stride-1 3x3x3 conv kernels on one layer shape (tuning aid, not a bench line).
+Usage: python tools/bench_conv.py [N D H W]   -- prints ms and TFLOP/s per (algo, Cin, Cout, epilogue variant)."""
+import ctypes as C
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from jointimagegeneration_b200 import _C, ops
+    N, D, H, W = [int(v) for v in sys.argv[1:5]] if len(sys.argv) >= 5 else (8, 64, 128, 128)
+    algos = [int(v) for v in os.environ.get("ALGOS", "2,3,4").split(",")]
+    rs = np.random.RandomState(0)
+    dev = "cuda"
+    cases = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("CASES", "64:64,128:64,64:12,128:128").split(",")]
+    variants = os.environ.get("VARIANTS", "plain,res,stats,res+stats").split(",")
+    for Cin, Cout in cases:
+        x = torch.randn((N, D, H, W, Cin), device=dev, dtype=torch.bfloat16)
+        w = torch.from_numpy((rs.standard_normal((Cout, Cin, 3, 3, 3)) / math.sqrt(Cin * 27)).astype(np.float32)).to(dev)
+        b = torch.zeros(Cout, device=dev)
+        Cout8 = (Cout + 7) // 8 * 8
+        res = torch.randn((N, D, H, W, Cout8), device=dev, dtype=torch.bfloat16)
+        for algo in algos:
+            if algo == 4 and Cout > 80:
+                continue
+            wp = ops.pack_conv_weight(w, [Cin], chunk_major=True)
+            for variant in variants:
+                if "stats" in variant and Cout8 != 64:
+                    continue
+                y = torch.empty((N, D, H, W, Cout8), device=dev, dtype=torch.bfloat16)
+                bp = ops.pad_vec(b, Cout)
+                a = ops.make_conv_args([(x, False)], wp, Cout, y, dims=3, ksize=3, stride=1, bias=bp,
+                                       residual=res if "res" in variant else None, algo=algo)
+                part = None
+                if "stats" in variant:
+                    per = int(_C.lib().gg_conv_stats_chunks(C.byref(a)))
+                    part = torch.empty((N, per, Cout8, 2), device=dev)
+                    a.gn_partial, a.gn_chunk_base, a.gn_nchunks_total = _C.ptr(part), 0, per
+                for _ in range(2):
+                    ops.conv_fwd(a)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 5
+                e0.record()
+                for _ in range(reps):
+                    ops.conv_fwd(a)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                fl = 2.0 * N * D * H * W * Cout * Cin * 27
+                print(f"Cin {Cin:4d} Cout {Cout:4d} algo {algo} {variant:10s}: {ms:7.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
+        del x, res
+
+
+if __name__ == "__main__":
+    main()
