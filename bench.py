@@ -221,6 +221,9 @@ def run_ours(args):
     c_host = cond.cpu().pin_memory()
     out_host = torch.empty((B, Cc) + sp, dtype=torch.int64).pin_memory()
     Ke = max(2, min(K, 10))
+    # one untimed short call first: the public path's own one-time work (its plan / graph for this call signature,
+    # pinned staging buffers) is not part of a steady-state step
+    model(x_host, c_host, t=torch.tensor(10000 + 2), context=context)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

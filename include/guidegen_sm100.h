@@ -271,6 +271,16 @@ typedef struct {
      * and applies bias / emb / residual.  split_k <= 1: off. */
     int32_t split_k;
     float* workspace;
+    /* Fused GroupNorm + SiLU on the INPUT (algo 4 only): when src_ss[i] is not NULL, source i is the raw,
+     * un-normalised activation and the kernel applies  silu?(x * scale + shift)  to each halo plane in shared
+     * memory before the MMAs read it (the separate gg_gn_apply pass and its tensor disappear).  src_ss[i] points
+     * at the (scale, shift) pair of the source's first channel for sample 0 -- gg_gn_finalize's output, offset by
+     * the source's position in a concatenated norm -- and ss_stride is the number of floats between samples.
+     * Positions outside the tensor stay zero (the reference zero-pads the normalised tensor): in h / w by bounds,
+     * in depth for local planes z outside [xf_z_lo, xf_z_hi) (0..D unsplit; a depth slab widens it by the halo
+     * planes that hold a neighbour's data). */
+    const float* src_ss[4];
+    int32_t ss_stride, xf_silu, xf_z_lo, xf_z_hi;
 } gg_conv_args;
 
 /* N tile (accumulator columns) the kernel uses for a given Cout */

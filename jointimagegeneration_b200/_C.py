@@ -81,7 +81,9 @@ class ConvArgs(C.Structure):
                 ("y_sn", C.c_int64), ("y_sd", C.c_int64), ("y_sh", C.c_int64), ("y_sw", C.c_int64),
                 ("y_is_f32", C.c_int32), ("Cout", C.c_int32), ("block_n", C.c_int32), ("brick", C.c_int32 * 4),
                 ("gn_partial", C.c_void_p), ("gn_chunk_base", C.c_int32), ("gn_nchunks_total", C.c_int32),
-                ("stats_d_min", C.c_int32), ("algo", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p)]
+                ("stats_d_min", C.c_int32), ("algo", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p),
+                ("src_ss", C.c_void_p * 4), ("ss_stride", C.c_int32), ("xf_silu", C.c_int32),
+                ("xf_z_lo", C.c_int32), ("xf_z_hi", C.c_int32)]
 
 
 class AttnArgs(C.Structure):

@@ -32,20 +32,28 @@ namespace gg {
 
 constexpr int R_MAX_SA = 4, R_MAX_SB = 6;
 constexpr int R_THREADS = 352;      // warps 0, 1, 6 = producers / MMA; warps 2..5 drain brick 0, warps 7..10 drain brick 1
+constexpr int R_THREADS_XF = 480;   // + warps 11..14: GroupNorm/SiLU transform of the landed halo planes
+constexpr int R_STAGE_BYTES = 16384; // 128 rows x 128 B output / residual staging tile
+constexpr int R_SS_BYTES = 4096;    // (scale, shift) table: up to 512 channels over all sources
 
 struct RollSeg {
     int nchunks, centre;
     int kh, kw, oh, ow, dshift;
-    int pitch;
+    int pitch, inv_pitch;      // rows per h line of the halo plane; ceil(2^16 / pitch)
     uint32_t a_bytes;
     int g;           // kw taps per B stage (kw or 1)
     int kb_base;     // first 64-wide K block of this source in the packed weights
     int taps;        // K blocks per chunk: 3 kh kw, or 1 (centre_only)
+    int C;           // channels
+    int ss_off;      // XFORM: first entry of this source in the shared (scale, shift) table, -1 = used as is
+    const float* ss; // XFORM: (scale, shift) of channel 0, sample 0
 };
 
 struct alignas(64) RollParams {
     CUtensorMap amap[H_MAX_SEGS];
     CUtensorMap wmap;              // box = 64 k x (BNs / 2) weight rows: one "unit" = half a slot
+    CUtensorMap ymap, rmap;        // tma_epi: output / residual bricks (64 ch x 8 w x 16 h), SWIZZLE_128B
+    int tma_epi;                   // bf16 64-channel outputs leave (and residuals arrive) through a staging tile + TMA
     RollSeg seg[H_MAX_SEGS];
     int nseg, BNs, SA, SB;
     uint32_t a_stage_bytes, b_stage_bytes, b_unit_bytes;
@@ -62,6 +70,7 @@ struct alignas(64) RollParams {
     int y_is_f32;
     float* gn_partial;
     int gn_chunk_base, gn_nchunks_total;
+    int ss_stride, xf_silu, z_lo, z_hi, ss_entries;      // XFORM (fused GroupNorm + SiLU on the input planes)
     unsigned long long* dbg;       // tuning aid (GG_ROLL_DBG=1): per leader CTA, clocks the MMA issuer spent in each wait
 };
 
@@ -71,6 +80,12 @@ __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
         ::"r"(taddr), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 
 // accumulator slot -> registers (the slot is handed back to the tensor core BEFORE the row is finished and stored)
 template <int BNS>
@@ -83,7 +98,7 @@ __device__ __forceinline__ void load_slot(uint32_t t_addr, uint32_t (&r)[BNS]) {
 // stored (bf16-rounded) values as floats, zeros for rows outside the tensor, for warp_colsum64.
 template <int BNS, bool STATS>
 __device__ __forceinline__ void finish_row(uint32_t (&r)[BNS], const uint4 (&rr)[BNS / 8], int ncols, const float* __restrict__ bvec,
-                                           void* y_row, int y_is_f32, bool valid) {
+                                           void* y_row, int y_is_f32, bool valid, bool to_stage = false, int swz = 0) {
 #pragma unroll
     for (int g = 0; g < BNS / 8; ++g) {
         const float4 b0 = *reinterpret_cast<const float4*>(bvec + 8 * g), b1 = *reinterpret_cast<const float4*>(bvec + 8 * g + 4);
@@ -100,7 +115,9 @@ __device__ __forceinline__ void finish_row(uint32_t (&r)[BNS], const uint4 (&rr)
             }
         } else {
             const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            if (valid && 8 * g < ncols) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_row) + 8 * g) = pk;
+            // to_stage: the row goes to the swizzled staging tile (every row, TMA clips), else straight to global memory
+            if (to_stage) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_row) + 8 * (g ^ swz)) = pk;
+            else if (valid && 8 * g < ncols) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_row) + 8 * g) = pk;
             if constexpr (STATS) {
                 const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
@@ -140,21 +157,49 @@ __device__ __forceinline__ RollItem roll_item(const RollParams& p, int item) {
     return it;
 }
 
-template <int G, bool STATS, int BNS>
-__global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_constant__ RollParams p) {
+// Transform of one bf16 pair (packed f32x2 arithmetic, two FMAs per instruction).  q = (s0, s1, b0, b1) of the two
+// channels.  SiLU: q is pre-halved so that h = x s/2 + b/2 = v/2 exactly, and silu(v) = v sigmoid(v) = h + h tanh(h)
+// (one MUFU per element; the same formulation and rounding points as gg_gn_apply).
+__device__ __forceinline__ uint32_t xf_pair(uint32_t w, float4 q, bool silu) {
+    uint64_t x, sc, sh, h;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(w << 16), "r"(w & 0xffff0000u));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sc) : "f"(q.x), "f"(q.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sh) : "f"(q.z), "f"(q.w));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(h) : "l"(x), "l"(sc), "l"(sh));
+    float h0, h1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(h));
+    if (silu) {
+        float t0, t1;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+        uint64_t t, y;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+        asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(y) : "l"(h), "l"(t));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(y));
+    }
+    return pack_bf16(h0, h1);
+}
+
+template <int G, bool STATS, int BNS, bool XFORM>
+__global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll_kernel(const __grid_constant__ RollParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int SA = p.SA, SB = p.SB;
     constexpr int BNs = BNS;
     uint8_t* smem_b = smem + (size_t)SA * p.a_stage_bytes;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)SB * p.b_stage_bytes);
+    uint8_t* smem_c = smem_b + (size_t)SB * p.b_stage_bytes;            // tma_epi: one 16 KB staging tile per epilogue group
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_c + (p.tma_epi ? 2 * R_STAGE_BYTES : 0));
     uint64_t* a_empty = a_full + R_MAX_SA;
     uint64_t* b_full = a_empty + R_MAX_SA;
     uint64_t* b_empty = b_full + R_MAX_SB;
     uint64_t* step_done = b_empty + R_MAX_SB;       // [wi]: the MMAs of one step of brick wi have completed
     uint64_t* slot_free = step_done + 2;            // [wi] (leader's): finished slot of brick wi drained and zeroed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_free + 2);
+    uint64_t* a_ready = slot_free + 2;              // XFORM (leader's): plane landed AND transformed in both CTAs
+    uint64_t* res_full = a_ready + R_MAX_SA;        // [wi] tma_epi: residual brick landed in the staging tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+    // XFORM: per channel PAIR (2k, 2k+1) the quad (s_2k, s_2k+1, b_2k, b_2k+1), halved when SiLU follows: [ss_entries / 2]
+    float4* ss_tab = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a_full) + 1024);
     float* bvec_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512);  // [2][BNs] bias + emb[n], per epilogue group
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -166,9 +211,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 8); }
             for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&step_done[i], 1); mbar_init(&slot_free[i], 8); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&step_done[i], 1); mbar_init(&slot_free[i], 8); mbar_init(&res_full[i], 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -198,9 +243,21 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
                         for (int j = 0; j < sg.nchunks; ++j) {
                             mbar_wait(&a_empty[sa], pha ^ 1u);
                             if (elect_one()) {
-                                if (rank == 0) mbar_expect_tx(&a_full[sa], 2u * sg.a_bytes);
-                                tma_load_5d_pair(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], leader_addr(&a_full[sa]), j * BK,
-                                                 w0 + sg.ow, h0 + sg.oh, z + sg.dshift, it.n);
+                                if constexpr (XFORM) {      // each CTA's transform warps watch their own plane land
+                                    mbar_expect_tx(&a_full[sa], sg.a_bytes);
+                                    tma_load_5d(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], &a_full[sa], j * BK, w0 + sg.ow,
+                                                h0 + sg.oh, z + sg.dshift, it.n);
+                                    // the transform is one more hop between HBM and the tensor core and the plane ring is
+                                    // only four deep: pull the plane of two steps ahead into L2 now
+                                    if (t + 2 < it.L + 2)
+                                        asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+                                                     ::"l"(&p.amap[s]), "r"(j * BK), "r"(w0 + sg.ow), "r"(h0 + sg.oh), "r"(z + 2 + sg.dshift), "r"(it.n)
+                                                     : "memory");
+                                } else {
+                                    if (rank == 0) mbar_expect_tx(&a_full[sa], 2u * sg.a_bytes);
+                                    tma_load_5d_pair(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], leader_addr(&a_full[sa]), j * BK,
+                                                     w0 + sg.ow, h0 + sg.oh, z + sg.dshift, it.n);
+                                }
                             }
                             __syncwarp();
                             if (++sa == SA) { sa = 0; pha ^= 1u; }
@@ -284,8 +341,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
                             const uint64_t a_tmpl = make_sw128_desc_sbo(0, (uint32_t)sg.pitch * 128u);
                             for (int j = 0; j < sg.nchunks; ++j) {
                                 tq = clock64();
-                                mbar_wait(&a_full[sa], pha);
+                                mbar_wait(XFORM ? &a_ready[sa] : &a_full[sa], pha);
                                 w_a += clock64() - tq;
+                                if constexpr (XFORM) tc_fence_after();
                                 const uint32_t a_stage16 = (a_base + (uint32_t)sa * p.a_stage_bytes) >> 4;
                                 if (sg.centre) {
                                     mbar_wait(&b_full[sb], phb);
@@ -344,6 +402,89 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
                 o[2] = (unsigned long long)w_a; o[3] = (unsigned long long)w_b;
             }
         }
+    } else if (XFORM && warp >= 11) {
+        // ================================================================ transform (warps 11..14): GroupNorm (+ SiLU) in place
+        // on each landed halo plane.  Rows are 128 B = 64 channels, SWIZZLE_128B: the 16-byte chunk at physical
+        // slot jp of stage row r holds channels 8 (jp ^ (r & 7)) .. +7.  Rows outside the tensor stay zero.
+        const int xt = (int)threadIdx.x - R_THREADS;        // 0..127
+        int sa = 0, cur_n = -1;
+        uint32_t pha = 0;
+        const bool silu = p.xf_silu != 0;
+        long long x_wait = 0, x_begin = clock64(), xq;
+        for (int item = item0; item < p.total_items; item += istep) {
+            const RollItem it = roll_item(p, item);
+            if (it.n != cur_n) {        // (scale, shift) of this sample; uniform over the four warps
+                asm volatile("bar.sync 3, 128;" ::: "memory");
+                for (int s = 0; s < p.nseg; ++s) {
+                    const RollSeg sg = p.seg[s];
+                    if (sg.ss_off < 0) continue;
+                    const float4* src = reinterpret_cast<const float4*>(sg.ss + (long long)it.n * p.ss_stride);
+                    const float k = silu ? 0.5f : 1.f;
+                    for (int c = xt; c < sg.nchunks * (BK / 2); c += 128) {
+                        const float4 v = 2 * c < sg.C ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);      // (s0, b0, s1, b1)
+                        ss_tab[(sg.ss_off >> 1) + c] = make_float4(k * v.x, k * v.z, k * v.y, k * v.w);
+                    }
+                }
+                asm volatile("bar.sync 3, 128;" ::: "memory");
+                cur_n = it.n;
+            }
+            const int w0 = (2 * it.iwp + rank) * H_BW;
+            for (int t = 0; t < it.L + 2; ++t)
+                for (int wi = 0; wi < 2; ++wi) {
+                    const int h0 = (2 * it.ihp + wi) * H_BH, z = it.d0 - 1 + t;
+                    for (int s = 0; s < p.nseg; ++s) {
+                        const RollSeg sg = p.seg[s];
+                        if (sg.centre && (t == 0 || t == it.L + 1)) continue;
+                        for (int j = 0; j < sg.nchunks; ++j) {
+                            xq = clock64();
+                            mbar_wait(&a_full[sa], pha);
+                            x_wait += clock64() - xq;
+                            if (sg.ss_off >= 0 && z >= p.z_lo && z < p.z_hi) {
+                                uint8_t* stg = smem + (size_t)sa * p.a_stage_bytes;
+                                const int nrow = (H_BH + sg.kh - 1) * sg.pitch;
+                                // thread -> (logical 8-channel group jl, row group): its four channel-pair quads stay in
+                                // registers for the whole plane; 8 consecutive threads cover one 128-byte row
+                                const int jl = xt & 7;
+                                const float4* tb = ss_tab + ((sg.ss_off + j * BK) >> 1) + 4 * jl;
+                                const float4 q0 = tb[0], q1 = tb[1], q2 = tb[2], q3 = tb[3];
+                                // four rows per batch, loads first: a lone warp per scheduler needs the ILP (a per-row
+                                // branch would serialise LDS -> FMA -> MUFU -> FMA -> STS chains)
+#pragma unroll 1
+                                for (int r0 = xt >> 3; r0 < nrow; r0 += 64) {
+                                    uint4 v[4];
+                                    uint4* ptr[4];
+                                    bool ok[4];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const int r = r0 + 16 * u, rc = min(r, nrow - 1);
+                                        const int hh = (int)(((uint32_t)rc * (uint32_t)sg.inv_pitch) >> 16), ww = rc - hh * sg.pitch;    // rc < 2^10
+                                        const int gh = h0 + sg.oh + hh, gw = w0 + sg.ow + ww;
+                                        ok[u] = r < nrow && gh >= 0 && gh < p.Ho && gw >= 0 && gw < p.Wo;      // stride 1: input extent = output extent
+                                        ptr[u] = reinterpret_cast<uint4*>(stg + rc * 128 + ((jl ^ (rc & 7)) << 4));
+                                        v[u] = *ptr[u];
+                                    }
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        v[u].x = xf_pair(v[u].x, q0, silu); v[u].y = xf_pair(v[u].y, q1, silu);
+                                        v[u].z = xf_pair(v[u].z, q2, silu); v[u].w = xf_pair(v[u].w, q3, silu);
+                                    }
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u)
+                                        if (ok[u]) *ptr[u] = v[u];
+                                }
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> tensor-core reads
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_remote(leader_addr(&a_ready[sa]));
+                            if (++sa == SA) { sa = 0; pha ^= 1u; }
+                        }
+                    }
+                }
+        }
+        if (p.dbg != nullptr && rank == 0 && xt == 0) {
+            unsigned long long* o = p.dbg + 2048 + (size_t)(blockIdx.x >> 1) * 2;
+            o[0] = (unsigned long long)(clock64() - x_begin); o[1] = (unsigned long long)x_wait;
+        }
     } else {
         // ================================================================ epilogue: warps 2..5 drain brick 0, warps 7..10 brick 1
         const int wi = warp >= 7 ? 1 : 0;
@@ -360,7 +501,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(free_r);
-        uint32_t phd = 0;
+        uint32_t phd = 0, ph_res = 0;
         int cur_n = -1;
         float4 st = make_float4(0.f, 0.f, 0.f, 0.f);       // STATS: (sum, sum sq) of columns 2 lane, 2 lane + 1 over this warp's rows
         int stat_n = -1;
@@ -400,12 +541,26 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
                     const int h = (2 * it.ihp + wi) * H_BH + rh;
                     const bool valid = store && h < p.Ho && w < p.Wo;
                     const long long lin = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
-                    // the residual row is requested before waiting for the accumulator: its latency hides behind the MMAs
+                    const bool tma_epi = BNS == 64 && p.tma_epi != 0;
+                    uint8_t* stage = smem_c + wi * R_STAGE_BYTES;
+                    const int hb = (2 * it.ihp + wi) * H_BH, wb = (2 * it.iwp + rank) * H_BW;
+                    // the residual is requested before waiting for the accumulator: its latency hides behind the MMAs
                     uint4 rr[BNS / 8];
+                    if (tma_epi) {
+                        if (store) {
+                            if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous brick left the tile
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + wi) : "memory");
+                            if (p.residual != nullptr && etid == 0) {
+                                mbar_expect_tx(&res_full[wi], R_STAGE_BYTES);
+                                tma_load_5d(stage, &p.rmap, &res_full[wi], 0, wb, hb, d, n);
+                            }
+                        }
+                    } else {
 #pragma unroll
-                    for (int g = 0; g < BNS / 8; ++g)
-                        rr[g] = (p.residual != nullptr && valid && 8 * g < p.Cout8) ? ldg_nc_u4(p.residual + lin * p.res_stride + 8 * g)
-                                                                                    : make_uint4(0, 0, 0, 0);
+                        for (int g = 0; g < BNS / 8; ++g)
+                            rr[g] = (p.residual != nullptr && valid && 8 * g < p.Cout8) ? ldg_nc_u4(p.residual + lin * p.res_stride + 8 * g)
+                                                                                        : make_uint4(0, 0, 0, 0);
+                    }
                     mbar_wait(&step_done[wi], phd);
                     phd ^= 1u;
                     tc_fence_after();
@@ -423,10 +578,28 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(free_r);
                     if (store) {
-                        const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw;
-                        void* y_row = p.y_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.y) + yoff)
-                                                 : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff);
-                        finish_row<BNS, STATS>(r, rr, p.Cout8, bvec, y_row, p.y_is_f32, valid);
+                        if (tma_epi) {
+                            // row `row` of the tile is 128 bytes; SWIZZLE_128B puts its 16-byte chunk g at slot g ^ (row & 7)
+                            uint8_t* srow = stage + row * 128;
+                            if (p.residual != nullptr) {
+                                mbar_wait(&res_full[wi], ph_res);
+                                ph_res ^= 1u;
+#pragma unroll
+                                for (int g = 0; g < BNS / 8; ++g) rr[g] = *reinterpret_cast<const uint4*>(srow + ((g ^ (row & 7)) << 4));
+                            } else {
+#pragma unroll
+                                for (int g = 0; g < BNS / 8; ++g) rr[g] = make_uint4(0, 0, 0, 0);
+                            }
+                            finish_row<BNS, STATS>(r, rr, p.Cout8, bvec, srow, 0, valid, true, row & 7);
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic writes -> TMA store reads
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + wi) : "memory");
+                            if (etid == 0) tma_store_5d(&p.ymap, stage, 0, wb, hb, d, n);
+                        } else {
+                            const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw;
+                            void* y_row = p.y_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.y) + yoff)
+                                                     : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff);
+                            finish_row<BNS, STATS>(r, rr, p.Cout8, bvec, y_row, p.y_is_f32, valid);
+                        }
                         if constexpr (STATS) {       // squares first: the reduction destroys its input
                             float b[64];
 #pragma unroll
@@ -444,6 +617,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
         if constexpr (STATS) {
             if (stat_n >= 0) flush(stat_n);
         }
+        if (BNS == 64 && p.tma_epi != 0 && etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // bricks are in global memory
     }
 
     tc_fence_before();
@@ -456,9 +630,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) conv_roll_kernel(const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------- host
-template <int G, bool STATS, int BNS>
+template <int G, bool STATS, int BNS, bool XFORM>
 static int launch_roll(const RollParams& p, int grid, size_t smem, cudaStream_t stream) {
-    auto* fn = conv_roll_kernel<G, STATS, BNS>;
+    auto* fn = conv_roll_kernel<G, STATS, BNS, XFORM>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
@@ -467,7 +641,7 @@ static int launch_roll(const RollParams& p, int grid, size_t smem, cudaStream_t 
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(R_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(XFORM ? R_THREADS_XF : R_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -519,7 +693,8 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
     p.Cout8 = (a->Cout + 7) / 8 * 8;
     const int64_t W = a->W, H = a->H, D = a->D, N = a->N;
     uint32_t max_a = 0;
-    int num_kb = 0, kwmax = 1;
+    int num_kb = 0, kwmax = 1, ss_entries = 0;
+    bool xform = false;
     for (int s = 0; s < a->nsrc; ++s) {
         const gg_conv_src& src = a->src[s];
         GG_REQUIRE(src.x != nullptr && src.C > 0 && src.C % 8 == 0, GG_ERR_BAD_ARG);
@@ -528,9 +703,19 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
         sg.nchunks = (src.C + BK - 1) / BK;
         sg.dshift = src.d_shift;
         sg.centre = src.centre_only ? 1 : 0;
+        sg.C = src.C;
+        sg.ss = a->src_ss[s];
+        sg.ss_off = -1;
+        if (sg.ss != nullptr) {
+            GG_REQUIRE(aligned(sg.ss, 16) && a->ss_stride % 4 == 0, GG_ERR_ALIGNMENT);
+            sg.ss_off = ss_entries;
+            ss_entries += sg.nchunks * BK;
+            xform = true;
+        }
         if (src.centre_only) { sg.kh = sg.kw = 1; sg.oh = sg.ow = 0; sg.taps = 1; }
         else { sg.kh = a->kh; sg.kw = a->kw; sg.oh = a->oh; sg.ow = a->ow; sg.taps = 3 * a->kh * a->kw; }
         sg.pitch = H_BW + sg.kw - 1;
+        sg.inv_pitch = (65536 + sg.pitch - 1) / sg.pitch;
         sg.a_bytes = (uint32_t)((H_BH + sg.kh - 1) * sg.pitch) * 128u;
         max_a = std::max(max_a, sg.a_bytes);
         kwmax = std::max(kwmax, sg.kw);
@@ -546,18 +731,38 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
     if (!encode_w_map(&p.wmap, a->w_packed, (int64_t)num_kb * BK, a->Cout, g.BNs / 2)) return GG_ERR_DRIVER;
     p.a_stage_bytes = (max_a + 1023u) & ~1023u;
     p.b_unit_bytes = (uint32_t)(g.BNs / 2) * 128u;
-    const int bar_bytes = 512 + 1024;        // barriers + two [BNs] additive vectors
+    GG_REQUIRE(ss_entries * (int)sizeof(float2) <= R_SS_BYTES, GG_ERR_UNSUPPORTED);
+    p.ss_stride = a->ss_stride; p.xf_silu = a->xf_silu; p.z_lo = a->xf_z_lo; p.z_hi = a->xf_z_hi; p.ss_entries = ss_entries;
+    // bf16 64-channel outputs (and their residuals) move through a swizzled staging tile by TMA: coalesced, clipped
+    // by the tensor map, and none of the epilogue's global-memory instructions left to contend with the transform
+    p.tma_epi = (g.BNs == 64 && !a->y_is_f32 && p.Cout8 == 64 && aligned(a->y, 16) && a->y_sw % 8 == 0 && a->y_sh % 8 == 0 &&
+                 a->y_sd % 8 == 0 && a->y_sn % 8 == 0 && (a->residual == nullptr || (aligned(a->residual, 16) && a->res_stride % 8 == 0)))
+                    ? 1 : 0;
+    if (getenv("GG_ROLL_NO_TMA_EPI")) p.tma_epi = 0;       // tuning knob
+    if (p.tma_epi) {
+        const int64_t dim[4] = {a->Wo, a->Ho, a->Do, a->N};
+        const int box[4] = {H_BW, H_BH, 1, 1};
+        const int64_t ystr[4] = {a->y_sw, a->y_sh, a->y_sd, a->y_sn};
+        if (!encode_act_map(&p.ymap, a->y, p.Cout8, dim, ystr, box)) return GG_ERR_DRIVER;
+        if (a->residual != nullptr) {
+            const int64_t rs = a->res_stride;
+            const int64_t rstr[4] = {rs, (int64_t)a->Wo * rs, (int64_t)a->Ho * a->Wo * rs, (int64_t)a->Do * a->Ho * a->Wo * rs};
+            if (!encode_act_map(&p.rmap, a->residual, p.Cout8, dim, rstr, box)) return GG_ERR_DRIVER;
+        }
+    }
+    const int bar_bytes = 1024 + (xform ? R_SS_BYTES : 0) + (p.tma_epi ? 2 * R_STAGE_BYTES : 0);   // + barriers, additive vectors, (scale, shift) table
     const int avail = H_SMEM_BUDGET - 1024 - bar_bytes;
-    int G = kwmax, SA = 3;
-    const int tap_bytes = 3 * (int)p.b_unit_bytes;
+    const int G = kwmax, tap_bytes = 3 * (int)p.b_unit_bytes;
+    GG_REQUIRE(G == 3, GG_ERR_UNSUPPORTED);                       // a B stage = one kw row of stacked tap tiles
+    // the transform adds a hop between "plane landed" and "plane usable": a fourth plane stage, one fewer weight stage
+    int SA = xform ? 4 : 3;
     int SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes);
-    if (SB < 3) { G = 1; SB = (avail - SA * (int)p.a_stage_bytes) / tap_bytes; }
+    if (SB < 3 && SA > 3) { SA = 3; SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes); }
     GG_REQUIRE(SB >= 2, GG_ERR_UNSUPPORTED);
     if (SB > R_MAX_SB) {
         SA = std::min(R_MAX_SA, (avail - R_MAX_SB * G * tap_bytes) / (int)p.a_stage_bytes);
         SB = R_MAX_SB;
     }
-    GG_REQUIRE(G == 1 || G == 3, GG_ERR_UNSUPPORTED);
     p.b_stage_bytes = (uint32_t)(G * tap_bytes);
     for (int s = 0; s < a->nsrc; ++s) p.seg[s].g = (G > 1 && p.seg[s].kw == G) ? G : 1;
     p.SA = SA; p.SB = SB;
@@ -585,6 +790,11 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
             for (int i = 0; i < pairs; ++i) for (int k = 0; k < 4; ++k) s[k] += (double)h[(size_t)i * 4 + k] / pairs;
             fprintf(stderr, "[conv_roll] MMA issuer clocks: total %.0f, waiting slot_free %.0f, a_full %.0f, b_full %.0f (avg of %d pairs)\n",
                     s[0], s[1], s[2], s[3], pairs);
+            std::vector<unsigned long long> hx((size_t)pairs * 2);
+            cudaMemcpy(hx.data(), buf + 2048, hx.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            double x[2] = {0, 0};
+            for (int i = 0; i < pairs; ++i) for (int k = 0; k < 2; ++k) x[k] += (double)hx[(size_t)i * 2 + k] / pairs;
+            fprintf(stderr, "[conv_roll] transform warp clocks: total %.0f, waiting for planes %.0f\n", x[0], x[1]);
         }
     } dbg_print{dbg, g.grid / 2, stream, dbg_buf};
     if (a->gn_partial != nullptr) {
@@ -596,10 +806,10 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
                                             (size_t)g.grid * 8 * 128 * sizeof(float), stream);
             if (e != cudaSuccess) return (int)e;
         }
-        return G == 3 ? launch_roll<3, true, 64>(p, g.grid, smem, stream) : launch_roll<1, true, 64>(p, g.grid, smem, stream);
+        return xform ? launch_roll<3, true, 64, true>(p, g.grid, smem, stream) : launch_roll<3, true, 64, false>(p, g.grid, smem, stream);
     }
-    if (g.BNs == 16) return G == 3 ? launch_roll<3, false, 16>(p, g.grid, smem, stream) : launch_roll<1, false, 16>(p, g.grid, smem, stream);
-    return G == 3 ? launch_roll<3, false, 64>(p, g.grid, smem, stream) : launch_roll<1, false, 64>(p, g.grid, smem, stream);
+    if (g.BNs == 16) return xform ? launch_roll<3, false, 16, true>(p, g.grid, smem, stream) : launch_roll<3, false, 16, false>(p, g.grid, smem, stream);
+    return xform ? launch_roll<3, false, 64, true>(p, g.grid, smem, stream) : launch_roll<3, false, 64, false>(p, g.grid, smem, stream);
 }
 
 }  // namespace gg

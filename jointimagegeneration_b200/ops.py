@@ -249,9 +249,13 @@ def pad_vec(v: Optional[torch.Tensor], n: int) -> Optional[torch.Tensor]:
 
 def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=None, emb=None, residual=None,
                    taps=None, offsets=None, out_spatial=None, y_strides=None, block_n=0, brick=None, d_shift=0,
-                   y_f32=False, algo=0, split_k=0, workspace=None) -> _C.ConvArgs:
+                   y_f32=False, algo=0, split_k=0, workspace=None, src_ss=None, ss_stride=0, xf_silu=True,
+                   xf_z=None) -> _C.ConvArgs:
     """srcs: list of (CL tensor [N, D, H, W, C], centre_only).  y: CL tensor [N, Do, Ho, Wo, >= Cout8]
-    (bf16 or fp32).  Returns the filled gg_conv_args (keeps nothing alive: the caller owns the tensors)."""
+    (bf16 or fp32).  src_ss (algo 4): per source, None or the device address of its first (scale, shift) pair in
+    gg_gn_finalize's output -- the kernel then normalises (+ SiLU) that source itself; ss_stride = floats per
+    sample; xf_z = (lo, hi) local depth planes holding real data (default 0..D).
+    Returns the filled gg_conv_args (keeps nothing alive: the caller owns the tensors)."""
     a = _C.ConvArgs()
     x0 = srcs[0][0]
     N, D, H, W = x0.shape[:4]
@@ -296,6 +300,11 @@ def make_conv_args(srcs, w_packed, cout, y, *, dims, ksize=3, stride=1, bias=Non
     a.algo = algo
     a.split_k = split_k
     a.workspace = _C.ptr(workspace)
+    if src_ss is not None:
+        for i, v in enumerate(src_ss):
+            a.src_ss[i] = v if (v is None or isinstance(v, int)) else _C.ptr(v)
+        a.ss_stride, a.xf_silu = int(ss_stride), int(bool(xf_silu))
+    a.xf_z_lo, a.xf_z_hi = xf_z if xf_z is not None else (0, D)
     a.block_n = block_n
     if brick is not None:
         for i in range(4):

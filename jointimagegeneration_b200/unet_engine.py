@@ -16,6 +16,7 @@ graph (the timestep enters through a device tensor).
 """
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -171,6 +172,8 @@ class UNetEngine:
         self.fused_upsample = fused_upsample
         self.use_halo_conv = True
         self.use_roll_conv = True
+        # GroupNorm + SiLU applied inside the depth-rolling conv (no separate pass); GG_FUSED_GN=0 is a tuning knob
+        self.fused_gn_apply = os.environ.get("GG_FUSED_GN", "1") != "0"
         self.use_split_k = True
         self.num_sms = torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count \
             if next(model.parameters()).is_cuda else 148
@@ -224,7 +227,8 @@ class UNetEngine:
         x.halo_valid = need_lo and need_hi
 
     # --------------------------------------------------------------------------- primitives
-    def _gn(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm, silu: bool) -> Act:
+    def _gn_scale_shift(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm) -> torch.Tensor:
+        """Per-(sample, channel) (scale, shift) of GroupNorm over cat([x1, x2], channel): fp32 [N, C1 + C2, 2]."""
         lib = self.lib
         N, S = x1.N, x1.S
         C1, C2 = x1.C, (x2.C if x2 is not None else 0)
@@ -254,12 +258,59 @@ class UNetEngine:
                                _C.ptr(self._f32(norm.bias)), _C.ptr(ss), N, norm.groups, S * R, float(norm.eps))
         plan.keep.append(fa)
         plan.add(lib.gg_gn_finalize, C.byref(fa))
-        y = self._new_act(ar, N, x1.sp, C1 + C2)
-        plan.add(lib.gg_gn_apply, x1.ip, C1, x2.ip if x2 is not None else 0, C2, _C.ptr(ss), y.ip, N, S, int(silu))
         for tbuf in temps:
             ar.release(tbuf)
+        return ss
+
+    def _gn(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm, silu: bool) -> Act:
+        """GroupNorm (+SiLU) over cat([x1, x2], channel) as a materialised tensor."""
+        ss = self._gn_scale_shift(plan, ar, x1, x2, norm)
+        C1, C2 = x1.C, (x2.C if x2 is not None else 0)
+        y = self._new_act(ar, x1.N, x1.sp, C1 + C2)
+        plan.add(self.lib.gg_gn_apply, x1.ip, C1, x2.ip if x2 is not None else 0, C2, _C.ptr(ss), y.ip, x1.N, x1.S, int(silu))
         ar.release(ss)
         return y
+
+    def _gn_conv(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm, silu: bool, packer, cout: int, *,
+                 dims: int, extra_srcs=(), **kw) -> Act:
+        """conv(silu?(GroupNorm(cat([x1, x2])))) [+ un-normalised centre-only sources].  `packer(splits)` returns the
+        packed-weight callable for the given channel split of the normalised input.  When the depth-rolling kernel
+        takes the conv, the normalisation is applied to the halo planes inside it (no gg_gn_apply pass, no
+        normalised tensor); otherwise the tensor is materialised first."""
+        C1, C2 = x1.C, (x2.C if x2 is not None else 0)
+        fuse = (self.fused_gn_apply and self._roll_ok(dims, 1, None, None, cout, x1.sp, None)
+                and (C1 + C2) * 8 <= 4096 and C1 % 64 == 0 and C2 % 64 == 0)
+        if not fuse:
+            a = self._gn(plan, ar, x1, x2, norm, silu)
+            out = self._conv(plan, ar, [(a, False)] + list(extra_srcs), packer([a.C]), cout, dims=dims, **kw)
+            self._free(ar, a)
+            return out
+        ss = self._gn_scale_shift(plan, ar, x1, x2, norm)
+        xs = [x1] + ([x2] if x2 is not None else [])
+        ptrs, off = [], 0
+        for x in xs:
+            ptrs.append(_C.ptr(ss) + 8 * off)
+            off += x.C
+        out = self._conv(plan, ar, [(x, False) for x in xs] + list(extra_srcs), packer([x.C for x in xs]), cout, dims=dims,
+                         src_ss=ptrs + [None] * len(extra_srcs), ss_stride=2 * (C1 + C2), xf_silu=silu, **kw)
+        plan.keep.append(ss)
+        ar.release(ss)          # stream order: the conv that reads it is enqueued before any later writer
+        return out
+
+    def _roll_ok(self, dims, stride, taps, offsets, cout, out_spatial, y_strides) -> bool:
+        """The depth-rolling kernel (conv_roll.cu): 3x3x3 stride-1 filters with a narrow output on grids that fill a
+        2 x 2 group of 16 x 8 bricks."""
+        return (self.use_halo_conv and self.use_roll_conv and dims == 3 and stride == 1
+                and (taps is None or tuple(taps) == (3, 3, 3)) and (offsets is None or tuple(offsets) == (-1, -1, -1))
+                and (cout + 15) // 16 * 16 in (16, 64) and out_spatial[1] >= 32 and out_spatial[2] >= 16 and y_strides is None)
+
+    def _xf_z(self, D):
+        """Local depth planes that hold real data for a fused-normalisation conv: the interior, plus the halo planes
+        that carry a neighbouring slab's data (planes beyond the volume must stay zero: the reference pads the
+        NORMALISED tensor)."""
+        if self.slab is None:
+            return (0, D)
+        return (-1 if self.slab.rank > 0 else 0, D + 1 if self.slab.rank < self.slab.world - 1 else D)
 
     def _free(self, ar, a: Optional[Act]):
         if a is None:
@@ -277,7 +328,8 @@ class UNetEngine:
     def _conv(self, plan: Plan, ar: _Arena, srcs: List[Tuple[Act, bool]], w_packed, cout: int, *, dims: int,
               ksize: int = 3, stride: int = 1, bias=None, emb=None, emb_stride=0, residual: Optional[Act] = None,
               f32_out: bool = False, taps=None, offsets=None, y_ptr: Optional[int] = None, y_strides=None,
-              out_spatial=None, out: Optional[Act] = None, stats: bool = False, stats_part=(0, 1)) -> Act:
+              out_spatial=None, out: Optional[Act] = None, stats: bool = False, stats_part=(0, 1),
+              src_ss=None, ss_stride=0, xf_silu=True) -> Act:
         x0 = srcs[0][0]
         N, (D, H, W) = x0.N, x0.sp
         cout8 = (cout + 7) // 8 * 8
@@ -297,9 +349,9 @@ class UNetEngine:
         # the halo kernel keeps GroupNorm column sums in registers when one 64-wide tile covers all output channels
         halo_stats = halo and stats and self.halo_gn_stats and cout8 == 64 and not f32_out
         algo = 1 if halo and (halo_stats or not (stats and self.fused_gn_stats)) else 0
-        if (algo == 1 and self.use_roll_conv and dims == 3 and tuple(taps) == (3, 3, 3) and tuple(offsets) == (-1, -1, -1)
-                and (cout + 15) // 16 * 16 in (16, 64) and out_spatial[1] >= 32 and out_spatial[2] >= 16 and y_strides is None):
+        if algo == 1 and self._roll_ok(dims, stride, taps, offsets, cout, out_spatial, y_strides):
             algo = 4        # narrow outputs: depth-rolling kernel (three depth taps stacked along N)
+        assert src_ss is None or (algo == 4 and callable(w_packed)), "fused input GroupNorm needs the depth-rolling kernel"
         if callable(w_packed):          # packed-weight K order depends on the kernel
             w_packed = w_packed(algo >= 1)
         else:
@@ -322,7 +374,8 @@ class UNetEngine:
         a = ops.make_conv_args([(s.t, c) for s, c in srcs], w_packed, cout, y_base, dims=dims, ksize=ksize, stride=stride,
                                bias=bias, emb=None, residual=residual.ip if residual is not None else None, taps=taps,
                                offsets=offsets, out_spatial=kernel_out_sp, y_strides=y_strides, d_shift=d_shift,
-                               y_f32=f32_out, algo=algo)
+                               y_f32=f32_out, algo=algo, src_ss=src_ss, ss_stride=ss_stride, xf_silu=xf_silu,
+                               xf_z=self._xf_z(D) if src_ss is not None else None)
         if emb is not None:
             a.emb = emb
             a.emb_stride = emb_stride
@@ -373,19 +426,15 @@ class UNetEngine:
     def _resblock(self, plan, ar, rb: M.ResBlock, x1: Act, x2: Optional[Act], emb_ptr: int, emb_stride: int) -> Act:
         dims = rb.dims
         cout = rb.out_channels
-        a1 = self._gn(plan, ar, x1, x2, rb.in_layers[0], True)
         c1 = rb.in_layers[2]
-        h1 = self._conv(plan, ar, [(a1, False)], self._packer(c1, [a1.C]), cout, dims=dims, emb=emb_ptr, emb_stride=emb_stride,
-                        stats=True)
-        self._free(ar, a1)
-        a2 = self._gn(plan, ar, h1, None, rb.out_layers[0], True)
-        self._free(ar, h1)
+        h1 = self._gn_conv(plan, ar, x1, x2, rb.in_layers[0], True, lambda splits: self._packer(c1, splits), cout, dims=dims,
+                           emb=emb_ptr, emb_stride=emb_stride, stats=True)
         c2 = rb.out_layers[3]
         if isinstance(rb.skip_connection, torch.nn.Identity):
             assert x2 is None and x1.C == cout
             b2 = self._vec8((id(c2.bias), "b"), lambda: c2.bias, cout)
-            out = self._conv(plan, ar, [(a2, False)], self._packer(c2, [a2.C]), cout, dims=dims, bias=_C.ptr(b2), residual=x1,
-                             stats=True)
+            out = self._gn_conv(plan, ar, h1, None, rb.out_layers[0], True, lambda splits: self._packer(c2, splits), cout,
+                                dims=dims, bias=_C.ptr(b2), residual=x1, stats=True)
         else:
             sk = rb.skip_connection
             if sk.kernel_size != 1:
@@ -397,10 +446,15 @@ class UNetEngine:
                 extras.append(skw[:, c0:c0 + x.C])
                 c0 += x.C
             key = (id(c2.weight), id(sk.weight), tuple(x.C for x in xs))
-            wp = lambda cm: self._cached(key + (cm,), lambda: ops.pack_conv_weight(c2.weight, [a2.C], extra=extras, chunk_major=cm))  # noqa: E731
+
+            def packer(splits):
+                return lambda cm: self._cached(key + (tuple(splits), cm),
+                                               lambda: ops.pack_conv_weight(c2.weight, list(splits), extra=extras, chunk_major=cm))
+
             b2 = self._vec8((id(c2.bias), id(sk.bias), "b"), lambda: c2.bias.detach() + sk.bias.detach(), cout)
-            out = self._conv(plan, ar, [(a2, False)] + [(x, True) for x in xs], wp, cout, dims=dims, bias=_C.ptr(b2), stats=True)
-        self._free(ar, a2)
+            out = self._gn_conv(plan, ar, h1, None, rb.out_layers[0], True, packer, cout, dims=dims,
+                                extra_srcs=[(x, True) for x in xs], bias=_C.ptr(b2), stats=True)
+        self._free(ar, h1)
         return out
 
     def _heads(self, ch):
@@ -653,13 +707,11 @@ class UNetEngine:
             skip = hs.pop()
             h = run_block(block, h, skip, hs)
         # ---- head: GN -> SiLU -> conv (-> softmax fused downstream)   unet.py:715-721
-        a = self._gn(plan, ar, h, None, m.out[0], True)
-        self._free(ar, h)
         oc = m.out[2]
         b = self._vec8((id(oc.bias), "b"), lambda: oc.bias, oc.out_channels)
-        head = self._conv(plan, ar, [(a, False)], self._packer(oc, [a.C]), oc.out_channels, dims=oc.dims, bias=_C.ptr(b),
-                          f32_out=f32_head)
-        ar.release(a.t)
+        head = self._gn_conv(plan, ar, h, None, m.out[0], True, lambda splits: self._packer(oc, splits), oc.out_channels,
+                             dims=oc.dims, bias=_C.ptr(b), f32_out=f32_head)
+        self._free(ar, h)
         plan.outputs["head"] = head.interior
         plan.keep.extend([emb_all, emb, e1, temb])
         plan.keep.append(ar.stores)      # kernels hold raw pointers into these: they must outlive the plan

@@ -348,6 +348,49 @@ def test_conv_tcgen05(ops, name):
     assert err <= tol, f"{name}: rel err {err}"
 
 
+@pytest.mark.parametrize("N,sp,C1,C2,Cskip,Cout,silu", [(2, (5, 32, 32), 64, 0, 0, 64, True), (1, (3, 40, 24), 128, 64, 192, 64, True),
+                                                       (2, (4, 32, 16), 64, 0, 0, 12, True), (1, (2, 32, 16), 64, 64, 0, 64, False)])
+def test_conv_roll_fused_groupnorm(ops, N, sp, C1, C2, Cskip, Cout, silu):
+    """algo 4 with src_ss: GroupNorm (+SiLU) applied to the raw input planes inside the conv kernel must give exactly
+    what gg_gn_apply followed by the same conv gives (same bf16 operands into the same MMA sequence) -- including
+    the zero padding of the NORMALISED tensor at the h / w / d borders, concatenated norms and an un-normalised
+    1x1x1 skip source."""
+    no_tf32()
+    rs = np.random.RandomState(5)
+    mk = lambda c: (torch.from_numpy(rs.standard_normal((N,) + sp + (c,)).astype(np.float32) * 1.7 + 0.3)).cuda().to(torch.bfloat16)
+    x1, x2 = mk(C1), (mk(C2) if C2 else None)
+    xs = mk(Cskip) if Cskip else None
+    C = C1 + C2
+    gamma = torch.from_numpy(rs.standard_normal(C).astype(np.float32)).cuda()
+    beta = torch.from_numpy(rs.standard_normal(C).astype(np.float32)).cuda()
+    S = sp[0] * sp[1] * sp[2]
+    ss = ops.gn_finalize(ops.gn_partial(x1), ops.gn_partial(x2) if C2 else None, gamma, beta, S, 1e-5)
+    a_norm = ops.gn_apply(x1, x2, ss, silu)
+    w = torch.from_numpy((rs.standard_normal((Cout, C, 3, 3, 3)) / math.sqrt(C * 27)).astype(np.float32)).cuda()
+    extra = []
+    if Cskip:
+        extra = [torch.from_numpy((rs.standard_normal((Cout, Cskip)) / math.sqrt(Cskip)).astype(np.float32)).cuda()]
+    b_pad = ops.pad_vec(torch.from_numpy(rs.standard_normal(Cout).astype(np.float32)).cuda(), Cout)
+    Cout8 = (Cout + 7) // 8 * 8
+
+    def run(srcs, splits, src_ss):
+        wp = ops.pack_conv_weight(w, splits, extra=extra, chunk_major=True)
+        y = torch.full((N,) + sp + (Cout8,), float("nan"), dtype=torch.bfloat16, device="cuda")
+        a = ops.make_conv_args(srcs, wp, Cout, y, dims=3, ksize=3, stride=1, bias=b_pad, algo=4, src_ss=src_ss,
+                               ss_stride=2 * C, xf_silu=silu)
+        ops.conv_fwd(a)
+        torch.cuda.synchronize()
+        return y
+
+    skip = [(xs, True)] if Cskip else []
+    want = run([(a_norm, False)] + skip, [C], None)
+    fused_srcs = [(x1, False)] + ([(x2, False)] if C2 else []) + skip
+    ss_ptrs = [ss.data_ptr()] + ([ss.data_ptr() + 8 * C1] if C2 else []) + ([None] if Cskip else [])
+    got = run(fused_srcs, [C1] + ([C2] if C2 else []), ss_ptrs)
+    assert not torch.isnan(got.float()).any()
+    assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
+
+
 # -------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,H,T,d", [(2, 4, 64, 32), (1, 8, 2048, 32), (2, 10, 256, 32), (3, 2, 16, 32), (1, 5, 100, 32),
                                      (1, 2, 130, 64)])

@@ -303,6 +303,29 @@ def test_slab_layout_single_rank_equals_plain_plan():
         m.unet.enable_slab(None)
 
 
+def test_conv_kernel_choices_agree_on_the_full_network():
+    """The reference-shaped CCDM network (64 base channels) through the engine's kernel choices: the depth-rolling
+    conv with GroupNorm + SiLU fused on its input planes must equal the same kernel fed by a separate gg_gn_apply
+    pass bit for bit, and both must agree with the halo-brick / general kernels (other summation order only)."""
+    from oracle import configs, weights
+    C, spatial = 12, (16, 32, 32)
+    m, _ = _ccdm(configs.CCDM_PARAMS_YML, 10, C, spatial, 9)
+    x = weights.uniform_one_hot(4, 2, C, spatial).cuda()
+    cond = torch.zeros(2, 1, *spatial).cuda()
+    t = torch.tensor([3.0, 9.0]).cuda()
+    eng = m.unet.engine
+    outs = {}
+    for name, roll, fused in (("fused", True, True), ("unfused", True, False), ("halo", False, False)):
+        eng.use_roll_conv, eng.fused_gn_apply = roll, fused
+        m.unet.invalidate()
+        outs[name] = m.unet(x, cond, None, t)["diffusion_out"].float().clone()
+    eng.use_roll_conv, eng.fused_gn_apply = True, True
+    m.unet.invalidate()
+    assert torch.isfinite(outs["fused"]).all()
+    assert torch.equal(outs["fused"], outs["unfused"]), float((outs["fused"] - outs["unfused"]).abs().max())
+    assert rel(outs["fused"].cpu().numpy(), outs["halo"].cpu().numpy()) <= 2e-2
+
+
 def test_ccdm_text_cross_attention_3d_vs_oracle():
     """Text-conditioned CCDM (BASELINE config 2's 'text-conditioned'): the reference declares
     use_spatial_transformer but cannot construct it; the oracle applies the LDM

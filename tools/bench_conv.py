@@ -35,8 +35,15 @@ def main():
                     continue
                 y = torch.empty((N, D, H, W, Cout8), device=dev, dtype=torch.bfloat16)
                 bp = ops.pad_vec(b, Cout)
+                ss = None
+                if "xf" in variant:       # fused input GroupNorm + SiLU (algo 4 only)
+                    if algo != 4:
+                        continue
+                    gam, bet = torch.ones(Cin, device=dev), torch.zeros(Cin, device=dev)
+                    ss = ops.gn_finalize(ops.gn_partial(x), None, gam, bet, D * H * W, 1e-5)
                 a = ops.make_conv_args([(x, False)], wp, Cout, y, dims=3, ksize=3, stride=1, bias=bp,
-                                       residual=res if "res" in variant else None, algo=algo)
+                                       residual=res if "res" in variant else None, algo=algo,
+                                       src_ss=[ss] if ss is not None else None, ss_stride=2 * Cin)
                 part = None
                 if "stats" in variant:
                     per = int(_C.lib().gg_conv_stats_chunks(C.byref(a)))
