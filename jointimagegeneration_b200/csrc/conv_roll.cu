@@ -763,6 +763,10 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
         SA = std::min(R_MAX_SA, (avail - R_MAX_SB * G * tap_bytes) / (int)p.a_stage_bytes);
         SB = R_MAX_SB;
     }
+    if (const char* e = getenv("GG_ROLL_SA")) {       // tuning knob: plane stages (weight stages take the rest)
+        const int sa = atoi(e), sb = (avail - sa * (int)p.a_stage_bytes) / (G * tap_bytes);
+        if (sa >= 2 && sa <= R_MAX_SA && sb >= 2) { SA = sa; SB = std::min(sb, R_MAX_SB); }
+    }
     p.b_stage_bytes = (uint32_t)(G * tap_bytes);
     for (int s = 0; s < a->nsrc; ++s) p.seg[s].g = (G > 1 && p.seg[s].kw == G) ? G : 1;
     p.SA = SA; p.SB = SB;

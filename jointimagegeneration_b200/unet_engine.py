@@ -172,6 +172,7 @@ class UNetEngine:
         self.fused_upsample = fused_upsample
         self.use_halo_conv = True
         self.use_roll_conv = True
+        self.separate_skip = os.environ.get("GG_SEPARATE_SKIP", "0") != "0"     # see _resblock (measured: no gain, off)
         # GroupNorm + SiLU applied inside the depth-rolling conv (no separate pass); GG_FUSED_GN=0 is a tuning knob
         self.fused_gn_apply = os.environ.get("GG_FUSED_GN", "1") != "0"
         self.use_split_k = True
@@ -452,8 +453,18 @@ class UNetEngine:
                                                lambda: ops.pack_conv_weight(c2.weight, list(splits), extra=extras, chunk_major=cm))
 
             b2 = self._vec8((id(c2.bias), id(sk.bias), "b"), lambda: c2.bias.detach() + sk.bias.detach(), cout)
-            out = self._gn_conv(plan, ar, h1, None, rb.out_layers[0], True, packer, cout, dims=dims,
-                                extra_srcs=[(x, True) for x in xs], bias=_C.ptr(b2), stats=True)
+            if self.separate_skip and self._roll_ok(dims, 1, None, None, cout, h1.sp, None):
+                # experiment: in the depth-rolling kernel extra 1x1x1 sources take plane / weight ring slots every
+                # step; a stand-alone (HBM-bound) 1x1x1 conv whose result enters conv2 as the residual measured
+                # the same step time on B200 (46.4 vs 46.1 ms), so the fused form stays the default
+                wsk = self._pack(sk, [x.C for x in xs])
+                skip = self._conv(plan, ar, [(x, False) for x in xs], wsk, cout, dims=dims, ksize=1)
+                out = self._gn_conv(plan, ar, h1, None, rb.out_layers[0], True, lambda splits: self._packer(c2, splits), cout,
+                                    dims=dims, bias=_C.ptr(b2), residual=skip, stats=True)
+                self._free(ar, skip)
+            else:
+                out = self._gn_conv(plan, ar, h1, None, rb.out_layers[0], True, packer, cout, dims=dims,
+                                    extra_srcs=[(x, True) for x in xs], bias=_C.ptr(b2), stats=True)
         self._free(ar, h1)
         return out
 
