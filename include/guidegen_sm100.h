@@ -263,7 +263,7 @@ typedef struct {
      * 4 = "depth-rolling" kernel for 3x3x3 stride-1 filters with 3 * Cout <= 256 (conv_roll.cu): walks input
      * depth planes and stacks the three depth taps along N, so each plane is loaded once and each A slice feeds
      * 3 Cout accumulator columns (same packed-weight K order as algo 1; always CTA pairs).
-     * With algo 1..4 and a 64-channel output, gn_partial rows are per (CTA, epilogue warp) register sums. */
+     * With algo 1..4 (bf16 outputs) gn_partial holds one row per (CTA, epilogue warp): per-tile shuffle-reduced column sums. */
     int32_t algo;
     /* Split-K (algo 0): layers whose output has fewer tiles than the GPU has SMs but a long reduction (the
      * low-resolution 3^d convs) are cut into split_k K ranges; each (tile, range) work item writes raw fp32
@@ -287,7 +287,8 @@ typedef struct {
 int32_t gg_conv_pick_block_n(int32_t Cout);
 /* output tiles (128 positions x N tile) algo 0 will process for `a`: what split-K decisions are based on */
 int32_t gg_conv_num_tiles(const gg_conv_args* a);
-/* rows of gn_partial one launch of `a` fills per sample (4 per M tile), 0 if fused statistics are unsupported */
+/* rows of gn_partial one launch of `a` fills per sample (algo 0: 4 per M tile; algo 1..4: one per (CTA, epilogue
+ * warp), accumulated in a fixed order into rows the launch zeroes first), 0 if fused statistics are unsupported */
 int32_t gg_conv_stats_chunks(const gg_conv_args* a);
 /* K extent (columns) of the packed weight matrix for the sources / taps in `a` */
 int64_t gg_conv_packed_k(const gg_conv_args* a);

@@ -259,12 +259,6 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         const int etid = threadIdx.x - 64;             // 0..127 among the epilogue warps
         uint32_t acc = 0, acc_phase = 0;
         int cur_n = -1, cur_nt = -1;
-        float s1[STATS ? 64 : 1], s2[STATS ? 64 : 1];
-        int stat_n = -1;
-        if (STATS) {
-#pragma unroll
-            for (int i = 0; i < (STATS ? 64 : 1); ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-        }
         const uint32_t tempty_r0 = PAIR ? leader_addr(&tempty[0]) : 0u, tempty_r1 = PAIR ? leader_addr(&tempty[1]) : 0u;
         for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
             const int nt = tile % p.n_tiles_n;
@@ -298,13 +292,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * H_ACC_COLS + ((uint32_t)(q * 32) << 16);
             if constexpr (STATS) {
-                if (n != stat_n) {         // tiles are ordered by sample: flush the finished sample's sums
-                    if (stat_n >= 0)
-                        flush_stats64(s1, s2, p.gn_partial + (((long long)stat_n * p.gn_nchunks_total + p.gn_chunk_base +
-                                                                (long long)blockIdx.x * 4 + q) * 64) * 2, lane);
-                    stat_n = n;
-                }
-                epilogue_row_stats64(t_addr, bvec, res_row, reinterpret_cast<__nv_bfloat16*>(y_row), valid, s1, s2);
+                float* stat_row = p.gn_partial + (((long long)n * p.gn_nchunks_total + p.gn_chunk_base + (long long)blockIdx.x * 4 + q) *
+                                                      p.Cout8 + nt * BN) * 2;
+                epilogue_row_stats(t_addr, BN, ncols, bvec, res_row, reinterpret_cast<__nv_bfloat16*>(y_row), valid, stat_row, lane);
             } else {
                 epilogue_row(t_addr, BN, ncols, bvec, res_row, y_row, p.y_is_f32, valid);
             }
@@ -316,11 +306,6 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             }
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;
-        }
-        if constexpr (STATS) {
-            if (stat_n >= 0)
-                flush_stats64(s1, s2, p.gn_partial + (((long long)stat_n * p.gn_nchunks_total + p.gn_chunk_base +
-                                                        (long long)blockIdx.x * 4 + q) * 64) * 2, lane);
         }
     }
 
@@ -450,14 +435,15 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     p.y = a->y; p.y_sn = a->y_sn; p.y_sd = a->y_sd; p.y_sh = a->y_sh; p.y_sw = a->y_sw; p.y_is_f32 = a->y_is_f32;
 
     if (a->gn_partial != nullptr) {
-        // fused GroupNorm statistics: one partial row per (CTA, epilogue warp) and sample; CTAs that never touch a
-        // sample leave zeros, so the rows are cleared first (a memset node under graph capture)
-        GG_REQUIRE(BN == 64 && p.Cout8 == 64 && p.n_tiles_n == 1 && !a->y_is_f32, GG_ERR_UNSUPPORTED);
+        // fused GroupNorm statistics: one partial row per (CTA, epilogue warp) and sample, accumulated tile by tile by its
+        // owner lanes (plain read-modify-write: deterministic)
+        // after a per-tile shuffle reduction, so the rows are cleared first (a memset node under graph capture)
+        GG_REQUIRE(!a->y_is_f32, GG_ERR_UNSUPPORTED);
         GG_REQUIRE(aligned(a->gn_partial, 16) && a->gn_chunk_base >= 0 && a->gn_chunk_base + grid * 4 <= a->gn_nchunks_total, GG_ERR_BAD_ARG);
         p.gn_partial = a->gn_partial; p.gn_chunk_base = a->gn_chunk_base; p.gn_nchunks_total = a->gn_nchunks_total;
         for (int n = 0; n < a->N; ++n) {
-            cudaError_t e = cudaMemsetAsync(a->gn_partial + ((size_t)n * a->gn_nchunks_total + a->gn_chunk_base) * 128, 0,
-                                            (size_t)grid * 4 * 128 * sizeof(float), stream);
+            cudaError_t e = cudaMemsetAsync(a->gn_partial + ((size_t)n * a->gn_nchunks_total + a->gn_chunk_base) * p.Cout8 * 2, 0,
+                                            (size_t)grid * 4 * p.Cout8 * 2 * sizeof(float), stream);
             if (e != cudaSuccess) return (int)e;
         }
         return pair ? launch_halo_g<true, true>(G, p, grid, smem, stream) : launch_halo_g<true, false>(G, p, grid, smem, stream);

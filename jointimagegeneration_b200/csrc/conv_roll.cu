@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
         int cur_n = -1;
         float4 st = make_float4(0.f, 0.f, 0.f, 0.f);       // STATS: (sum, sum sq) of columns 2 lane, 2 lane + 1 over this warp's rows
         int stat_n = -1;
-        auto flush = [&](int n) {
+        auto flush = [&](int n) {        // one partial row per (CTA, epilogue warp): written once per sample, fixed order
             *reinterpret_cast<float4*>(p.gn_partial + (((long long)n * p.gn_nchunks_total + p.gn_chunk_base + (long long)blockIdx.x * 8 + wi * 4 + q) * 64) * 2 +
                                        4 * lane) = st;
             st = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -485,9 +485,8 @@ extern "C" int32_t gg_conv_num_tiles(const gg_conv_args* a) {
 extern "C" int32_t gg_conv_stats_chunks(const gg_conv_args* a) {
     if (!a || a->Do <= 0 || a->Ho <= 0 || a->Wo <= 0) return 0;
     if (a->algo >= 1 && a->algo <= 3) {
-        // halo kernel: register-resident column sums, one row per (CTA, epilogue warp); 64-channel outputs only
-        const int BNh = a->block_n > 0 ? a->block_n : gg_conv_pick_block_n(a->Cout);
-        if (BNh != 64 || (a->Cout + 7) / 8 * 8 != 64 || a->y_is_f32) return 0;
+        // halo kernel: per-tile shuffle-reduced column sums, one row per (CTA, epilogue warp); bf16 outputs
+        if (a->y_is_f32) return 0;
         return conv_halo_grid(a, nullptr) * 4;
     }
     if (a->algo == 4) {

@@ -10,59 +10,63 @@ constexpr int H_MAX_SEGS = 4;
 constexpr int H_THREADS = 224;
 constexpr int H_SMEM_BUDGET = 227 * 1024;
 
-// Epilogue of one row for the BN = 64 statistics variant: as epilogue_row, plus per-thread running sums of the
-// stored (bf16-rounded) values per column, kept in registers across all tiles of a sample.
-__device__ __forceinline__ void epilogue_row_stats64(uint32_t t_addr, const float* __restrict__ bvec,
-                                                     const __nv_bfloat16* __restrict__ res_row, __nv_bfloat16* y_row, bool valid,
-                                                     float (&s1)[64], float (&s2)[64]) {
-    uint32_t r[64];
-    tmem_ld16_nowait(t_addr, r);
-    tmem_ld16_nowait(t_addr + 16, r + 16);
-    tmem_ld16_nowait(t_addr + 32, r + 32);
-    tmem_ld16_nowait(t_addr + 48, r + 48);
-    uint4 rr[8];
+// Epilogue of one row with fused GroupNorm statistics (bf16 outputs, any N tile): as epilogue_row, 32 columns per
+// step; after each step the warp's 32 rows x 32 columns of STORED (bf16-rounded) values are summed per column by a
+// butterfly reduce-scatter (31 shuffles per quantity) and lane l adds (sum, sum of squares) of column c0 + l to the
+// partial row `stat_row` ([Cout8][2] floats owned by this (CTA, warp), zeroed by the launch).  Every lane must call.
+__device__ __forceinline__ void epilogue_row_stats(uint32_t t_addr, int BN, int ncols, const float* __restrict__ bvec,
+                                                   const __nv_bfloat16* __restrict__ res_row, __nv_bfloat16* y_row, bool valid,
+                                                   float* __restrict__ stat_row, int lane) {
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld16_nowait(t_addr + c0, r);
+        if (c0 + 16 < BN) tmem_ld16_nowait(t_addr + c0 + 16, r + 16);
+        uint4 rr[4];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) rr[g] = (res_row != nullptr && valid) ? ldg_nc_u4(res_row + 8 * g) : make_uint4(0, 0, 0, 0);
-    tmem_ld_wait();
-    if (!valid) return;
+        for (int g = 0; g < 4; ++g)
+            rr[g] = (res_row != nullptr && valid && c0 + 8 * g < ncols) ? ldg_nc_u4(res_row + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+        tmem_ld_wait();
+        float a[32];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bvec + 8 * g), b1 = *reinterpret_cast<const float4*>(bvec + 8 * g + 4);
-        float v[8];
-        v[0] = __uint_as_float(r[8 * g + 0]) + b0.x + bf16_lo(rr[g].x); v[1] = __uint_as_float(r[8 * g + 1]) + b0.y + bf16_hi(rr[g].x);
-        v[2] = __uint_as_float(r[8 * g + 2]) + b0.z + bf16_lo(rr[g].y); v[3] = __uint_as_float(r[8 * g + 3]) + b0.w + bf16_hi(rr[g].y);
-        v[4] = __uint_as_float(r[8 * g + 4]) + b1.x + bf16_lo(rr[g].z); v[5] = __uint_as_float(r[8 * g + 5]) + b1.y + bf16_hi(rr[g].z);
-        v[6] = __uint_as_float(r[8 * g + 6]) + b1.z + bf16_lo(rr[g].w); v[7] = __uint_as_float(r[8 * g + 7]) + b1.w + bf16_hi(rr[g].w);
-        const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        *reinterpret_cast<uint4*>(y_row + 8 * g) = pk;
-        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+        for (int g = 0; g < 4; ++g) {
+            const int c = c0 + 8 * g;
+            const bool on = valid && c < ncols;
+            const float4 b0 = on ? *reinterpret_cast<const float4*>(bvec + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b1 = on ? *reinterpret_cast<const float4*>(bvec + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float v[8];
+            v[0] = __uint_as_float(r[8 * g + 0]) + b0.x + bf16_lo(rr[g].x); v[1] = __uint_as_float(r[8 * g + 1]) + b0.y + bf16_hi(rr[g].x);
+            v[2] = __uint_as_float(r[8 * g + 2]) + b0.z + bf16_lo(rr[g].y); v[3] = __uint_as_float(r[8 * g + 3]) + b0.w + bf16_hi(rr[g].y);
+            v[4] = __uint_as_float(r[8 * g + 4]) + b1.x + bf16_lo(rr[g].z); v[5] = __uint_as_float(r[8 * g + 5]) + b1.y + bf16_hi(rr[g].z);
+            v[6] = __uint_as_float(r[8 * g + 6]) + b1.z + bf16_lo(rr[g].w); v[7] = __uint_as_float(r[8 * g + 7]) + b1.w + bf16_hi(rr[g].w);
+            const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            if (on) *reinterpret_cast<uint4*>(y_row + c) = pk;
+            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
-            s1[8 * g + 2 * e] += lo; s2[8 * g + 2 * e] = fmaf(lo, lo, s2[8 * g + 2 * e]);
-            s1[8 * g + 2 * e + 1] += hi; s2[8 * g + 2 * e + 1] = fmaf(hi, hi, s2[8 * g + 2 * e + 1]);
+            for (int e = 0; e < 4; ++e) {
+                a[8 * g + 2 * e] = on ? bf16_lo(w[e]) : 0.f;
+                a[8 * g + 2 * e + 1] = on ? bf16_hi(w[e]) : 0.f;
+            }
+        }
+        float b[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) b[i] = a[i] * a[i];
+#pragma unroll
+        for (int half = 16; half >= 1; half >>= 1) {      // lane mask 16, 8, 4, 2, 1: lane l ends with column l
+            const bool up = (lane & half) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float ka = up ? a[i + half] : a[i], xa = up ? a[i] : a[i + half];
+                const float kb = up ? b[i + half] : b[i], xb = up ? b[i] : b[i + half];
+                a[i] = ka + __shfl_xor_sync(0xffffffffu, xa, half);
+                b[i] = kb + __shfl_xor_sync(0xffffffffu, xb, half);
+            }
+        }
+        if (c0 + lane < ncols) {        // this lane is the only writer of its two floats: plain RMW keeps the sum order fixed
+            float2* dst = reinterpret_cast<float2*>(stat_row) + c0 + lane;
+            const float2 o = *dst;
+            *dst = make_float2(o.x + a[0], o.y + b[0]);
         }
     }
-}
-
-// sum the 64 per-thread column sums over the 32 lanes of a warp (butterfly reduce-scatter: 62 shuffles per
-// quantity, once per (CTA, sample)); lane l ends with columns 2l, 2l+1 and writes them to the partial row
-__device__ __forceinline__ void flush_stats64(float (&s1)[64], float (&s2)[64], float* __restrict__ dst, int lane) {
-#pragma unroll
-    for (int half = 32; half >= 2; half >>= 1) {
-        const int m = half >> 1;          // lane mask 16, 8, 4, 2, 1
-        const bool up = (lane & m) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const float k1 = up ? s1[i + half] : s1[i], x1 = up ? s1[i] : s1[i + half];
-            const float k2 = up ? s2[i + half] : s2[i], x2 = up ? s2[i] : s2[i + half];
-            s1[i] = k1 + __shfl_xor_sync(0xffffffffu, x1, m);
-            s2[i] = k2 + __shfl_xor_sync(0xffffffffu, x2, m);
-        }
-    }
-    *reinterpret_cast<float4*>(dst + 4 * lane) = make_float4(s1[0], s2[0], s1[1], s2[1]);
-#pragma unroll
-    for (int i = 0; i < 64; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
 }
 
 __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {

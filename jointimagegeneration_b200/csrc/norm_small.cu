@@ -73,9 +73,19 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const gg_gn_finalize_a
         if (c < a.C1) { part = a.partial1; Cs = a.C1; nch = a.nchunks1; cl = c; }
         else { part = a.partial2; Cs = a.C2; nch = a.nchunks2; cl = c - a.C1; }
         const float* p = part + ((int64_t)n * nch) * 2 * Cs + 2 * cl;
-        for (int k = threadIdx.x; k < nch; k += 128) {
-            s += (double)p[(int64_t)k * 2 * Cs];
-            ss += (double)p[(int64_t)k * 2 * Cs + 1];
+        // rows are a few hundred to a few thousand (one per CTA x warp of the producing conv): issue the loads of
+        // eight rows before the dependent fp64 adds (the summation order per thread is unchanged)
+        int k = threadIdx.x;
+        for (; k + 7 * 128 < nch; k += 8 * 128) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float2*>(p + (int64_t)(k + u * 128) * 2 * Cs));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s += (double)v[u].x; ss += (double)v[u].y; }
+        }
+        for (; k < nch; k += 128) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(p + (int64_t)k * 2 * Cs));
+            s += (double)v.x; ss += (double)v.y;
         }
     }
     __shared__ double sh[2][4];

@@ -178,7 +178,7 @@ class UNetEngine:
         self.use_split_k = True
         self.num_sms = torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count \
             if next(model.parameters()).is_cuda else 148
-        self.halo_gn_stats = True       # ... except in the halo kernel's 64-channel layers, where they are register sums
+        self.halo_gn_stats = os.environ.get("GG_HALO_STATS", "1") != "0"    # ... except in the halo / roll kernels (shuffle-reduced per tile)
         self.fused_gn_stats = False     # GroupNorm statistics from the conv epilogue: correct, but the extra epilogue
                                         # work costs more than the separate (cached) statistics pass saves on B200
         self.slab = None            # sharding.SlabComm: depth-slab decomposition of ONE volume over ranks
@@ -347,8 +347,8 @@ class UNetEngine:
         if out is None:
             out = self._new_act(ar, N, out_spatial, cout8, torch.float32 if f32_out else torch.bfloat16)
         halo = self._halo_ok(taps, stride, out_spatial) and callable(w_packed)
-        # the halo kernel keeps GroupNorm column sums in registers when one 64-wide tile covers all output channels
-        halo_stats = halo and stats and self.halo_gn_stats and cout8 == 64 and not f32_out
+        # the halo kernels reduce GroupNorm column sums in their epilogue (bf16 outputs)
+        halo_stats = halo and stats and self.halo_gn_stats and not f32_out
         algo = 1 if halo and (halo_stats or not (stats and self.fused_gn_stats)) else 0
         if algo == 1 and self._roll_ok(dims, stride, taps, offsets, cout, out_spatial, y_strides):
             algo = 4        # narrow outputs: depth-rolling kernel (three depth taps stacked along N)

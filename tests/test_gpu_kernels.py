@@ -328,6 +328,9 @@ CONV_CASES = {
     "halo_pair_head_f32": dict(N=1, sp=(4, 16, 16), Cs=[64], Cout=12, dims=3, f32_out=True, algo=3),
     "halo_pair_many_tiles": dict(N=2, sp=(16, 64, 64), Cs=[64], Cout=64, dims=3, residual=True, algo=3, stats=True),
     "halo_pair_cout_192": dict(N=1, sp=(2, 32, 16), Cs=[128], Cout=192, dims=3, algo=3),
+    "halo_pair_stats_128": dict(N=2, sp=(4, 32, 32), Cs=[128], Cout=128, dims=3, residual=True, emb=True, algo=3, stats=True),
+    "halo_stats_2d_320": dict(N=2, sp=(32, 24), Cs=[160], Cout=320, dims=2, emb=True, algo=1, stats=True),
+    "halo_single_stats_72": dict(N=1, sp=(3, 16, 8), Cs=[64], Cout=72, dims=3, algo=2, stats=True),
     # depth-rolling kernel (algo 4): three depth taps stacked along N, two interleaved bricks per CTA, CTA pairs
     "roll_64": dict(N=1, sp=(4, 32, 16), Cs=[64], Cout=64, dims=3, algo=4),
     "roll_one_plane": dict(N=2, sp=(1, 32, 16), Cs=[64], Cout=64, dims=3, algo=4),
