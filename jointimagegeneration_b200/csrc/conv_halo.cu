@@ -441,9 +441,10 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
         GG_REQUIRE(!a->y_is_f32, GG_ERR_UNSUPPORTED);
         GG_REQUIRE(aligned(a->gn_partial, 16) && a->gn_chunk_base >= 0 && a->gn_chunk_base + grid * 4 <= a->gn_nchunks_total, GG_ERR_BAD_ARG);
         p.gn_partial = a->gn_partial; p.gn_chunk_base = a->gn_chunk_base; p.gn_nchunks_total = a->gn_nchunks_total;
-        for (int n = 0; n < a->N; ++n) {
-            cudaError_t e = cudaMemsetAsync(a->gn_partial + ((size_t)n * a->gn_nchunks_total + a->gn_chunk_base) * p.Cout8 * 2, 0,
-                                            (size_t)grid * 4 * p.Cout8 * 2 * sizeof(float), stream);
+        {   // one 2-D memset: this launch's rows of every sample
+            const size_t row_bytes = (size_t)(p.Cout8 * 2) * sizeof(float);
+            cudaError_t e = cudaMemset2DAsync(a->gn_partial + (size_t)a->gn_chunk_base * (p.Cout8 * 2), (size_t)a->gn_nchunks_total * row_bytes, 0,
+                                              (size_t)(grid * 4) * row_bytes, (size_t)a->N, stream);
             if (e != cudaSuccess) return (int)e;
         }
         return pair ? launch_halo_g<true, true>(G, p, grid, smem, stream) : launch_halo_g<true, false>(G, p, grid, smem, stream);

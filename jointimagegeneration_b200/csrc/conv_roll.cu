@@ -805,9 +805,10 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
         GG_REQUIRE(g.BNs == 64 && p.Cout8 == 64 && !a->y_is_f32, GG_ERR_UNSUPPORTED);
         GG_REQUIRE(aligned(a->gn_partial, 16) && a->gn_chunk_base >= 0 && a->gn_chunk_base + g.grid * 8 <= a->gn_nchunks_total, GG_ERR_BAD_ARG);
         p.gn_partial = a->gn_partial; p.gn_chunk_base = a->gn_chunk_base; p.gn_nchunks_total = a->gn_nchunks_total;
-        for (int n = 0; n < a->N; ++n) {
-            cudaError_t e = cudaMemsetAsync(a->gn_partial + ((size_t)n * a->gn_nchunks_total + a->gn_chunk_base) * 128, 0,
-                                            (size_t)g.grid * 8 * 128 * sizeof(float), stream);
+        {   // one 2-D memset: this launch's rows of every sample
+            const size_t row_bytes = (size_t)(128) * sizeof(float);
+            cudaError_t e = cudaMemset2DAsync(a->gn_partial + (size_t)a->gn_chunk_base * (128), (size_t)a->gn_nchunks_total * row_bytes, 0,
+                                              (size_t)(g.grid * 8) * row_bytes, (size_t)a->N, stream);
             if (e != cudaSuccess) return (int)e;
         }
         return xform ? launch_roll<3, true, 64, true>(p, g.grid, smem, stream) : launch_roll<3, true, 64, false>(p, g.grid, smem, stream);

@@ -347,8 +347,10 @@ class UNetEngine:
         if out is None:
             out = self._new_act(ar, N, out_spatial, cout8, torch.float32 if f32_out else torch.bfloat16)
         halo = self._halo_ok(taps, stride, out_spatial) and callable(w_packed)
-        # the halo kernels reduce GroupNorm column sums in their epilogue (bf16 outputs)
-        halo_stats = halo and stats and self.halo_gn_stats and not f32_out
+        # the halo kernels reduce GroupNorm column sums in their epilogue (bf16 outputs): one partial row per (CTA, warp),
+        # i.e. up to 592 rows of C (sum, sum sq) pairs per sample -- less traffic than re-reading the tensor only when
+        # a sample has well over 8 x 592 positions (the 64 x 64 latents of the LDM configs do not)
+        halo_stats = halo and stats and self.halo_gn_stats and not f32_out and int(math.prod(out_spatial)) >= 8192
         algo = 1 if halo and (halo_stats or not (stats and self.fused_gn_stats)) else 0
         if algo == 1 and self._roll_ok(dims, stride, taps, offsets, cout, out_spatial, y_strides):
             algo = 4        # narrow outputs: depth-rolling kernel (three depth taps stacked along N)
