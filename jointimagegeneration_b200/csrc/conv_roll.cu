@@ -30,7 +30,7 @@
 
 namespace gg {
 
-constexpr int R_MAX_SA = 4, R_MAX_SB = 6;
+constexpr int R_MAX_SA = 4, R_MAX_SB = 8;
 constexpr int R_THREADS = 352;      // warps 0, 1, 6 = producers / MMA; warps 2..5 drain brick 0, warps 7..10 drain brick 1
 constexpr int R_THREADS_XF = 480;   // + warps 11..14: GroupNorm/SiLU transform of the landed halo planes
 constexpr int R_STAGE_BYTES = 16384; // 128 rows x 128 B output / residual staging tile
@@ -752,10 +752,17 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
     }
     const int bar_bytes = 1024 + (xform ? R_SS_BYTES : 0) + (p.tma_epi ? 2 * R_STAGE_BYTES : 0);   // + barriers, additive vectors, (scale, shift) table
     const int avail = H_SMEM_BUDGET - 1024 - bar_bytes;
-    const int G = kwmax, tap_bytes = 3 * (int)p.b_unit_bytes;
-    GG_REQUIRE(G == 3, GG_ERR_UNSUPPORTED);                       // a B stage = one kw row of stacked tap tiles
-    // the transform adds a hop between "plane landed" and "plane usable": a fourth plane stage, one fewer weight stage
-    int SA = xform ? 4 : 3;
+    const int tap_bytes = 3 * (int)p.b_unit_bytes;
+    GG_REQUIRE(kwmax == 3, GG_ERR_UNSUPPORTED);
+    // Ring shapes.  Default: a weight stage = one kw row of stacked tap tiles (G = 3, 12 MMAs per stage), three plane
+    // stages (four when the transform adds a hop between "landed" and "usable").  With 1x1x1 extra sources every step
+    // pushes 2-3 more (small) planes through the plane ring and each is held for a whole TMA latency but only four
+    // MMAs: those convs take single-tap weight stages (G = 1) and spend the shared memory on a fourth plane stage.
+    bool has_centre = false;
+    for (int s = 0; s < a->nsrc; ++s) has_centre = has_centre || a->src[s].centre_only;
+    int G = has_centre ? 1 : 3;
+    if (const char* e = getenv("GG_ROLL_G")) { const int v = atoi(e); if (v == 1 || v == 3) G = v; }     // tuning knob
+    int SA = (xform || has_centre) ? 4 : 3;
     int SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes);
     if (SB < 3 && SA > 3) { SA = 3; SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes); }
     GG_REQUIRE(SB >= 2, GG_ERR_UNSUPPORTED);
@@ -811,9 +818,14 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
                                               (size_t)(g.grid * 8) * row_bytes, (size_t)a->N, stream);
             if (e != cudaSuccess) return (int)e;
         }
+        if (G == 1) return xform ? launch_roll<1, true, 64, true>(p, g.grid, smem, stream) : launch_roll<1, true, 64, false>(p, g.grid, smem, stream);
         return xform ? launch_roll<3, true, 64, true>(p, g.grid, smem, stream) : launch_roll<3, true, 64, false>(p, g.grid, smem, stream);
     }
-    if (g.BNs == 16) return xform ? launch_roll<3, false, 16, true>(p, g.grid, smem, stream) : launch_roll<3, false, 16, false>(p, g.grid, smem, stream);
+    if (g.BNs == 16) {
+        if (G == 1) return xform ? launch_roll<1, false, 16, true>(p, g.grid, smem, stream) : launch_roll<1, false, 16, false>(p, g.grid, smem, stream);
+        return xform ? launch_roll<3, false, 16, true>(p, g.grid, smem, stream) : launch_roll<3, false, 16, false>(p, g.grid, smem, stream);
+    }
+    if (G == 1) return xform ? launch_roll<1, false, 64, true>(p, g.grid, smem, stream) : launch_roll<1, false, 64, false>(p, g.grid, smem, stream);
     return xform ? launch_roll<3, false, 64, true>(p, g.grid, smem, stream) : launch_roll<3, false, 64, false>(p, g.grid, smem, stream);
 }
 

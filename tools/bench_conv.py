@@ -41,9 +41,17 @@ def main():
                         continue
                     gam, bet = torch.ones(Cin, device=dev), torch.zeros(Cin, device=dev)
                     ss = ops.gn_finalize(ops.gn_partial(x), None, gam, bet, D * H * W, 1e-5)
-                a = ops.make_conv_args([(x, False)], wp, Cout, y, dims=3, ksize=3, stride=1, bias=bp,
+                srcs, wpk, ssl = [(x, False)], wp, ([ss] if ss is not None else None)
+                if "skip" in variant:       # fused 1x1x1 skip over two extra raw sources (128 + 64 channels)
+                    xa = torch.randn((N, D, H, W, 128), device=dev, dtype=torch.bfloat16)
+                    xb = torch.randn((N, D, H, W, 64), device=dev, dtype=torch.bfloat16)
+                    ex = [torch.randn((Cout, 128), device=dev) * 0.05, torch.randn((Cout, 64), device=dev) * 0.05]
+                    wpk = ops.pack_conv_weight(w, [Cin], extra=ex, chunk_major=True)
+                    srcs = [(x, False), (xa, True), (xb, True)]
+                    ssl = ([ss, None, None] if ss is not None else None)
+                a = ops.make_conv_args(srcs, wpk, Cout, y, dims=3, ksize=3, stride=1, bias=bp,
                                        residual=res if "res" in variant else None, algo=algo,
-                                       src_ss=[ss] if ss is not None else None, ss_stride=2 * Cin)
+                                       src_ss=ssl, ss_stride=2 * Cin)
                 part = None
                 if "stats" in variant:
                     per = int(_C.lib().gg_conv_stats_chunks(C.byref(a)))
