@@ -305,15 +305,33 @@ def run_ours(args):
             with open(os.path.join(ROOT, "gpurun_out", "bench_detail.txt"), "w") as f:
                 f.write("\n".join(rows) + "\n")
         kernel_ms = {k: round(v[0], 4) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
+        # conv launches by kernel (gg_conv_args.algo): launches, ms and issued TFLOP/s (issued = incl. channel padding)
+        import ctypes as _ct
+        by_kernel = {}
+        for (fn, fargs), (name, a, b) in zip(plan.steps, evs):
+            if name != "gg_conv_fwd":
+                continue
+            ca = fargs[0]._obj if hasattr(fargs[0], "_obj") else _ct.cast(fargs[0], _ct.POINTER(_C.ConvArgs)).contents
+            kname = {0: "conv_tcgen05_kernel", 4: "conv_roll_kernel"}.get(int(ca.algo), "conv_halo_kernel")
+            kk = _C.lib().gg_conv_packed_k(_ct.byref(ca))
+            e = by_kernel.setdefault(kname, {"launches": 0, "ms": 0.0, "issued_flop": 0.0})
+            e["launches"] += 1
+            e["ms"] += a.elapsed_time(b)
+            e["issued_flop"] += 2.0 * ca.N * ca.Do * ca.Ho * ca.Wo * ca.Cout * kk
+        for e in by_kernel.values():
+            e["tflops_issued"] = round(e["issued_flop"] / max(e["ms"], 1e-9) / 1e9, 1)
+            e["frac_of_peak"] = round(e["tflops_issued"] / peaks["tf_sustained"], 3)
+            e["ms"] = round(e["ms"], 3)
         n_conv = kinds["gg_conv_fwd"][1] // reps
         conv_ms = kinds["gg_conv_fwd"][0]
         share = (1.0 / world) if slab else 1.0                          # FLOPs this rank executes
         attn_flops = wl.get("attn_flop", 0.022e12 / 6.324e12 * wl["flop_per_sample"])
         conv_alg = (wl["flop_per_sample"] - attn_flops) * B * share
         ach = conv_alg / (conv_ms / 1e3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_tcgen05_kernel (all %d conv launches of one step)" % n_conv,
+        line["roofline"] = {"bound": "tensor", "kernel": "conv_roll_kernel + conv_halo_kernel + conv_tcgen05_kernel (all %d conv launches of one step)" % n_conv,
                             "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
                             "traffic": None, "algorithmic_flop": conv_alg, "issued_flop": plan.flops, "avg_launch_ms": conv_ms / n_conv,
+                            "by_kernel": by_kernel,
                             "peak_source": peaks["source"] + " (bf16 sustained: kernel timed inside a long step)",
                             "whole_step_frac": wl["flop_per_sample"] * B * share / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
         cat_ms = kinds["gg_cat_step_cl"][0]
@@ -487,7 +505,7 @@ def run_ours_ldm(args):
         kinds = instrument_plan(plan, detail_path=os.path.join(ROOT, "gpurun_out", "bench_detail_ldm.txt") if args.detail else None)
         conv_ms, n_conv = kinds["gg_conv_fwd"]
         ach = wl["flop_per_sample"] * B / (conv_ms / 1e3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_tcgen05_kernel (all %d conv launches of one step)" % n_conv, "achieved": ach,
+        line["roofline"] = {"bound": "tensor", "kernel": "conv_roll_kernel + conv_halo_kernel + conv_tcgen05_kernel (all %d conv launches of one step)" % n_conv, "achieved": ach,
                             "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "traffic": None,
                             "algorithmic_flop": wl["flop_per_sample"] * B, "issued_flop": plan.flops,
                             "peak_source": peaks["source"] + " (bf16 sustained)",

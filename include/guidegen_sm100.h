@@ -130,6 +130,30 @@ typedef struct {
 
 int gg_ddim_update(const gg_ddim_args* a, gg_stream_t stream);
 
+/* PLMS noise-prediction combination   latentdiffusion/ldm/models/diffusion/plms.py:178-233 (p_sample_plms).
+ * The pseudo linear multistep sampler replaces e_t in the DDIM update (eta = 0) by an Adams-Bashforth
+ * combination of the current and up to three previous predictions (:219-230), evaluated in fp32 in the
+ * reference's order, one rounding per operation:
+ *   order 0 (first step, old1 = the prediction at x_prev, t_next):  (e + old1) / 2
+ *   order 1: (3 e - old1) / 2      order 2: (23 e - 16 old1 + 5 old2) / 12
+ *   order 3: (55 e - 59 old1 + 37 old2 - 9 old3) / 24
+ * With e_uncond the classifier-free-guidance mix (:183-188) is applied to e_t first; e_cur receives that
+ * guided prediction (what the sampler appends to old_eps), e_prime the combination (input of gg_ddim_update). */
+typedef struct {
+    const float* e_t;
+    const float* e_uncond;  /* optional */
+    const float* old1;      /* newest previous prediction (order >= 1), or e_t_next (order 0) */
+    const float* old2;
+    const float* old3;
+    float* e_cur;           /* optional; may alias e_t */
+    float* e_prime;
+    int64_t n;
+    int32_t order;          /* 0..3 */
+    float guidance_scale;
+} gg_plms_args;
+
+int gg_plms_eps(const gg_plms_args* a, gg_stream_t stream);
+
 /* Ancestral DDPM update   latentdiffusion/ldm/models/diffusion/ddpm.py:1060-1120 (p_mean_variance, p_sample),
  * :215-230 (predict_start_from_noise, q_posterior); used by sample_diffusion.py --vanilla_sample.
  * coef fp32 [B, 6] = (sqrt_recip_acp[t], sqrt_recipm1_acp[t], posterior_mean_coef1[t], posterior_mean_coef2[t],

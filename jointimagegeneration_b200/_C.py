@@ -66,6 +66,11 @@ class GnFinalizeArgs(C.Structure):
                 ("N", C.c_int32), ("groups", C.c_int32), ("S", C.c_int64), ("eps", C.c_float)]
 
 
+class PlmsArgs(C.Structure):
+    _fields_ = [("e_t", C.c_void_p), ("e_uncond", C.c_void_p), ("old1", C.c_void_p), ("old2", C.c_void_p), ("old3", C.c_void_p),
+                ("e_cur", C.c_void_p), ("e_prime", C.c_void_p), ("n", C.c_int64), ("order", C.c_int32), ("guidance_scale", C.c_float)]
+
+
 class ConvSrc(C.Structure):
     _fields_ = [("x", C.c_void_p), ("C", C.c_int32), ("centre_only", C.c_int32), ("d_shift", C.c_int32), ("reserved", C.c_int32)]
 
@@ -107,6 +112,7 @@ SYMBOLS = {
     "gg_cat_step_cl": (C.c_int, [C.POINTER(CatStepCLArgs), _vp]),
     "gg_ddim_update": (C.c_int, [C.POINTER(DdimArgs), _vp]),
     "gg_ddpm_update": (C.c_int, [C.POINTER(DdpmArgs), _vp]),
+    "gg_plms_eps": (C.c_int, [C.POINTER(PlmsArgs), _vp]),
     "gg_labels_to_mask": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "gg_minmax_normalize": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _vp]),
     "gg_nchw_to_cl": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i64, _vp]),

@@ -539,6 +539,31 @@ __global__ void __launch_bounds__(256) ddim_kernel(const gg_ddim_args a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// PLMS: Adams-Bashforth combination of noise predictions (ldm/models/diffusion/plms.py:219-230), torch's fp32
+// evaluation order with one rounding per operation
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plms_eps_kernel(const gg_plms_args a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    float e = a.e_t[i];
+    if (a.e_uncond) e = __fadd_rn(a.e_uncond[i], __fmul_rn(a.guidance_scale, __fsub_rn(e, a.e_uncond[i])));
+    if (a.e_cur) a.e_cur[i] = e;
+    float r;
+    if (a.order == 0) {
+        r = __fdiv_rn(__fadd_rn(e, a.old1[i]), 2.0f);
+    } else if (a.order == 1) {
+        r = __fdiv_rn(__fsub_rn(__fmul_rn(3.0f, e), a.old1[i]), 2.0f);
+    } else if (a.order == 2) {
+        r = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.0f, e), __fmul_rn(16.0f, a.old1[i])), __fmul_rn(5.0f, a.old2[i])), 12.0f);
+    } else {
+        r = __fsub_rn(__fmul_rn(55.0f, e), __fmul_rn(59.0f, a.old1[i]));
+        r = __fadd_rn(r, __fmul_rn(37.0f, a.old2[i]));
+        r = __fdiv_rn(__fsub_rn(r, __fmul_rn(9.0f, a.old3[i])), 24.0f);
+    }
+    a.e_prime[i] = r;
+}
+
+// ------------------------------------------------------------------------------------------
 // ancestral DDPM update (ldm/models/diffusion/ddpm.py:1060-1120 p_mean_variance + p_sample)
 //   x0 = sr x - srm1 e ; clip ; mean = c1 x0 + c2 x ; x_prev = mean + nz * exp(0.5 logvar) * (noise * T)
 // coef[b] = (sr, srm1, c1, c2, logvar, nz) gathered per sample by the host wrapper
@@ -720,6 +745,14 @@ extern "C" int gg_ddim_update(const gg_ddim_args* a, gg_stream_t stream) {
         const unsigned blocks = (unsigned)((a->n + 255) / 256);
         ddim_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(*a);
     }
+    return launch_result();
+}
+
+extern "C" int gg_plms_eps(const gg_plms_args* a, gg_stream_t stream) {
+    GG_REQUIRE(a != nullptr && a->e_t && a->e_prime && a->n > 0 && a->order >= 0 && a->order <= 3, GG_ERR_BAD_ARG);
+    GG_REQUIRE(a->old1 != nullptr && (a->order < 2 || a->old2 != nullptr) && (a->order < 3 || a->old3 != nullptr), GG_ERR_BAD_ARG);
+    const unsigned blocks = (unsigned)((a->n + 255) / 256);
+    plms_eps_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*a);
     return launch_result();
 }
 

@@ -2,3 +2,4 @@
 from .ddim import DDIMSampler  # noqa: F401
 from .ddpm import DiffusionWrapper, LatentDiffusion  # noqa: F401
 from .openaimodel import UNetModel  # noqa: F401
+from .plms import PLMSSampler  # noqa: F401

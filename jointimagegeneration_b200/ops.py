@@ -81,6 +81,26 @@ def ddim_update(x, e_t, coef, noise=None, temperature=1.0, want_pred_x0=True, x_
     return x_prev, pred_x0
 
 
+def plms_eps(e_t, olds, order, e_uncond=None, guidance_scale=1.0, e_cur=None, e_prime=None):
+    """PLMS combination of noise predictions (plms.py:219-230).  olds = [newest, ..., oldest] previous predictions
+    (order 0: [e_t_next]).  Returns (e_cur, e_prime): the (guided) current prediction and the combination."""
+    _chk(e_t, torch.float32)
+    for o in olds:
+        _chk(o, torch.float32)
+    assert 0 <= order <= 3 and len(olds) >= max(order, 1)
+    if e_uncond is not None:
+        _chk(e_uncond, torch.float32)
+        if e_cur is None:
+            e_cur = torch.empty_like(e_t)
+    if e_prime is None:
+        e_prime = torch.empty_like(e_t)
+    o = list(olds) + [None, None, None]
+    a = _C.PlmsArgs(_C.ptr(e_t), _C.ptr(e_uncond), _C.ptr(o[0]), _C.ptr(o[1]), _C.ptr(o[2]), _C.ptr(e_cur), _C.ptr(e_prime),
+                    e_t.numel(), int(order), float(guidance_scale))
+    _C.check(_C.lib().gg_plms_eps(C.byref(a), _C.stream()), "gg_plms_eps")
+    return (e_cur if e_cur is not None else e_t), e_prime
+
+
 def ddpm_update(x, e_t, coef, noise=None, temperature=1.0, clip_denoised=False, want_x0=False):
     """Ancestral DDPM step (ddpm.py:1060-1120).  coef: device fp32 [B, 6]."""
     _chk(x, torch.float32), _chk(e_t, torch.float32), _chk(coef, torch.float32)

@@ -97,6 +97,50 @@ def ddim_sample(eps_fn: Callable[[Tensor, Tensor], Tensor], acp_f32: np.ndarray,
     return img
 
 
+def plms_combine(e_t: np.ndarray, old_eps) -> np.ndarray:
+    """Adams-Bashforth combination of plms.py:224-230 (old_eps = chronological list, newest last), fp32,
+    torch's left-to-right evaluation with one rounding per operation."""
+    f = np.float32
+    if len(old_eps) == 1:
+        return ((f(3) * e_t - old_eps[-1]) / f(2)).astype(np.float32)
+    if len(old_eps) == 2:
+        return ((f(23) * e_t - f(16) * old_eps[-1] + f(5) * old_eps[-2]) / f(12)).astype(np.float32)
+    return ((f(55) * e_t - f(59) * old_eps[-1] + f(37) * old_eps[-2] - f(9) * old_eps[-3]) / f(24)).astype(np.float32)
+
+
+def plms_sample(eps_fn: Callable[[Tensor, Tensor], Tensor], acp_f32: np.ndarray, x_T: Tensor, S: int, record=None) -> Tensor:
+    """PLMSSampler.plms_sampling + p_sample_plms (plms.py:119-236) at eta = 0 without guidance: the DDIM update
+    (get_x_prev_and_pred_x0, :198-213) fed with the multistep combination; the first step evaluates the model a
+    second time at (x_prev, t_next) and averages (:219-223).  `record(i, pred_x0, e_t)` is called per step."""
+    ts = make_ddim_timesteps(S, acp_f32.shape[0])
+    tab = ddim_tables(acp_f32, ts, 0.0)
+    sig, a, ap, s1m = tab["sigmas"], tab["alphas"], tab["alphas_prev"], tab["sqrt_one_minus_alphas"]
+    time_range = np.flip(ts)
+    x = x_T.clone()
+    B = x.shape[0]
+    old = []
+    for i, step in enumerate(time_range):
+        index = len(ts) - i - 1
+        t = torch.full((B,), int(step), dtype=torch.long)
+        t_next = torch.full((B,), int(time_range[min(i + 1, len(time_range) - 1)]), dtype=torch.long)
+        e_t = eps_fn(x, t).numpy().astype(np.float32)
+        xn = x.numpy()
+        if len(old) == 0:
+            x_prev0, _ = ddim_update(xn, e_t, a[index], ap[index], sig[index], s1m[index], None)
+            e_next = eps_fn(torch.from_numpy(x_prev0), t_next).numpy().astype(np.float32)
+            e_prime = ((e_t + e_next) / np.float32(2)).astype(np.float32)
+        else:
+            e_prime = plms_combine(e_t, old)
+        x_prev, pred_x0 = ddim_update(xn, e_prime, a[index], ap[index], sig[index], s1m[index], None)
+        old.append(e_t)
+        if len(old) >= 4:
+            old.pop(0)
+        if record is not None:
+            record(i, pred_x0, e_t)
+        x = torch.from_numpy(x_prev)
+    return x
+
+
 def ddpm_tables(betas: np.ndarray):
     """ddpm.py:118-163 -> dict of f32 arrays used by the ancestral sampler."""
     alphas = 1.0 - betas

@@ -185,6 +185,33 @@ def ldm_ddim(name, params, B, hw, S, eta, hybrid=False, seed_w=11, store_full=Tr
 
 
 @torch.no_grad()
+def ldm_plms(name, params, B, hw, S, seed_w=11):
+    """PLMSSampler.sample of the unmodified reference (plms.py) on the tiny concat-conditioned LDM network."""
+    ref = refshim.ldm()
+    unet = ref.UNetModel(**params).eval()
+    unet.load_state_dict(weights.synth_state_dict(weights.shapes_of(unet), seed_w))
+    model = _DuckLDM(ref, unet, "concat")
+    x_T = weights.normal(21, (B, 4) + hw)
+    cond = weights.normal(22, (B, 4) + hw)
+    sampler = ref.PLMSSamplerCPU(model)
+    inter, eps = [], []
+    real = sampler.p_sample_plms
+
+    def spy(*a, **k):
+        out = real(*a, **k)
+        eps.append(out[2].clone())
+        return out
+
+    sampler.p_sample_plms = spy
+    out, _ = sampler.sample(S=S, batch_size=B, shape=(4,) + hw, conditioning=cond, eta=0.0, x_T=x_T, verbose=False,
+                            img_callback=lambda p, i: inter.append(p.clone()))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), B=B, hw=np.asarray(hw), S=S, seed_w=seed_w, final=out.numpy(),
+                        pred_x0=np.stack([p.numpy() for p in inter]), e_t=np.stack([e.numpy() for e in eps]),
+                        alphas_cumprod=model.alphas_cumprod.numpy())
+    print(name, "final std", float(out.std()))
+
+
+@torch.no_grad()
 def ldm_forward(name, params, B, hw, sub, seed_w=12):
     ref = refshim.ldm()
     unet = ref.UNetModel(**params).eval()
@@ -255,6 +282,8 @@ def main(argv):
         ldm_ddim("ldm_tiny_eta0", configs.LDM_TINY, B=2, hw=(16, 16), S=5, eta=0.0)
         ldm_ddim("ldm_tiny_eta05", configs.LDM_TINY, B=2, hw=(16, 16), S=5, eta=0.5)
         ldm_ddim("ldm_tiny_hybrid", configs.LDM_TINY_XATTN, B=2, hw=(16, 16), S=4, eta=0.0, hybrid=True)
+    if want("ldm_plms"):
+        ldm_plms("ldm_tiny_plms", configs.LDM_TINY, B=2, hw=(16, 16), S=7)
     if want("ccdm_cfg1"):
         ccdm_chain("ccdm_cfg1", configs.CCDM_PARAMS_YML, T=10, B=1, C=12, spatial=(32, 32, 32), sub=4)
     if want("ldm_ae"):

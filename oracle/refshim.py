@@ -89,6 +89,14 @@ def ldm():
         def register_buffer(self, name, attr):  # D8: keep tensors where they are
             setattr(self, name, attr)
 
+    pm = importlib.import_module("ldm.models.diffusion.plms")
+
+    class PLMSSamplerCPU(pm.PLMSSampler):
+        def register_buffer(self, name, attr):  # D8: keep tensors where they are
+            setattr(self, name, attr)
+
+    ns.PLMSSamplerCPU = PLMSSamplerCPU
+    ns.plms_module = pm
     ns.UNetModel = om.UNetModel
     ns.SpatialTransformer = at.SpatialTransformer
     ns.CrossAttention = at.CrossAttention

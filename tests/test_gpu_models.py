@@ -262,6 +262,70 @@ def test_ddim_sampler_bit_exact_given_identical_eps():
     assert np.array_equal(gp.cpu().numpy(), want_prev) and np.array_equal(g0.cpu().numpy(), want_x0)
 
 
+def test_plms_sampler_vs_reference_and_oracle():
+    """PLMSSampler (ldm/plms.py) against the unmodified reference's PLMS chain on the tiny LDM network (bf16 network vs
+    fp32 reference: tolerance), the multistep combination kernel bit for bit against the oracle for every order incl.
+    guidance, and a whole chain with a fixed eps function against the oracle's PLMS loop."""
+    from jointimagegeneration_b200 import ops
+    from jointimagegeneration_b200.ldm.plms import PLMSSampler
+    from oracle import configs, ddim, weights
+    g = golden("ldm_tiny_plms")
+    B, hw, S = int(g["B"]), tuple(int(v) for v in g["hw"]), int(g["S"])
+    model, _ = _ldm(configs.LDM_TINY, int(g["seed_w"]), "concat")
+    x_T = weights.normal(21, (B, 4) + hw).cuda()
+    cc = weights.normal(22, (B, 4) + hw).cuda()
+    sampler = PLMSSampler(model)
+    inter = []
+    out, _ = sampler.sample(S=S, batch_size=B, shape=(4,) + hw, conditioning=cc, eta=0.0, x_T=x_T, verbose=False, dims=2,
+                            img_callback=lambda p, i: inter.append(p.clone()))
+    assert len(inter) == g["pred_x0"].shape[0]
+    out = out.cpu().numpy()
+    print(f"plms: pred_x0[0] rel {rel(inter[0].cpu().numpy(), g['pred_x0'][0]):.4f}  final rel {rel(out, g['final']):.4f}  "
+          f"PSNR {psnr(out, g['final']):.1f} dB")
+    assert rel(inter[0].cpu().numpy(), g["pred_x0"][0]) <= 3e-2
+    assert psnr(out, g["final"]) >= 30.0 and rel(out, g["final"]) <= 8e-2
+    with pytest.raises(ValueError):
+        sampler.make_schedule(5, ddim_eta=0.5, verbose=False)
+
+    # the combination kernel: exact for every order, with and without classifier-free guidance
+    rs = np.random.RandomState(3)
+    e, eu, o1, o2, o3 = (rs.standard_normal((2, 4, 8, 8)).astype(np.float32) for _ in range(5))
+    cu = lambda a: torch.from_numpy(a).cuda()
+    for guided in (False, True):
+        scale = np.float32(2.5)
+        e_in = (eu + (scale * (e - eu).astype(np.float32)).astype(np.float32)).astype(np.float32) if guided else e
+        wants = {0: ((e_in + o1) / np.float32(2)).astype(np.float32), 1: ddim.plms_combine(e_in, [o1]),
+                 2: ddim.plms_combine(e_in, [o2, o1]), 3: ddim.plms_combine(e_in, [o3, o2, o1])}
+        for order, want in wants.items():
+            e_cur, e_prime = ops.plms_eps(cu(e), [cu(o1), cu(o2), cu(o3)][:max(order, 1)], order,
+                                          e_uncond=cu(eu) if guided else None, guidance_scale=2.5)
+            assert np.array_equal(e_prime.cpu().numpy(), want), (guided, order)
+            assert np.array_equal(e_cur.cpu().numpy(), e_in), (guided, order)
+
+    # a chain with a fixed eps function: same loop structure (second evaluation on the first step, history of three)
+    class Fixed:
+        def __init__(self, dev):
+            betas = ddim.make_beta_schedule_linear(1000, configs.LDM_SCHEDULE["linear_start"], configs.LDM_SCHEDULE["linear_end"])
+            acp = np.cumprod(1.0 - betas)
+            self.num_timesteps = 1000
+            self.betas = torch.tensor(betas, dtype=torch.float32, device=dev)
+            self.alphas_cumprod = torch.tensor(acp, dtype=torch.float32, device=dev)
+            self.alphas_cumprod_prev = torch.tensor(np.append(1.0, acp[:-1]), dtype=torch.float32, device=dev)
+            self.device = torch.device(dev)
+            self.parameterization = "eps"
+
+        def apply_model(self, x, t, c):
+            return (torch.sin(3 * x) * 0.5 + c * 0.25 - t.float().reshape(-1, 1, 1, 1) * 1e-3).contiguous()
+
+    Bf, shape, Sf = 3, (4, 8, 8), 10
+    xT, c = weights.normal(1, (Bf,) + shape), weights.normal(2, (Bf,) + shape)
+    got, _ = PLMSSampler(Fixed("cuda")).sample(S=Sf, batch_size=Bf, shape=shape, conditioning=c.cuda(), eta=0.0, x_T=xT.cuda(),
+                                               verbose=False)
+    cpu = Fixed("cpu")
+    want = ddim.plms_sample(lambda x, t: cpu.apply_model(x, t, c), cpu.alphas_cumprod.numpy(), xT, Sf)
+    assert rel(got.cpu().numpy(), want.numpy()) <= 1e-5       # sin() differs in the last bit between CPU and GPU
+
+
 @pytest.mark.slow
 def test_ldm_ae_config_forward_vs_reference():
     """BASELINE config 3 network (ruijin-ldm_from_controlnet_ae.yaml), one forward at B=1."""
