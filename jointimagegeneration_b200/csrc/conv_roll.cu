@@ -34,6 +34,7 @@ constexpr int R_MAX_SA = 4, R_MAX_SB = 8;
 constexpr int R_THREADS = 352;      // warps 0, 1, 6 = producers / MMA; warps 2..5 drain brick 0, warps 7..10 drain brick 1
 constexpr int R_THREADS_XF = 480;   // + warps 11..14: GroupNorm/SiLU transform of the landed halo planes
 constexpr int R_STAGE_BYTES = 16384; // 128 rows x 128 B output / residual staging tile
+constexpr int XB = 4;               // rows a transform thread handles per batch (6 measured the same)
 constexpr int R_SS_BYTES = 4096;    // (scale, shift) table: up to 512 channels over all sources
 
 struct RollSeg {
@@ -447,15 +448,15 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
                                 const int jl = xt & 7;
                                 const float4* tb = ss_tab + ((sg.ss_off + j * BK) >> 1) + 4 * jl;
                                 const float4 q0 = tb[0], q1 = tb[1], q2 = tb[2], q3 = tb[3];
-                                // four rows per batch, loads first: a lone warp per scheduler needs the ILP (a per-row
+                                // XB rows per batch, loads first: a lone warp per scheduler needs the ILP (a per-row
                                 // branch would serialise LDS -> FMA -> MUFU -> FMA -> STS chains)
 #pragma unroll 1
-                                for (int r0 = xt >> 3; r0 < nrow; r0 += 64) {
-                                    uint4 v[4];
-                                    uint4* ptr[4];
-                                    bool ok[4];
+                                for (int r0 = xt >> 3; r0 < nrow; r0 += 16 * XB) {
+                                    uint4 v[XB];
+                                    uint4* ptr[XB];
+                                    bool ok[XB];
 #pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
+                                    for (int u = 0; u < XB; ++u) {
                                         const int r = r0 + 16 * u, rc = min(r, nrow - 1);
                                         const int hh = (int)(((uint32_t)rc * (uint32_t)sg.inv_pitch) >> 16), ww = rc - hh * sg.pitch;    // rc < 2^10
                                         const int gh = h0 + sg.oh + hh, gw = w0 + sg.ow + ww;
@@ -464,12 +465,12 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
                                         v[u] = *ptr[u];
                                     }
 #pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
+                                    for (int u = 0; u < XB; ++u) {
                                         v[u].x = xf_pair(v[u].x, q0, silu); v[u].y = xf_pair(v[u].y, q1, silu);
                                         v[u].z = xf_pair(v[u].z, q2, silu); v[u].w = xf_pair(v[u].w, q3, silu);
                                     }
 #pragma unroll
-                                    for (int u = 0; u < 4; ++u)
+                                    for (int u = 0; u < XB; ++u)
                                         if (ok[u]) *ptr[u] = v[u];
                                 }
                                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> tensor-core reads
