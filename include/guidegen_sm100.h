@@ -43,6 +43,10 @@ int gg_version(void);
 const char* gg_status_string(int status);
 /* 0 when the current device is compute capability 10.x, GG_ERR_NO_DEVICE otherwise */
 int gg_device_check(void);
+/* sizeof() of the argument structs, in header order (gg_cat_args, gg_cat_step_cl_args, gg_ddim_args, gg_plms_args,
+ * gg_ddpm_args, gg_gn_finalize_args, gg_conv_src, gg_conv_args, gg_attn_args): lets a binding in another language
+ * check its mirror of this header without a GPU.  Writes min(n, 9) entries, returns 9. */
+int gg_abi_sizes(int32_t* out, int n);
 /* number of kernels launched by this library since load / since last reset (host counter) */
 uint64_t gg_launch_count(void);
 void gg_launch_count_reset(void);

@@ -100,12 +100,16 @@ class AttnArgs(C.Structure):
                 ("scale", C.c_float)]
 
 
+# the ctypes mirrors above, in the order gg_abi_sizes() reports the C structs
+ABI_STRUCTS = [CatArgs, CatStepCLArgs, DdimArgs, PlmsArgs, DdpmArgs, GnFinalizeArgs, ConvSrc, ConvArgs, AttnArgs]
+
 # every symbol include/guidegen_sm100.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SYMBOLS = {
     "gg_version": (C.c_int, []),
     "gg_status_string": (C.c_char_p, [C.c_int]),
     "gg_device_check": (C.c_int, []),
+    "gg_abi_sizes": (C.c_int, [C.POINTER(C.c_int32), C.c_int]),
     "gg_launch_count": (C.c_uint64, []),
     "gg_launch_count_reset": (None, []),
     "gg_cat_posterior_sample": (C.c_int, [C.POINTER(CatArgs), _vp]),

@@ -37,6 +37,13 @@ def test_library_exports_every_declared_symbol():
     a.kd = a.kh = a.kw = 3
     assert lib.gg_conv_packed_k(ctypes.byref(a)) == 27 * 192 + 64
     assert lib.gg_cat_posterior_sample(None, None) == -1
+    # the ctypes mirrors of the argument structs have the C structs' sizes (ABI drift shows up here, without a GPU)
+    n = lib.gg_abi_sizes(None, 0)
+    assert n == len(_C.ABI_STRUCTS)
+    sizes = (ctypes.c_int32 * n)()
+    lib.gg_abi_sizes(sizes, n)
+    for cls, want in zip(_C.ABI_STRUCTS, list(sizes)):
+        assert ctypes.sizeof(cls) == want, (cls.__name__, ctypes.sizeof(cls), want)
 
 
 def test_sass_has_blackwell_tensor_and_tma_instructions():
