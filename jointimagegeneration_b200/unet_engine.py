@@ -553,6 +553,46 @@ class UNetEngine:
                  x.N * x.S, x.C, float(norm.eps))
         return y
 
+    def _transformer_block(self, plan, ar, blk: M.BasicTransformerBlock, h: Act, ctx: Optional[Act]) -> Act:
+        """BasicTransformerBlock._forward (ldm/modules/attention.py:210-214, ccdm unet_openai/attention.py:142-146):
+        self-attention, cross-attention (self when ctx is None), GEGLU feed-forward, each with its residual.
+        Consumes (releases) h."""
+        n1 = self._layernorm(plan, ar, h, blk.norm1)
+        h2 = self._cross_attention(plan, ar, blk.attn1, n1, None, h)
+        ar.release(n1.t), ar.release(h.t)
+        n2 = self._layernorm(plan, ar, h2, blk.norm2)
+        h3 = self._cross_attention(plan, ar, blk.attn2, n2, ctx, h2)
+        ar.release(n2.t), ar.release(h2.t)
+        n3 = self._layernorm(plan, ar, h3, blk.norm3)
+        gp = blk.ff.net[0].proj
+        f1 = self._linear(plan, ar, n3, gp.weight, (id(gp.weight), "p"), gp.out_features, gp.bias)
+        ar.release(n3.t)
+        inner = gp.out_features // 2
+        g = self._new_act(ar, h3.N, h3.sp, inner)
+        plan.add(self.lib.gg_geglu, f1.ip, g.ip, h3.N * h3.S, inner)
+        ar.release(f1.t)
+        l2 = blk.ff.net[2]
+        out = self._linear(plan, ar, g, l2.weight, (id(l2.weight), "p"), l2.out_features, l2.bias, h3)
+        ar.release(g.t), ar.release(h3.t)
+        return out
+
+    def build_token_plan(self, N: int, L: int, Cc: int, blocks) -> Plan:
+        """A stack of BasicTransformerBlocks over a token tensor [N, L, C] (bf16, channels-last): the text-context
+        encoder of the CCDM (ccdm/ddpm/models/encoder.py:103-123).  inputs['tokens'] -> outputs['tokens']."""
+        self.lib = _C.lib()
+        dev = self._dev()
+        plan, ar = Plan(), _Arena(dev)
+        t_in = torch.zeros((N, 1, 1, L, Cc), dtype=torch.bfloat16, device=dev)
+        plan.inputs["tokens"] = t_in
+        plan.keep.append(t_in)
+        h = Act(t_in)           # not arena memory: the first block's release of its input is a no-op
+        for blk in blocks:
+            h = self._transformer_block(plan, ar, blk, h, None)
+        plan.outputs["tokens"] = h.interior
+        plan.keep.append(ar.stores)
+        plan.arena_bytes = ar.total
+        return plan
+
     def _spatial_transformer(self, plan, ar, st: M.SpatialTransformer, x: Act, ctx: Optional[Act]) -> Act:
         if self.slab is not None:
             raise NotImplementedError("depth-slab mode covers the shipped CCDM network (AttentionBlock), not SpatialTransformer")
@@ -561,23 +601,7 @@ class UNetEngine:
         h = self._linear(plan, ar, xn, pin.weight.reshape(pin.out_channels, -1), (id(pin.weight), "p"), pin.out_channels, pin.bias)
         ar.release(xn.t)
         for blk in st.transformer_blocks:
-            n1 = self._layernorm(plan, ar, h, blk.norm1)
-            h2 = self._cross_attention(plan, ar, blk.attn1, n1, None, h)
-            ar.release(n1.t), ar.release(h.t)
-            n2 = self._layernorm(plan, ar, h2, blk.norm2)
-            h3 = self._cross_attention(plan, ar, blk.attn2, n2, ctx, h2)
-            ar.release(n2.t), ar.release(h2.t)
-            n3 = self._layernorm(plan, ar, h3, blk.norm3)
-            gp = blk.ff.net[0].proj
-            f1 = self._linear(plan, ar, n3, gp.weight, (id(gp.weight), "p"), gp.out_features, gp.bias)
-            ar.release(n3.t)
-            inner = gp.out_features // 2
-            g = self._new_act(ar, h3.N, h3.sp, inner)
-            plan.add(self.lib.gg_geglu, f1.ip, g.ip, h3.N * h3.S, inner)
-            ar.release(f1.t)
-            l2 = blk.ff.net[2]
-            h = self._linear(plan, ar, g, l2.weight, (id(l2.weight), "p"), l2.out_features, l2.bias, h3)
-            ar.release(g.t), ar.release(h3.t)
+            h = self._transformer_block(plan, ar, blk, h, ctx)
         po = st.proj_out
         out = self._linear(plan, ar, h, po.weight.reshape(po.out_channels, -1), (id(po.weight), "p"), po.out_channels, po.bias, x)
         ar.release(h.t)

@@ -212,6 +212,26 @@ def ldm_plms(name, params, B, hw, S, seed_w=11):
 
 
 @torch.no_grad()
+def text_encoder(name="ccdm_text_encoder", seed_w=17):
+    """PreloadedBERTEncoder of the unmodified reference (ccdm/ddpm/models/encoder.py:103-123): a small instance in full
+    and the shipped size (768 wide, 8 heads x 64, depth 4, 512 tokens) sub-sampled."""
+    import importlib
+    refshim.ccdm()
+    enc = importlib.import_module("ddpm.models.encoder")
+    out = {}
+    for tag, (dim, heads, d_head, depth, B, L, sub) in (("small", (128, 2, 64, 2, 2, 24, 1)), ("full", (768, 8, 64, 4, 1, 512, 8))):
+        m = enc.PreloadedBERTEncoder(embed_dim=dim, n_heads=heads, depth=depth, d_head=d_head).eval()
+        m.load_state_dict(weights.synth_state_dict(weights.shapes_of(m), seed_w))
+        x = weights.normal(41, (B, dim, L))
+        y = m(x)
+        out[tag + "_cfg"] = np.asarray([dim, heads, d_head, depth, B, L, sub])
+        out[tag + "_out"] = y[:, ::sub, ::sub].numpy()
+        out[tag + "_std"] = float((y - x).std())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed_w=seed_w, **out)
+    print(name, {k: v for k, v in out.items() if k.endswith("_std")})
+
+
+@torch.no_grad()
 def ldm_forward(name, params, B, hw, sub, seed_w=12):
     ref = refshim.ldm()
     unet = ref.UNetModel(**params).eval()
@@ -282,6 +302,8 @@ def main(argv):
         ldm_ddim("ldm_tiny_eta0", configs.LDM_TINY, B=2, hw=(16, 16), S=5, eta=0.0)
         ldm_ddim("ldm_tiny_eta05", configs.LDM_TINY, B=2, hw=(16, 16), S=5, eta=0.5)
         ldm_ddim("ldm_tiny_hybrid", configs.LDM_TINY_XATTN, B=2, hw=(16, 16), S=4, eta=0.0, hybrid=True)
+    if want("text_encoder"):
+        text_encoder()
     if want("ldm_plms"):
         ldm_plms("ldm_tiny_plms", configs.LDM_TINY, B=2, hw=(16, 16), S=7)
     if want("ccdm_cfg1"):

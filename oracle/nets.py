@@ -144,6 +144,17 @@ def spatial_transformer(sd, p, x, context, heads):
     return h + x_in
 
 
+def preloaded_bert_encoder(sd, x: Tensor, heads: int) -> Tensor:
+    """PreloadedBERTEncoder.forward (ccdm/ddpm/models/encoder.py:115-123): x [b, c, l]; depth BasicTransformerBlocks
+    without context over the token axis, then inputs + outputs."""
+    h = x.transpose(1, 2)
+    i = 0
+    while f"transformer_blocks.{i}.norm1.weight" in sd:
+        h = basic_transformer_block(sd, f"transformer_blocks.{i}", h, None, heads)
+        i += 1
+    return x + h.transpose(1, 2)
+
+
 def upsample(sd, p, x):
     """unet.py:105-116: nearest x2 in ALL spatial dims (3-D too), then 3^d conv."""
     x = F.interpolate(x, scale_factor=2, mode="nearest")

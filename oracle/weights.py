@@ -57,6 +57,28 @@ def normal(seed: int, shape) -> torch.Tensor:
     return torch.from_numpy(np.random.RandomState(seed).standard_normal(shape).astype(np.float32))
 
 
+def encoder_shapes(dim: int, heads: int, d_head: int, depth: int) -> Dict[str, tuple]:
+    """Parameter names / shapes of PreloadedBERTEncoder (ccdm/ddpm/models/encoder.py:103-113: `depth`
+    BasicTransformerBlock(dim, heads, d_head) without context, unet_openai/attention.py:127-137; GEGLU feed-forward
+    with inner width 4 dim).  Checked against the reference module when it is importable."""
+    inner, out = heads * d_head, {}
+    for i in range(depth):
+        p = f"transformer_blocks.{i}."
+        for a in ("attn1", "attn2"):
+            for n in ("to_q", "to_k", "to_v"):
+                out[p + f"{a}.{n}.weight"] = (inner, dim)
+            out[p + f"{a}.to_out.0.weight"] = (dim, inner)
+            out[p + f"{a}.to_out.0.bias"] = (dim,)
+        out[p + "ff.net.0.proj.weight"] = (8 * dim, dim)
+        out[p + "ff.net.0.proj.bias"] = (8 * dim,)
+        out[p + "ff.net.2.weight"] = (dim, 4 * dim)
+        out[p + "ff.net.2.bias"] = (dim,)
+        for n in ("norm1", "norm2", "norm3"):
+            out[p + n + ".weight"] = (dim,)
+            out[p + n + ".bias"] = (dim,)
+    return out
+
+
 def reference_shapes(name: str) -> Dict[str, tuple]:
     """Parameter shapes of a named reference network (oracle/param_shapes.json, written by
     make_golden.py from the reference modules themselves)."""

@@ -414,6 +414,33 @@ def test_ccdm_text_cross_attention_3d_vs_oracle():
     assert np.array_equal(got, got2)
 
 
+def test_text_context_encoder_vs_reference():
+    """ccdm.encoder.PreloadedBERTEncoder against the unmodified reference module's outputs: small instance in
+    full, shipped size (768 wide, 8 x 64 heads, depth 4, 512 tokens) sub-sampled.  bf16 blocks vs fp32 reference."""
+    from jointimagegeneration_b200.ccdm.encoder import PreloadedBERTEncoder
+    from oracle import weights
+    g = golden("ccdm_text_encoder")
+    for tag in ("small", "full"):
+        dim, heads, d_head, depth, B, L, sub = (int(v) for v in g[tag + "_cfg"])
+        m = PreloadedBERTEncoder(embed_dim=dim, n_heads=heads, depth=depth, d_head=d_head)
+        assert weights.shapes_of(m) == weights.encoder_shapes(dim, heads, d_head, depth)
+        m.load_state_dict(weights.synth_state_dict(weights.shapes_of(m), int(g["seed_w"])))
+        m = m.cuda().eval()
+        x = weights.normal(41, (B, dim, L)).cuda()
+        y = m(x)
+        assert y.shape == x.shape and y.dtype == x.dtype
+        got, want = y[:, ::sub, ::sub].cpu().numpy(), g[tag + "_out"]
+        # compare what the blocks add (the output is dominated by the identity term)
+        xin = x[:, ::sub, ::sub].cpu().numpy()
+        r = rel(got - xin, want - xin)
+        print(f"text encoder {tag}: rel err of the residual branch {r:.4f}")
+        assert r <= 3e-2, (tag, r)
+        y2 = m(x)                      # second call reuses the plan
+        assert torch.equal(y, y2)
+    with pytest.raises(RuntimeError):
+        PreloadedBERTEncoder(embed_dim=128, n_heads=2, depth=1, d_head=64)(torch.zeros(1, 128, 8))
+
+
 @pytest.mark.slow
 def test_ldm_pixel_config_forward_vs_oracle():
     """BASELINE config 4 network (ruijin-ldm_from_controlnet.yaml: pixel-space, in 3 / out 1, mc 128,
