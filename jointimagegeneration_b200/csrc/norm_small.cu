@@ -66,27 +66,42 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const gg_gn_finalize_a
     const int cpg = C / a.groups;
     const int g = blockIdx.x, n = blockIdx.y;
     double s = 0.0, ss = 0.0;
-    // channels of this group may live in either source
-    for (int cc = 0; cc < cpg; ++cc) {
-        const int c = g * cpg + cc;
-        const float* part; int Cs, nch, cl;
-        if (c < a.C1) { part = a.partial1; Cs = a.C1; nch = a.nchunks1; cl = c; }
-        else { part = a.partial2; Cs = a.C2; nch = a.nchunks2; cl = c - a.C1; }
-        const float* p = part + ((int64_t)n * nch) * 2 * Cs + 2 * cl;
-        // rows are a few hundred to a few thousand (one per CTA x warp of the producing conv): issue the loads of
-        // eight rows before the dependent fp64 adds (the summation order per thread is unchanged)
-        int k = threadIdx.x;
-        for (; k + 7 * 128 < nch; k += 8 * 128) {
-            float2 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float2*>(p + (int64_t)(k + u * 128) * 2 * Cs));
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { s += (double)v[u].x; ss += (double)v[u].y; }
+    // One flat index space over (partial row, channel of the group): 128 threads stride over it with four independent
+    // loads in flight, instead of walking the group's channels one after the other (a launch used to cost cpg
+    // dependent load latencies, ~13 us for the LDM widths).  Channels of the group may live in either source; the
+    // summation order per thread is fixed, so results stay reproducible.
+    const int c0 = g * cpg;
+    auto load = [&](int e) -> float2 {
+        int c, k;
+        if (c0 + cpg <= a.C1 || c0 >= a.C1) {       // the whole group sits in one source (always true when C1 % cpg == 0)
+            const bool first = c0 < a.C1;
+            const int nch = first ? a.nchunks1 : a.nchunks2, Cs = first ? a.C1 : a.C2;
+            k = e / cpg; c = e - k * cpg;
+            if (k >= nch) return make_float2(0.f, 0.f);
+            const float* part = first ? a.partial1 : a.partial2;
+            return __ldg(reinterpret_cast<const float2*>(part + (((int64_t)n * nch + k) * Cs + (c0 - (first ? 0 : a.C1) + c)) * 2));
         }
-        for (; k < nch; k += 128) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(p + (int64_t)k * 2 * Cs));
-            s += (double)v.x; ss += (double)v.y;
-        }
+        // group straddles the two sources: channel-major walk over max(nchunks) rows
+        const int nmax = max(a.nchunks1, a.nchunks2);
+        c = e / nmax; k = e - c * nmax;
+        const int ch = c0 + c;
+        const bool first = ch < a.C1;
+        const int nch = first ? a.nchunks1 : a.nchunks2, Cs = first ? a.C1 : a.C2;
+        if (k >= nch) return make_float2(0.f, 0.f);
+        const float* part = first ? a.partial1 : a.partial2;
+        return __ldg(reinterpret_cast<const float2*>(part + (((int64_t)n * nch + k) * Cs + (ch - (first ? 0 : a.C1))) * 2));
+    };
+    const bool one_src = (c0 + cpg <= a.C1 || c0 >= a.C1);
+    const int total = cpg * (one_src ? (c0 < a.C1 ? a.nchunks1 : a.nchunks2) : max(a.nchunks1, a.nchunks2));
+    int e = threadIdx.x;
+    for (; e + 3 * 128 < total; e += 4 * 128) {
+        const float2 v0 = load(e), v1 = load(e + 128), v2 = load(e + 256), v3 = load(e + 384);
+        s += (double)v0.x; ss += (double)v0.y; s += (double)v1.x; ss += (double)v1.y;
+        s += (double)v2.x; ss += (double)v2.y; s += (double)v3.x; ss += (double)v3.y;
+    }
+    for (; e < total; e += 128) {
+        const float2 v = load(e);
+        s += (double)v.x; ss += (double)v.y;
     }
     __shared__ double sh[2][4];
 #pragma unroll
