@@ -359,6 +359,14 @@ int gg_layernorm(const void* x, const float* gamma, const float* beta, void* y, 
 /* y[r, j] = x[r, j] * gelu(x[r, inner + j])  (exact erf GELU), bf16 */
 int gg_geglu(const void* x, void* y, int64_t rows, int32_t inner, gg_stream_t stream);
 
+/* Single-head full-channel attention of the VAE (latentdiffusion/ldm/modules/diffusionmodules/model.py:237-261
+ * AttnBlock2d.forward): the score matrix comes from gg_conv_fwd (queries as the activation, keys as the "weights",
+ * fp32 out), then  P = softmax(scale * S) over each row (:250-251), bf16 out, and the values are transposed so that
+ * the second product is again a gg_conv_fwd (P as activation, V^T as weights, :254-256).
+ * gg_softmax_rows: x fp32 [rows, n] -> y bf16 [rows, n].   gg_transpose_bf16: x [R, C] -> y [C, R], bf16. */
+int gg_softmax_rows(const float* x, void* y, int64_t rows, int32_t n, float scale, gg_stream_t stream);
+int gg_transpose_bf16(const void* x, void* y, int32_t R, int32_t C, gg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

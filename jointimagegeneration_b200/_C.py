@@ -136,6 +136,8 @@ SYMBOLS = {
     "gg_small_linear": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "gg_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
     "gg_geglu": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "gg_softmax_rows": (C.c_int, [_vp, _vp, _i64, _i32, _f32, _vp]),
+    "gg_transpose_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
 }
 
 

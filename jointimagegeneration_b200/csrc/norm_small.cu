@@ -400,6 +400,88 @@ extern "C" int gg_layernorm(const void* x, const float* gamma, const float* beta
     return launch_result();
 }
 
+// row softmax of scale * x (fp32 in, bf16 out): one 256-thread block per row, the row held in registers
+// (n <= 256 * 4 * SM_MAXV), max and sum by warp shuffles + one smem exchange
+constexpr int SM_MAXV = 8;      // float4 per thread -> n <= 8192
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, float scale) {
+    const float* xr = x + (int64_t)blockIdx.x * n;
+    __nv_bfloat16* yr = y + (int64_t)blockIdx.x * n;
+    __shared__ float red[2][8];
+    float4 v[SM_MAXV];
+    const int nv = n >> 2;
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+        const int j = threadIdx.x + i * 256;
+        if (j < nv) {
+            v[i] = ldg_nc_f4(xr + 4 * j);
+            v[i].x *= scale; v[i].y *= scale; v[i].z *= scale; v[i].w *= scale;
+            m = fmaxf(fmaxf(fmaxf(m, v[i].x), fmaxf(v[i].y, v[i].z)), v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0][0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[0][i]);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+        const int j = threadIdx.x + i * 256;
+        if (j < nv) {
+            v[i].x = __expf(v[i].x - m); v[i].y = __expf(v[i].y - m); v[i].z = __expf(v[i].z - m); v[i].w = __expf(v[i].w - m);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[1][i];
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+        const int j = threadIdx.x + i * 256;
+        if (j < nv) *reinterpret_cast<uint2*>(yr + 4 * j) = make_uint2(pack_bf16(v[i].x * inv, v[i].y * inv), pack_bf16(v[i].z * inv, v[i].w * inv));
+    }
+}
+
+// bf16 [R, C] -> [C, R] through a padded 64 x 64 shared-memory tile
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int R, int C) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        tile[r][c] = (r0 + r < R && c0 + c < C) ? x[(int64_t)(r0 + r) * C + c0 + c] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int c = i >> 6, r = i & 63;
+        if (c0 + c < C && r0 + r < R) y[(int64_t)(c0 + c) * R + r0 + r] = tile[r][c];
+    }
+}
+
+extern "C" int gg_softmax_rows(const float* x, void* y, int64_t rows, int32_t n, float scale, gg_stream_t stream) {
+    GG_REQUIRE(x && y && rows > 0 && n > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE(n % 4 == 0 && n <= 256 * 4 * SM_MAXV && rows <= 0x7fffffffll, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(aligned(x, 16) && aligned(y, 8), GG_ERR_ALIGNMENT);
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, scale);
+    return launch_result();
+}
+
+extern "C" int gg_transpose_bf16(const void* x, void* y, int32_t R, int32_t C, gg_stream_t stream) {
+    GG_REQUIRE(x && y && R > 0 && C > 0, GG_ERR_BAD_ARG);
+    GG_REQUIRE((R + 63) / 64 <= 65535, GG_ERR_UNSUPPORTED);
+    const dim3 grid((unsigned)((C + 63) / 64), (unsigned)((R + 63) / 64));
+    transpose_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                             reinterpret_cast<__nv_bfloat16*>(y), R, C);
+    return launch_result();
+}
+
 extern "C" int gg_geglu(const void* x, void* y, int64_t rows, int32_t inner, gg_stream_t stream) {
     GG_REQUIRE(x && y && rows > 0 && inner > 0, GG_ERR_BAD_ARG);
     GG_REQUIRE(inner % 8 == 0, GG_ERR_UNSUPPORTED);

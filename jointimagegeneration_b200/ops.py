@@ -421,3 +421,23 @@ def geglu(x, out=None):
         out = torch.empty(tuple(x.shape[:-1]) + (inner,), dtype=torch.bfloat16, device=x.device)
     _C.check(_C.lib().gg_geglu(_C.ptr(x), _C.ptr(out), rows, inner, _C.stream()), "gg_geglu")
     return out
+
+
+def softmax_rows(x, scale=1.0, out=None):
+    """softmax(scale * x) over the last axis: fp32 [rows, n] -> bf16 (AttnBlock2d, model.py:250-251)."""
+    _chk(x, torch.float32)
+    rows, n = x.numel() // x.shape[-1], x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _C.check(_C.lib().gg_softmax_rows(_C.ptr(x), _C.ptr(out), rows, n, float(scale), _C.stream()), "gg_softmax_rows")
+    return out
+
+
+def transpose_bf16(x, out=None):
+    """bf16 [R, C] -> [C, R]."""
+    _chk(x, torch.bfloat16)
+    R, Cc = x.shape
+    if out is None:
+        out = torch.empty((Cc, R), dtype=torch.bfloat16, device=x.device)
+    _C.check(_C.lib().gg_transpose_bf16(_C.ptr(x), _C.ptr(out), R, Cc, _C.stream()), "gg_transpose_bf16")
+    return out

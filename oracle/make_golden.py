@@ -212,6 +212,32 @@ def ldm_plms(name, params, B, hw, S, seed_w=11):
 
 
 @torch.no_grad()
+def vae_decoder(name="vae_decoder", seed_w=19):
+    """Decoder of the unmodified reference (ldm/modules/diffusionmodules/model.py:524-631) behind a 1x1
+    post_quant_conv (AutoencoderKL.decode, autoencoder.py:355-359; AutoencoderKL itself needs taming / lightning and
+    cannot be imported here): a narrow instance in full and the shipped widths (ch 128, mult 1-2-4-4) sub-sampled."""
+    import importlib
+    refshim.ldm()
+    mdl = importlib.import_module("ldm.modules.diffusionmodules.model")
+    out = {}
+    for tag, (ch, zhw, sub) in (("small", (32, 16, 1)), ("wide", (128, 16, 4))):
+        dd = dict(ch=ch, out_ch=1, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0, in_channels=1,
+                  resolution=zhw * 8, z_channels=4, double_z=True, dims=2)
+        dec = mdl.Decoder(**dd).eval()
+        sd = weights.synth_state_dict({"decoder." + k: v for k, v in weights.shapes_of(dec).items()}, seed_w)
+        sd["post_quant_conv.weight"] = weights.synth_tensor("post_quant_conv.weight", (4, 4, 1, 1), seed_w)
+        sd["post_quant_conv.bias"] = weights.synth_tensor("post_quant_conv.bias", (4,), seed_w)
+        dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
+        z = weights.normal(51, (2, 4, zhw, zhw))
+        y = dec(torch.nn.functional.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"]))
+        out[tag + "_cfg"] = np.asarray([ch, zhw, sub])
+        out[tag + "_out"] = y[:, :, ::sub, ::sub].numpy()
+        out[tag + "_std"] = float(y.std())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed_w=seed_w, **out)
+    print(name, {k: v for k, v in out.items() if k.endswith("_std")})
+
+
+@torch.no_grad()
 def text_encoder(name="ccdm_text_encoder", seed_w=17):
     """PreloadedBERTEncoder of the unmodified reference (ccdm/ddpm/models/encoder.py:103-123): a small instance in full
     and the shipped size (768 wide, 8 heads x 64, depth 4, 512 tokens) sub-sampled."""
@@ -302,6 +328,8 @@ def main(argv):
         ldm_ddim("ldm_tiny_eta0", configs.LDM_TINY, B=2, hw=(16, 16), S=5, eta=0.0)
         ldm_ddim("ldm_tiny_eta05", configs.LDM_TINY, B=2, hw=(16, 16), S=5, eta=0.5)
         ldm_ddim("ldm_tiny_hybrid", configs.LDM_TINY_XATTN, B=2, hw=(16, 16), S=4, eta=0.0, hybrid=True)
+    if want("vae_decoder"):
+        vae_decoder()
     if want("text_encoder"):
         text_encoder()
     if want("ldm_plms"):

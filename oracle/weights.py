@@ -79,6 +79,47 @@ def encoder_shapes(dim: int, heads: int, d_head: int, depth: int) -> Dict[str, t
     return out
 
 
+def vae_decoder_shapes(ch: int, ch_mult=(1, 2, 4, 4), num_res_blocks: int = 2, z_channels: int = 4, out_ch: int = 1, embed_dim: int = 4,
+                       prefix: str = "decoder.") -> Dict[str, tuple]:
+    """Parameter names / shapes of AutoencoderKL's decode half (model.py:524-596 Decoder with attn_resolutions = [], plus
+    autoencoder.py:318 post_quant_conv).  Checked against the reference Decoder when it is importable."""
+    out: Dict[str, tuple] = {}
+
+    def conv(p, ci, co, k):
+        out[p + ".weight"] = (co, ci, k, k)
+        out[p + ".bias"] = (co,)
+
+    def norm(p, c):
+        out[p + ".weight"] = (c,)
+        out[p + ".bias"] = (c,)
+
+    def res(p, ci, co):
+        norm(p + ".norm1", ci), conv(p + ".conv1", ci, co, 3), norm(p + ".norm2", co), conv(p + ".conv2", co, co, 3)
+        if ci != co:
+            conv(p + ".nin_shortcut", ci, co, 1)
+
+    nres = len(ch_mult)
+    block_in = ch * ch_mult[-1]
+    conv(prefix + "conv_in", z_channels, block_in, 3)
+    res(prefix + "mid.block_1", block_in, block_in)
+    norm(prefix + "mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(prefix + "mid.attn_1." + n, block_in, block_in, 1)
+    res(prefix + "mid.block_2", block_in, block_in)
+    for i_level in reversed(range(nres)):
+        block_out = ch * ch_mult[i_level]
+        for i_block in range(num_res_blocks + 1):
+            res(prefix + f"up.{i_level}.block.{i_block}", block_in, block_out)
+            block_in = block_out
+        if i_level != 0:
+            conv(prefix + f"up.{i_level}.upsample.conv", block_in, block_in, 3)
+    norm(prefix + "norm_out", block_in)
+    conv(prefix + "conv_out", block_in, out_ch, 3)
+    if embed_dim:
+        conv("post_quant_conv", embed_dim, z_channels, 1)
+    return out
+
+
 def reference_shapes(name: str) -> Dict[str, tuple]:
     """Parameter shapes of a named reference network (oracle/param_shapes.json, written by
     make_golden.py from the reference modules themselves)."""

@@ -502,3 +502,19 @@ def test_cat_step_cl_fast_path_distribution_and_slab_invariance(ops):
     assert torch.equal(out3, out[half:])
     ops.cat_step_cl(logits, lab_in, coef, out2, 1, V, C, seed=3, offset=18)
     assert not torch.equal(out, out2)
+
+
+def test_softmax_rows_and_transpose(ops):
+    """gg_softmax_rows / gg_transpose_bf16 (the VAE's single-head attention, model.py:250-256) vs torch."""
+    no_tf32()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for rows, n in ((5, 64), (300, 4096), (7, 8192), (33, 260)):
+        x = torch.randn((rows, n), device="cuda", generator=g) * 6.0
+        y = ops.softmax_rows(x, scale=0.37)
+        want = torch.softmax(x * 0.37, -1)
+        assert y.dtype == torch.bfloat16 and y.shape == x.shape
+        assert float((y.float() - want).abs().max()) <= 2.0 ** -8 * float(want.max()) + 1e-6       # bf16 output rounding
+        assert float((y.float().sum(-1) - 1).abs().max()) <= 2e-2
+    for R, Cc in ((4096, 512), (100, 72), (64, 64), (1, 8)):
+        a = torch.randn((R, Cc), device="cuda", generator=g).to(torch.bfloat16)
+        assert torch.equal(ops.transpose_bf16(a), a.t().contiguous())

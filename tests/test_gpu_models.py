@@ -414,6 +414,32 @@ def test_ccdm_text_cross_attention_3d_vs_oracle():
     assert np.array_equal(got, got2)
 
 
+def test_vae_decode_vs_reference():
+    """ldm.autoencoder.AutoencoderKL.decode (decode half) against the unmodified reference Decoder behind a 1x1
+    post_quant_conv: narrow instance in full, shipped widths (ch 128: 512-wide single-head attention over 256 tokens)
+    sub-sampled.  bf16 network vs fp32 reference."""
+    from jointimagegeneration_b200.ldm.autoencoder import AutoencoderKL
+    from oracle import weights
+    g = golden("vae_decoder")
+    for tag in ("small", "wide"):
+        ch, zhw, sub = (int(v) for v in g[tag + "_cfg"])
+        dd = dict(ch=ch, out_ch=1, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0, in_channels=1,
+                  resolution=zhw * 8, z_channels=4, double_z=True, dims=2)
+        ae = AutoencoderKL(dd, 4)
+        assert weights.shapes_of(ae) == weights.vae_decoder_shapes(ch)
+        ae.load_state_dict(weights.synth_state_dict(weights.shapes_of(ae), int(g["seed_w"])))
+        ae = ae.cuda().eval()
+        z = weights.normal(51, (2, 4, zhw, zhw)).cuda()
+        y = ae.decode(z)
+        assert y.shape == (2, 1, zhw * 8, zhw * 8) and y.dtype == torch.float32
+        got, want = y[:, :, ::sub, ::sub].cpu().numpy(), g[tag + "_out"]
+        print(f"vae decode {tag}: rel err {rel(got, want):.4f}  PSNR {psnr(got, want):.1f} dB")
+        assert rel(got, want) <= 3e-2 and psnr(got, want) >= 35.0, (tag, rel(got, want))
+        assert torch.equal(y, ae.decode(z))
+    with pytest.raises(NotImplementedError):
+        ae.encode(z)
+
+
 def test_text_context_encoder_vs_reference():
     """ccdm.encoder.PreloadedBERTEncoder against the unmodified reference module's outputs: small instance in
     full, shipped size (768 wide, 8 x 64 heads, depth 4, 512 tokens) sub-sampled.  bf16 blocks vs fp32 reference."""
