@@ -30,7 +30,7 @@ struct ConvSeg {
     int nchunks;   // 64-channel chunks
     int kd, kh, kw;  // tap counts
     int od, oh, ow;  // offset of tap 0 (input coordinate = output coordinate + o + tap)
-    int stride2;   // 1: tap -> parity map (map0 + parity code) and offset {-1, 0, 0}
+    int stride2;   // 1: tap -> parity map (map0 + parity code) and offset floor((k + off) / 2)
     int s2d, s2h, s2w;  // which dims are strided (dims < 3 leave d (and h) unstrided)
     int dshift;    // extra depth offset of this source (halo-padded depth slabs)
 };
@@ -121,13 +121,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
                         for (int c = 0; c < sg.kw; ++c) {
                             int mi = sg.map0, od, oh, ow;
                             if (sg.stride2) {
-                                // input = 2*o + k - 1: k=0 -> odd grid at o-1, k=1 -> even grid at o, k=2 -> odd grid at o
-                                const int pd = sg.s2d ? ((a + 1) & 1) : 0, ph = sg.s2h ? ((b + 1) & 1) : 0,
-                                          pw = sg.s2w ? ((c + 1) & 1) : 0;
+                                // input = 2*o + (k + off), off = -1 (pad 1) or 0 (pad (0, 1)): parity grid (k + off) & 1 at
+                                // o + floor((k + off) / 2); e.g. off -1: k=0 -> odd grid at o-1, k=1 -> even at o, k=2 -> odd at o
+                                const int pd = sg.s2d ? ((a + sg.od) & 1) : 0, ph = sg.s2h ? ((b + sg.oh) & 1) : 0,
+                                          pw = sg.s2w ? ((c + sg.ow) & 1) : 0;
                                 mi += pd * 4 + ph * 2 + pw;
-                                od = sg.s2d ? (a == 0 ? -1 : 0) : sg.od + a;
-                                oh = sg.s2h ? (b == 0 ? -1 : 0) : sg.oh + b;
-                                ow = sg.s2w ? (c == 0 ? -1 : 0) : sg.ow + c;
+                                od = sg.s2d ? ((a + sg.od) >> 1) : sg.od + a;
+                                oh = sg.s2h ? ((b + sg.oh) >> 1) : sg.oh + b;
+                                ow = sg.s2w ? ((c + sg.ow) >> 1) : sg.ow + c;
                             } else {
                                 od = sg.od + a; oh = sg.oh + b; ow = sg.ow + c;
                             }
@@ -582,13 +583,14 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
             }
             nmaps += 1;
         } else {
-            // stride 2, 3-tap (pad 1) in every strided dim: 8 parity sub-grids
+            // stride 2, 3-tap in every strided dim: 8 parity sub-grids
             GG_REQUIRE(nmaps + 8 <= MAX_MAPS, GG_ERR_UNSUPPORTED);
             sg.stride2 = 1;
             sg.s2w = 1; sg.s2h = a->dims >= 2; sg.s2d = a->dims >= 3;
-            GG_REQUIRE(a->kw == 3 && a->ow == -1, GG_ERR_UNSUPPORTED);
-            if (sg.s2h) GG_REQUIRE(a->kh == 3 && a->oh == -1, GG_ERR_UNSUPPORTED);
-            if (sg.s2d) GG_REQUIRE(a->kd == 3 && a->od == -1, GG_ERR_UNSUPPORTED);
+            // tap offset -1 = symmetric pad 1 (unet.py:135-139); 0 = the VAE's pad (0, 1) before a pad-0 conv (model.py:75-78)
+            GG_REQUIRE(a->kw == 3 && (a->ow == -1 || a->ow == 0), GG_ERR_UNSUPPORTED);
+            if (sg.s2h) GG_REQUIRE(a->kh == 3 && (a->oh == -1 || a->oh == 0), GG_ERR_UNSUPPORTED);
+            if (sg.s2d) GG_REQUIRE(a->kd == 3 && (a->od == -1 || a->od == 0), GG_ERR_UNSUPPORTED);
             sg.kd = a->kd; sg.kh = a->kh; sg.kw = a->kw;
             sg.od = a->od; sg.oh = a->oh; sg.ow = a->ow;
             for (int code = 0; code < 8; ++code) {

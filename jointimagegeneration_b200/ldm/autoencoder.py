@@ -1,4 +1,4 @@
-"""Decode side of the first-stage autoencoder: drop-in for
+"""First-stage autoencoder at inference: drop-in for
 ``latentdiffusion/ldm/modules/diffusionmodules/model.py::Decoder`` (:524-631) and for
 ``AutoencoderKL.decode`` (``ldm/models/autoencoder.py:355-359``: ``post_quant_conv`` then the decoder), i.e. what
 ``decode_first_stage`` (``ddpm.py:717-776``) runs on every generated slice of the ``_ae`` configuration.
@@ -16,8 +16,9 @@ sm_100a kernels as the denoiser:
   (``gg_transpose_bf16``) so that the second product is the same GEMM kernel;
 * ``norm_out`` + swish + ``conv_out`` (:621-626).
 
-The encoder half (``AutoencoderKL.encode``, the posterior) is not on this path and raises NotImplementedError.
-There is no CPU / PyTorch fallback.
+``Encoder`` (:398-520) mirrors it: ``Downsample`` (:61-80, zero pad (0, 1, 0, 1) + pad-0 stride-2 conv) is the stride-2 conv
+kernel with tap offset 0; ``AutoencoderKL.encode`` returns the reference's ``DiagonalGaussianDistribution`` (mean / logvar /
+``mode()`` / ``sample()``) of ``quant_conv(encoder(x))``.  There is no CPU / PyTorch fallback.
 """
 import math
 from typing import Dict, Optional
@@ -70,7 +71,178 @@ class Upsample(nn.Module):
             self.conv = ParamConv(dims, in_channels, in_channels, 3, padding=1)
 
 
-class Decoder(nn.Module):
+class Downsample(nn.Module):
+    """model.py:61-80: zero pad (0, 1, 0, 1), then a 3x3 stride-2 conv without padding."""
+
+    def __init__(self, in_channels, with_conv, dims=2):
+        super().__init__()
+        if not with_conv:
+            raise NotImplementedError("avg_pool2d downsampling (resamp_with_conv=False) is not used by the shipped config")
+        self.with_conv, self.dims, self.in_channels = with_conv, dims, in_channels
+        self.conv = ParamConv(dims, in_channels, in_channels, 3, stride=2, padding=0)
+
+
+class _Planned(nn.Module):
+    """Shared plumbing of Encoder / Decoder: one engine, one plan per input shape, weights re-packed after a load / move."""
+
+    def _init_plumbing(self):
+        self._engine: Optional[UNetEngine] = None
+        self._plans: Dict[tuple, Plan] = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self):
+        self._engine = None
+        self._plans.clear()
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self.invalidate()
+        return r
+
+    def _eng(self) -> UNetEngine:
+        if self._engine is None:
+            self._engine = UNetEngine(self, 2, 1, -1)
+        self._engine.lib = _C.lib()
+        return self._engine
+
+
+class Encoder(_Planned):
+    """model.py:398-520.  ``post`` (AutoencoderKL.quant_conv, 1x1) is planned behind conv_out when set."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0, resamp_with_conv=True,
+                 in_channels, resolution, z_channels, double_z=True, use_linear_attn=False, attn_type="vanilla", dims=2,
+                 **ignore_kwargs):
+        super().__init__()
+        if dims != 2 or use_linear_attn or attn_type != "vanilla":
+            raise NotImplementedError("only the shipped 2-D vanilla-attention encoder is implemented")
+        self.ch, self.num_resolutions, self.num_res_blocks = ch, len(ch_mult), num_res_blocks
+        self.resolution, self.in_channels = resolution, in_channels
+        self.conv_in = ParamConv(2, in_channels, ch, 3, padding=1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block, attn = nn.ModuleList(), nn.ModuleList()
+            block_in, block_out = ch * in_ch_mult[i_level], ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(AttnBlock2d(block_in))
+            down = nn.Module()
+            down.block, down.attn = block, attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in)
+        self.mid.attn_1 = AttnBlock2d(block_in)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in)
+        self.norm_out = ParamNorm(block_in, eps=1e-6, groups=32)
+        self.out_channels = 2 * z_channels if double_z else z_channels
+        self.conv_out = ParamConv(2, block_in, self.out_channels, 3, padding=1)
+        self.post: Optional[ParamConv] = None
+        self._init_plumbing()
+
+    def _build_plan(self, N: int, hw) -> Plan:
+        eng = self._eng()
+        dev = next(self.parameters()).device
+        plan, ar = Plan(), _Arena(dev)
+        cpad = (self.in_channels + 7) // 8 * 8
+        x_in = torch.zeros((N, 1, hw[0], hw[1], cpad), dtype=torch.bfloat16, device=dev)
+        plan.inputs["x"] = x_in
+        plan.keep.append(x_in)
+        ci = self.conv_in
+        bi = eng._vec8((id(ci.bias), "b"), lambda: ci.bias, ci.out_channels)
+        h = eng._conv(plan, ar, [(Act(x_in), False)], eng._packer(ci, [cpad]), ci.out_channels, dims=2, bias=_C.ptr(bi), stats=True)
+        for i_level in range(self.num_resolutions):
+            dn = self.down[i_level]
+            for i_block in range(self.num_res_blocks):
+                nxt = Decoder._resnet(self, eng, plan, ar, dn.block[i_block], h)
+                eng._free(ar, h)
+                h = nxt
+                if len(dn.attn) > 0:
+                    nxt = Decoder._attn(self, eng, plan, ar, dn.attn[i_block], h)
+                    eng._free(ar, h)
+                    h = nxt
+            if i_level != self.num_resolutions - 1:
+                dc = dn.downsample.conv
+                bd = eng._vec8((id(dc.bias), "b"), lambda dc=dc: dc.bias, dc.out_channels)
+                Ho, Wo = (h.sp[1] + 1 - 3) // 2 + 1, (h.sp[2] + 1 - 3) // 2 + 1
+                # pad (0, 1, 0, 1) + pad-0 stride-2 conv == stride-2 conv whose taps start at offset 0 (right / bottom
+                # zeros come from the TMA out-of-bounds fill)
+                nxt = eng._conv(plan, ar, [(h, False)], eng._pack(dc, [h.C]), dc.out_channels, dims=2, stride=2, bias=_C.ptr(bd),
+                                offsets=(0, 0, 0), out_spatial=(1, Ho, Wo), stats=True)
+                eng._free(ar, h)
+                h = nxt
+        for blk in (self.mid.block_1, self.mid.attn_1, self.mid.block_2):
+            nxt = (Decoder._resnet(self, eng, plan, ar, blk, h) if isinstance(blk, ResnetBlock)
+                   else Decoder._attn(self, eng, plan, ar, blk, h))
+            eng._free(ar, h)
+            h = nxt
+        co = self.conv_out
+        bo = eng._vec8((id(co.bias), "b"), lambda: co.bias, co.out_channels)
+        last = self.post is None
+        y = eng._gn_conv(plan, ar, h, None, self.norm_out, True, lambda splits: eng._packer(co, splits), co.out_channels, dims=2,
+                         bias=_C.ptr(bo), f32_out=last)
+        eng._free(ar, h)
+        if not last:       # AutoencoderKL.encode: moments = quant_conv(h)
+            pq = self.post
+            w = pq.weight.detach().reshape(pq.out_channels, pq.in_channels)
+            wpad = torch.zeros((pq.out_channels, y.C), dtype=w.dtype, device=dev)
+            wpad[:, :pq.in_channels] = w
+            plan.keep.append(wpad)
+            bq = eng._vec8((id(pq.bias), "b"), lambda: pq.bias, pq.out_channels)
+            wp = eng._cached((id(pq.weight), "pq"), lambda: ops.pack_conv_weight(wpad.reshape(pq.out_channels, -1, 1), [y.C]))
+            m = eng._conv(plan, ar, [(y, False)], wp, pq.out_channels, dims=3, ksize=1, bias=_C.ptr(bq), f32_out=True)
+            eng._free(ar, y)
+            y = m
+        plan.outputs["y"] = y.interior
+        plan.keep.append(ar.stores)
+        plan.arena_bytes = ar.total
+        return plan
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """model.py:493-520.  x fp32 [N, in_channels, H, W] -> fp32 [N, 2 z_channels, H / 2^(levels-1), W / 2^(levels-1)]."""
+        if not x.is_cuda:
+            raise RuntimeError("the encoder runs on the sm_100a library only (no CPU fallback)")
+        N, hw = x.shape[0], tuple(x.shape[2:])
+        key = (N, hw)
+        if key not in self._plans:
+            self._eng()
+            self._plans[key] = self._build_plan(N, hw)
+        plan = self._plans[key]
+        ops.nchw_to_cl(x.float().contiguous(), None, c_pad=plan.inputs["x"].shape[-1], out=plan.inputs["x"])
+        plan.run()
+        f = 2 ** (self.num_resolutions - 1)
+        cout = self.post.out_channels if self.post is not None else self.out_channels
+        return ops.cl_to_nchw(plan.outputs["y"], cout, (hw[0] // f, hw[1] // f), softmax=False)
+
+
+class DiagonalGaussianDistribution(object):
+    """ldm/modules/distributions/distributions.py:24-62 (the members sampling uses; tensors of a few thousand elements)."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if self.deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self):
+        return self.mean + self.std * torch.randn(self.mean.shape, device=self.parameters.device)
+
+    def mode(self):
+        return self.mean
+
+
+class Decoder(_Planned):
     def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0, resamp_with_conv=True,
                  in_channels, resolution, z_channels, give_pre_end=False, tanh_out=False, use_linear_attn=False,
                  attn_type="vanilla", dims=2, **ignorekwargs):
@@ -104,20 +276,8 @@ class Decoder(nn.Module):
             self.up.insert(0, up)        # prepend to get consistent order (:592)
         self.norm_out = ParamNorm(block_in, eps=1e-6, groups=32)
         self.conv_out = ParamConv(2, block_in, out_ch, 3, padding=1)
-        self._engine: Optional[UNetEngine] = None
-        self._plans: Dict[tuple, Plan] = {}
         self.pre: Optional[ParamConv] = None          # AutoencoderKL.post_quant_conv, planned in front of conv_in
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
-
-    # ------------------------------------------------------------------------------------
-    def invalidate(self):
-        self._engine = None
-        self._plans.clear()
-
-    def _apply(self, fn, *a, **k):
-        r = super()._apply(fn, *a, **k)
-        self.invalidate()
-        return r
+        self._init_plumbing()
 
     # ------------------------------------------------------------------------------------ planning
     def _resnet(self, eng: UNetEngine, plan, ar, rb: ResnetBlock, x: Act) -> Act:
@@ -174,8 +334,7 @@ class Decoder(nn.Module):
         return out
 
     def _build_plan(self, N: int, hw) -> Plan:
-        eng = self._engine
-        eng.lib = _C.lib()
+        eng = self._eng()
         dev = next(self.parameters()).device
         plan, ar = Plan(), _Arena(dev)
         zc = self.pre.in_channels if self.pre is not None else self.z_channels
@@ -238,8 +397,6 @@ class Decoder(nn.Module):
             raise RuntimeError("the decoder runs on the sm_100a library only (no CPU fallback)")
         self.last_z_shape = z.shape
         N, hw = z.shape[0], tuple(z.shape[2:])
-        if self._engine is None:
-            self._engine = UNetEngine(self, 2, 1, -1)
         key = (N, hw)
         if key not in self._plans:
             self._plans[key] = self._build_plan(N, hw)
@@ -251,7 +408,8 @@ class Decoder(nn.Module):
 
 
 class AutoencoderKL(nn.Module):
-    """Decode half of ldm/models/autoencoder.py::AutoencoderKL (:304-371): ``decode(z)`` = ``decoder(post_quant_conv(z))``.
+    """Inference surface of ldm/models/autoencoder.py::AutoencoderKL (:304-371): ``encode(x)`` = posterior of
+    ``quant_conv(encoder(x))`` (:350-354), ``decode(z)`` = ``decoder(post_quant_conv(z))`` (:355-359).
     Constructor arguments other than ``ddconfig`` / ``embed_dim`` are accepted and ignored (losses, checkpoints, keys)."""
 
     def __init__(self, ddconfig, embed_dim, lossconfig=None, ckpt_path=None, ignore_keys=(), image_key="image", colorize_nlabels=None,
@@ -259,17 +417,23 @@ class AutoencoderKL(nn.Module):
         super().__init__()
         assert ddconfig["double_z"]
         self.embed_dim = embed_dim
+        self.encoder = Encoder(**ddconfig)
         self.decoder = Decoder(**ddconfig)
+        self.quant_conv = ParamConv(2, 2 * ddconfig["z_channels"], 2 * embed_dim, 1)
         self.post_quant_conv = ParamConv(2, embed_dim, ddconfig["z_channels"], 1)
-        self.decoder.pre = None
 
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
-        self.decoder.invalidate()
+        self.encoder.invalidate(), self.decoder.invalidate()
         return r
 
+    @torch.no_grad()
     def encode(self, x):
-        raise NotImplementedError("the encoder half (posterior of the conditioning slices) is outside this path (SURVEY.md N1)")
+        # the 1x1 quant_conv is planned behind conv_out (object.__setattr__: not a second registration)
+        if self.encoder.post is None:
+            object.__setattr__(self.encoder, "post", self.quant_conv)
+            self.encoder.invalidate()
+        return DiagonalGaussianDistribution(self.encoder(x))
 
     @torch.no_grad()
     def decode(self, z):

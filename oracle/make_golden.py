@@ -238,6 +238,31 @@ def vae_decoder(name="vae_decoder", seed_w=19):
 
 
 @torch.no_grad()
+def vae_encoder(name="vae_encoder", seed_w=23):
+    """Encoder of the unmodified reference (model.py:398-520) followed by a 1x1 quant_conv (AutoencoderKL.encode,
+    autoencoder.py:350-352): the posterior's moments; narrow instance and the shipped widths (ch 128) on a 128 x 128 slice."""
+    import importlib
+    refshim.ldm()
+    mdl = importlib.import_module("ldm.modules.diffusionmodules.model")
+    out = {}
+    for tag, (ch, hw) in (("small", (32, 128)), ("wide", (128, 128))):
+        dd = dict(ch=ch, out_ch=1, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0, in_channels=1,
+                  resolution=hw, z_channels=4, double_z=True, dims=2)
+        enc = mdl.Encoder(**dd).eval()
+        sd = weights.synth_state_dict({"encoder." + k: v for k, v in weights.shapes_of(enc).items()}, seed_w)
+        sd["quant_conv.weight"] = weights.synth_tensor("quant_conv.weight", (8, 8, 1, 1), seed_w)
+        sd["quant_conv.bias"] = weights.synth_tensor("quant_conv.bias", (8,), seed_w)
+        enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")})
+        x = weights.normal(61, (2, 1, hw, hw))
+        y = torch.nn.functional.conv2d(enc(x), sd["quant_conv.weight"], sd["quant_conv.bias"])
+        out[tag + "_cfg"] = np.asarray([ch, hw])
+        out[tag + "_out"] = y.numpy()
+        out[tag + "_std"] = float(y.std())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed_w=seed_w, **out)
+    print(name, {k: v for k, v in out.items() if k.endswith("_std")})
+
+
+@torch.no_grad()
 def text_encoder(name="ccdm_text_encoder", seed_w=17):
     """PreloadedBERTEncoder of the unmodified reference (ccdm/ddpm/models/encoder.py:103-123): a small instance in full
     and the shipped size (768 wide, 8 heads x 64, depth 4, 512 tokens) sub-sampled."""
@@ -330,6 +355,8 @@ def main(argv):
         ldm_ddim("ldm_tiny_hybrid", configs.LDM_TINY_XATTN, B=2, hw=(16, 16), S=4, eta=0.0, hybrid=True)
     if want("vae_decoder"):
         vae_decoder()
+    if want("vae_encoder"):
+        vae_encoder()
     if want("text_encoder"):
         text_encoder()
     if want("ldm_plms"):

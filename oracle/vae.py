@@ -65,6 +65,34 @@ def decoder_forward(sd: Dict[str, Tensor], z: Tensor, num_resolutions: int, num_
 
 
 @torch.no_grad()
+def encoder_forward(sd: Dict[str, Tensor], x: Tensor, num_resolutions: int, num_res_blocks: int, prefix: str = "") -> Tensor:
+    """Encoder.forward (model.py:493-520); Downsample :74-78 = zero pad (0, 1, 0, 1) then a pad-0 stride-2 conv."""
+    p = prefix
+    h = _conv(sd, p + "conv_in", x, 1)
+    for i_level in range(num_resolutions):
+        for i_block in range(num_res_blocks):
+            h = resnet_block(sd, p + f"down.{i_level}.block.{i_block}", h)
+            if (p + f"down.{i_level}.attn.{i_block}.norm.weight") in sd:
+                h = attn_block(sd, p + f"down.{i_level}.attn.{i_block}", h)
+        if i_level != num_resolutions - 1:
+            q = p + f"down.{i_level}.downsample.conv"
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[q + ".weight"], sd[q + ".bias"], stride=2)
+    h = resnet_block(sd, p + "mid.block_1", h)
+    h = attn_block(sd, p + "mid.attn_1", h)
+    h = resnet_block(sd, p + "mid.block_2", h)
+    h = _swish(_gn(sd, p + "norm_out", h))
+    return _conv(sd, p + "conv_out", h, 1)
+
+
+@torch.no_grad()
+def autoencoder_encode_moments(sd: Dict[str, Tensor], x: Tensor, num_resolutions: int, num_res_blocks: int) -> Tensor:
+    """AutoencoderKL.encode up to the posterior's parameters (autoencoder.py:350-352): quant_conv(encoder(x));
+    mean = first half of the channels (DiagonalGaussianDistribution.mode, distributions.py:27,61-62)."""
+    h = encoder_forward(sd, x, num_resolutions, num_res_blocks, prefix="encoder.")
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+@torch.no_grad()
 def autoencoder_decode(sd: Dict[str, Tensor], z: Tensor, num_resolutions: int, num_res_blocks: int) -> Tensor:
     """AutoencoderKL.decode: post_quant_conv (1x1) then the decoder; keys as in the reference checkpoint."""
     z = F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])

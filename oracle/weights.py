@@ -120,6 +120,47 @@ def vae_decoder_shapes(ch: int, ch_mult=(1, 2, 4, 4), num_res_blocks: int = 2, z
     return out
 
 
+def vae_encoder_shapes(ch: int, ch_mult=(1, 2, 4, 4), num_res_blocks: int = 2, z_channels: int = 4, in_channels: int = 1,
+                       embed_dim: int = 4, prefix: str = "encoder.") -> Dict[str, tuple]:
+    """Parameter names / shapes of AutoencoderKL's encode half (model.py:398-491 Encoder with attn_resolutions = [],
+    double_z, plus autoencoder.py:317 quant_conv).  Checked against the reference Encoder when it is importable."""
+    out: Dict[str, tuple] = {}
+
+    def conv(p, ci, co, k):
+        out[p + ".weight"] = (co, ci, k, k)
+        out[p + ".bias"] = (co,)
+
+    def norm(p, c):
+        out[p + ".weight"] = (c,)
+        out[p + ".bias"] = (c,)
+
+    def res(p, ci, co):
+        norm(p + ".norm1", ci), conv(p + ".conv1", ci, co, 3), norm(p + ".norm2", co), conv(p + ".conv2", co, co, 3)
+        if ci != co:
+            conv(p + ".nin_shortcut", ci, co, 1)
+
+    conv(prefix + "conv_in", in_channels, ch, 3)
+    in_mult = (1,) + tuple(ch_mult)
+    block_in = ch
+    for i_level in range(len(ch_mult)):
+        block_in, block_out = ch * in_mult[i_level], ch * ch_mult[i_level]
+        for i_block in range(num_res_blocks):
+            res(prefix + f"down.{i_level}.block.{i_block}", block_in, block_out)
+            block_in = block_out
+        if i_level != len(ch_mult) - 1:
+            conv(prefix + f"down.{i_level}.downsample.conv", block_in, block_in, 3)
+    res(prefix + "mid.block_1", block_in, block_in)
+    norm(prefix + "mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(prefix + "mid.attn_1." + n, block_in, block_in, 1)
+    res(prefix + "mid.block_2", block_in, block_in)
+    norm(prefix + "norm_out", block_in)
+    conv(prefix + "conv_out", block_in, 2 * z_channels, 3)
+    if embed_dim:
+        conv("quant_conv", 2 * z_channels, 2 * embed_dim, 1)
+    return out
+
+
 def reference_shapes(name: str) -> Dict[str, tuple]:
     """Parameter shapes of a named reference network (oracle/param_shapes.json, written by
     make_golden.py from the reference modules themselves)."""

@@ -518,3 +518,26 @@ def test_softmax_rows_and_transpose(ops):
     for R, Cc in ((4096, 512), (100, 72), (64, 64), (1, 8)):
         a = torch.randn((R, Cc), device="cuda", generator=g).to(torch.bfloat16)
         assert torch.equal(ops.transpose_bf16(a), a.t().contiguous())
+
+
+@pytest.mark.parametrize("sp,C,Cout", [((32, 32), 64, 64), ((18, 22), 32, 40), ((64, 64), 128, 128)])
+def test_conv_stride2_asymmetric_pad(ops, sp, C, Cout):
+    """The VAE Downsample (model.py:61-80): F.pad(x, (0, 1, 0, 1)) then a stride-2, padding-0 conv == tap offset 0."""
+    no_tf32()
+    rs = np.random.RandomState(2)
+    x = torch.from_numpy(rs.standard_normal((2, 1) + sp + (C,)).astype(np.float32)).cuda().to(torch.bfloat16)
+    w = torch.from_numpy((rs.standard_normal((Cout, C, 3, 3)) / math.sqrt(9 * C)).astype(np.float32)).cuda()
+    b = torch.from_numpy(rs.standard_normal(Cout).astype(np.float32)).cuda()
+    osp = ((sp[0] + 1 - 3) // 2 + 1, (sp[1] + 1 - 3) // 2 + 1)
+    Cout8 = (Cout + 7) // 8 * 8
+    y = torch.full((2, 1) + osp + (Cout8,), float("nan"), dtype=torch.bfloat16, device="cuda")
+    wp = ops.pack_conv_weight(w, [C])
+    b_pad = ops.pad_vec(b, Cout)
+    a = ops.make_conv_args([(x, False)], wp, Cout, y, dims=2, ksize=3, stride=2, bias=b_pad, offsets=(0, 0, 0), out_spatial=(1,) + osp)
+    ops.conv_fwd(a)
+    torch.cuda.synchronize()
+    xn = nchw_from_cl(x)[:, :, 0]
+    want = torch.nn.functional.conv2d(torch.nn.functional.pad(xn, (0, 1, 0, 1)), w.to(torch.bfloat16).float(), b, stride=2)
+    got = nchw_from_cl(y, Cout)[:, :, 0]
+    assert got.shape == want.shape and not torch.isnan(got).any()
+    assert rel_err(got, want) <= 6e-3

@@ -426,8 +426,10 @@ def test_vae_decode_vs_reference():
         dd = dict(ch=ch, out_ch=1, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0, in_channels=1,
                   resolution=zhw * 8, z_channels=4, double_z=True, dims=2)
         ae = AutoencoderKL(dd, 4)
-        assert weights.shapes_of(ae) == weights.vae_decoder_shapes(ch)
-        ae.load_state_dict(weights.synth_state_dict(weights.shapes_of(ae), int(g["seed_w"])))
+        dec_shapes = weights.vae_decoder_shapes(ch)
+        assert {k: v for k, v in weights.shapes_of(ae).items() if k.startswith(("decoder.", "post_quant_conv."))} == dec_shapes
+        missing = ae.load_state_dict(weights.synth_state_dict(dec_shapes, int(g["seed_w"])), strict=False)
+        assert all(k.startswith(("encoder.", "quant_conv.")) for k in missing.missing_keys)
         ae = ae.cuda().eval()
         z = weights.normal(51, (2, 4, zhw, zhw)).cuda()
         y = ae.decode(z)
@@ -436,8 +438,33 @@ def test_vae_decode_vs_reference():
         print(f"vae decode {tag}: rel err {rel(got, want):.4f}  PSNR {psnr(got, want):.1f} dB")
         assert rel(got, want) <= 3e-2 and psnr(got, want) >= 35.0, (tag, rel(got, want))
         assert torch.equal(y, ae.decode(z))
-    with pytest.raises(NotImplementedError):
-        ae.encode(z)
+
+
+def test_vae_encode_vs_reference():
+    """ldm.autoencoder.AutoencoderKL.encode (encode half) against the unmodified reference Encoder + quant_conv:
+    posterior moments on a 128 x 128 slice (narrow and shipped widths); the posterior object behaves like the reference's."""
+    from jointimagegeneration_b200.ldm.autoencoder import AutoencoderKL
+    from oracle import weights
+    g = golden("vae_encoder")
+    for tag in ("small", "wide"):
+        ch, hw = (int(v) for v in g[tag + "_cfg"])
+        dd = dict(ch=ch, out_ch=1, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0, in_channels=1,
+                  resolution=hw, z_channels=4, double_z=True, dims=2)
+        ae = AutoencoderKL(dd, 4)
+        want_shapes = dict(weights.vae_encoder_shapes(ch))
+        want_shapes.update(weights.vae_decoder_shapes(ch))
+        assert weights.shapes_of(ae) == want_shapes
+        sd = weights.synth_state_dict(weights.vae_encoder_shapes(ch), int(g["seed_w"]))
+        missing = ae.load_state_dict(sd, strict=False)
+        assert all(k.startswith(("decoder.", "post_quant_conv.")) for k in missing.missing_keys)
+        ae = ae.cuda().eval()
+        x = weights.normal(61, (2, 1, hw, hw)).cuda()
+        post = ae.encode(x)
+        got, want = post.parameters.cpu().numpy(), g[tag + "_out"]
+        print(f"vae encode {tag}: moments rel err {rel(got, want):.4f}  PSNR {psnr(got, want):.1f} dB")
+        assert got.shape == want.shape == (2, 8, hw // 8, hw // 8)
+        assert rel(got, want) <= 3e-2 and psnr(got, want) >= 35.0
+        assert torch.equal(post.mode(), post.parameters[:, :4]) and post.sample().shape == post.mean.shape
 
 
 def test_text_context_encoder_vs_reference():
