@@ -12,6 +12,8 @@ the minimal object ``DDIMSampler`` and ``sample_cond`` need: ``num_timesteps``, 
 """
 from contextlib import contextmanager
 
+from typing import Optional
+
 import numpy as np
 import torch
 from torch import nn
@@ -50,13 +52,15 @@ class DiffusionWrapper(nn.Module):
 class LatentDiffusion(nn.Module):
     def __init__(self, unet: nn.Module, conditioning_key="concat", timesteps=1000, beta_schedule="linear",
                  linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3, given_betas=None, parameterization="eps",
-                 scale_factor=1.0):
+                 scale_factor=1.0, first_stage_model: Optional[nn.Module] = None):
         super().__init__()
         assert parameterization in ["eps", "x0"]
         self.parameterization = parameterization
         self.model = DiffusionWrapper(unet, conditioning_key)
         self.conditioning_key = conditioning_key
         self.scale_factor = scale_factor
+        # ldm.autoencoder.AutoencoderKL for the `_ae` configuration; None = pixel-space LDM (`__is_no_first_stage__`)
+        self.first_stage_model = first_stage_model
         self.use_ema = False
         self.v_posterior = 0.
         self.register_schedule(given_betas, beta_schedule, timesteps, linear_start, linear_end, cosine_s)
@@ -85,6 +89,32 @@ class LatentDiffusion(nn.Module):
         self.register_buffer("posterior_log_variance_clipped", f32(np.log(np.maximum(post_var, 1e-20))))
         self.register_buffer("posterior_mean_coef1", f32(betas * np.sqrt(acp_prev) / (1. - acp)))
         self.register_buffer("posterior_mean_coef2", f32((1. - acp_prev) * np.sqrt(alphas) / (1. - acp)))
+
+    # ---- first stage (ddpm.py:551-558, :717-776, :839-862; the split_input_params patching is a training-time option)
+    @property
+    def no_first_stage(self):
+        return self.first_stage_model is None
+
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        return x if self.no_first_stage else self.first_stage_model.encode(x)
+
+    def get_first_stage_encoding(self, encoder_posterior):
+        if isinstance(encoder_posterior, torch.Tensor):
+            z = encoder_posterior
+        elif hasattr(encoder_posterior, "sample"):          # DiagonalGaussianDistribution
+            z = encoder_posterior.sample()
+        else:
+            raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
+        return self.scale_factor * z
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        if self.no_first_stage:
+            return z
+        if predict_cids:
+            raise NotImplementedError("codebook decoding belongs to VQModel first stages (not shipped)")
+        return self.first_stage_model.decode(1. / self.scale_factor * z)
 
     @torch.no_grad()
     def p_sample(self, x, c, t, clip_denoised=False, repeat_noise=False, return_codebook_ids=False, quantize_denoised=False,

@@ -467,6 +467,28 @@ def test_vae_encode_vs_reference():
         assert torch.equal(post.mode(), post.parameters[:, :4]) and post.sample().shape == post.mean.shape
 
 
+def test_latent_diffusion_first_stage_glue():
+    """LatentDiffusion.encode_first_stage / get_first_stage_encoding / decode_first_stage (ddpm.py:551-558,717-776,839-862)
+    around the AutoencoderKL drop-in: scale_factor handling and the `__is_no_first_stage__` identity."""
+    from jointimagegeneration_b200.ldm import LatentDiffusion, UNetModel
+    from jointimagegeneration_b200.ldm.autoencoder import AutoencoderKL
+    from oracle import configs, weights
+    dd = dict(ch=32, out_ch=1, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0, in_channels=1,
+              resolution=128, z_channels=4, double_z=True, dims=2)
+    ae = AutoencoderKL(dd, 4)
+    ae.load_state_dict(weights.synth_state_dict(weights.shapes_of(ae), 3))
+    ld = LatentDiffusion(UNetModel(**configs.LDM_TINY), conditioning_key="concat", scale_factor=0.5, first_stage_model=ae,
+                         **configs.LDM_SCHEDULE).cuda().eval()
+    x = weights.normal(7, (1, 1, 128, 128)).cuda()
+    post = ld.encode_first_stage(x)
+    z = ld.get_first_stage_encoding(post.mode())
+    assert z.shape == (1, 4, 16, 16) and torch.equal(z, 0.5 * post.mean)
+    y = ld.decode_first_stage(z)
+    assert y.shape == x.shape and torch.equal(y, ae.decode(post.mean))
+    plain = LatentDiffusion(UNetModel(**configs.LDM_TINY), conditioning_key="concat", **configs.LDM_SCHEDULE)
+    assert plain.no_first_stage and plain.decode_first_stage(z) is z and plain.encode_first_stage(x) is x
+
+
 def test_text_context_encoder_vs_reference():
     """ccdm.encoder.PreloadedBERTEncoder against the unmodified reference module's outputs: small instance in
     full, shipped size (768 wide, 8 x 64 heads, depth 4, 512 tokens) sub-sampled.  bf16 blocks vs fp32 reference."""
