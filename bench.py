@@ -328,9 +328,17 @@ def run_ours(args):
         attn_flops = wl.get("attn_flop", 0.022e12 / 6.324e12 * wl["flop_per_sample"])
         conv_alg = (wl["flop_per_sample"] - attn_flops) * B * share
         ach = conv_alg / (conv_ms / 1e3) / 1e12
+        # DRAM bytes per conv launch from the committed ncu pass (profiles/r1_conv_dram_ccdm_cfg2.md): only valid for the
+        # exact workload it was captured on (config 2, 8 volumes per GPU, no text conditioning, one rank's full volume)
+        traffic, traffic_src = None, None
+        if args.workload == "ccdm_cfg2" and B == 8 and not slab:
+            traffic = 55.87e9 / 114
+            traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum over the 114 conv launches of one forward = 55.87 GB " \
+                          "(profiles/r1_conv_dram_ccdm_cfg2.md); algorithmic conv input + output bytes: 56 GB (SURVEY.md 8d)"
         line["roofline"] = {"bound": "tensor", "kernel": "conv_roll_kernel + conv_halo_kernel + conv_tcgen05_kernel (all %d conv launches of one step)" % n_conv,
                             "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
-                            "traffic": None, "algorithmic_flop": conv_alg, "issued_flop": plan.flops, "avg_launch_ms": conv_ms / n_conv,
+                            "traffic": traffic, "traffic_source": traffic_src,
+                            "algorithmic_flop": conv_alg, "issued_flop": plan.flops, "avg_launch_ms": conv_ms / n_conv,
                             "by_kernel": by_kernel,
                             "peak_source": peaks["source"] + " (bf16 sustained: kernel timed inside a long step)",
                             "whole_step_frac": wl["flop_per_sample"] * B * share / (ms / K / 1e3) / 1e12 / peaks["tf_sustained"]}
@@ -339,7 +347,9 @@ def run_ours(args):
         act_b = (64 + 1 + 1 + 2 * plan.inputs["x"].shape[-1] + 2) * B * V
         line["roofline_hbm_resident"] = {"bound": "hbm", "kernel": "cat_step_cl_fast_kernel (softmax + posterior + clamp + Philox inverse-CDF draw + next input)",
                                          "achieved": alg_b / (cat_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                         "frac": alg_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                         "frac": alg_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                                         # ncu capture of this kernel's I/O at B = 8 (profiles/r1_ncu_full_summaries.md)
+                                         "traffic": 786.8e6 if (args.workload == "ccdm_cfg2" and B == 8 and not slab) else None,
                                          "algorithmic_bytes": alg_b, "moved_bytes": act_b,
                                          "moved_frac": act_b / (cat_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "launch_ms": cat_ms}
         # the per-voxel kernel at the reference's tensor interface (fp32 [B,C,V] in/out, injected Exp(1) noise):
