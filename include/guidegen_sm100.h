@@ -223,6 +223,11 @@ typedef struct {
 int gg_gn_finalize(const gg_gn_finalize_args* a, gg_stream_t stream);
 int gg_gn_apply(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* scale_shift,
                 void* y_cl, int32_t N, int64_t S, int32_t silu, gg_stream_t stream);
+/* The same GroupNorm (+SiLU) in ONE launch for tensors that fit in L2 (a cluster of 8 CTAs per sample, channel sums
+ * exchanged through distributed shared memory, fp64 combine in rank order): replaces the three dependent launches
+ * above where their launch latency dominates (LDM latents, deep CCDM levels).  C1 + C2 <= 2048. */
+int gg_gn_fused(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* gamma, const float* beta, void* y_cl,
+                int32_t N, int64_t S, int32_t groups, float eps, int32_t silu, gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1-K5,K15  implicit-GEMM convolution on tcgen05 tensor cores (bf16 x bf16 -> fp32 in TMEM)

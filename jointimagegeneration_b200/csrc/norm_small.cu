@@ -186,6 +186,119 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------------------------------
+// GroupNorm (+SiLU) of SMALL tensors in one launch: statistics + apply.  The three-kernel form above costs three
+// dependent launches of ~10 us each on tensors that fit in L2 (the 64 x 64 ... 8 x 8 latents of the LDM configs, the
+// deep levels of the CCDM network).  Here a cluster of GNF_CL CTAs owns one sample: every CTA sums its slice of the
+// positions per channel (fp32 per thread, fixed order), the per-CTA channel sums are exchanged through distributed
+// shared memory and combined in fp64 in rank order (identical in every CTA of the cluster), then each CTA normalises
+// its own slice, which it re-reads from L2.  Same apply formula and rounding points as gn_apply_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int GNF_CL = 8;
+template <bool SILU>
+__global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
+                                                       int C2, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       __nv_bfloat16* __restrict__ y, int64_t S, int groups, float eps) {
+    extern __shared__ float2 gsm[];
+    const int C = C1 + C2, P8 = C >> 3, R = 256 / P8;
+    float2* part = gsm;                 // [R][C]  per-thread-row channel sums of this CTA
+    float2* csum = gsm + R * C;         // [C]     this CTA's channel sums (read by the whole cluster)
+    float2* ssm = csum + C;             // [C]     (scale, shift)
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int n = blockIdx.x / GNF_CL;
+    const int oct = threadIdx.x % P8, row = threadIdx.x / P8;
+    const bool active = row < R;
+    const int c0 = oct * 8;
+    const int64_t chunk = (S + GNF_CL - 1) / GNF_CL, p0 = (int64_t)rank * chunk, p1 = min(S, p0 + chunk);
+    const __nv_bfloat16* src = nullptr;
+    int Cs = 0;
+    if (active) {
+        if (c0 < C1) { src = x1 + ((int64_t)n * S) * C1 + c0; Cs = C1; }
+        else { src = x2 + ((int64_t)n * S) * C2 + (c0 - C1); Cs = C2; }
+    }
+    // ---- pass 1: per-channel (sum, sum of squares) over this CTA's positions
+    if (active) {
+        float s1[8], s2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+        auto acc = [&](uint4 v) {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+                s1[2 * e] += lo; s2[2 * e] = fmaf(lo, lo, s2[2 * e]);
+                s1[2 * e + 1] += hi; s2[2 * e + 1] = fmaf(hi, hi, s2[2 * e + 1]);
+            }
+        };
+        int64_t p = p0 + row;
+        for (; p + 3 * R < p1; p += 4 * R) {
+            const uint4 a = ldg_nc_u4(src + p * Cs), b = ldg_nc_u4(src + (p + R) * Cs);
+            const uint4 c = ldg_nc_u4(src + (p + 2 * R) * Cs), d = ldg_nc_u4(src + (p + 3 * R) * Cs);
+            acc(a); acc(b); acc(c); acc(d);
+        }
+        for (; p < p1; p += R) acc(ldg_nc_u4(src + p * Cs));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part[row * C + c0 + e] = make_float2(s1[e], s2[e]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f, b = 0.f;
+        for (int r = 0; r < R; ++r) { const float2 v = part[r * C + c]; a += v.x; b += v.y; }
+        csum[c] = make_float2(a, b);
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // ---- group statistics: fp64 over the cluster's CTAs (rank order) and the group's channels
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += 256) {
+        double s = 0.0, q = 0.0;
+        for (int r = 0; r < GNF_CL; ++r) {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(csum + g * cpg)), "r"(r));
+            for (int c = 0; c < cpg; ++c) {
+                float2 v;
+                asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(remote + 8u * (uint32_t)c));
+                s += (double)v.x; q += (double)v.y;
+            }
+        }
+        const double cnt = (double)S * cpg, mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float sc = (gamma ? __ldg(gamma + c) : 1.0f) * rstd;
+            ssm[c] = make_float2(sc, (beta ? __ldg(beta + c) : 0.0f) - (float)mean * sc);
+        }
+    }
+    // nobody may leave (or reuse csum) while a peer still reads it; also publishes ssm within the CTA
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // ---- pass 2: apply to this CTA's slice (L2-resident re-read)
+    if (!active) return;
+    float sc[8], sh[8];
+    const float f = SILU ? 0.5f : 1.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float2 k = ssm[c0 + e]; sc[e] = k.x * f; sh[e] = k.y * f; }
+    __nv_bfloat16* dst = y + ((int64_t)n * S) * C + c0;
+    auto apply = [&](uint4 v, int64_t p) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float f0 = fmaf(bf16_lo(w[e]), sc[2 * e], sh[2 * e]), f1 = fmaf(bf16_hi(w[e]), sc[2 * e + 1], sh[2 * e + 1]);
+            if (SILU) { f0 = fmaf(f0, tanh_fast(f0), f0); f1 = fmaf(f1, tanh_fast(f1), f1); }
+            o[e] = pack_bf16(f0, f1);
+        }
+        *reinterpret_cast<uint4*>(dst + p * C) = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+    int64_t p = p0 + row;
+    for (; p + 3 * R < p1; p += 4 * R) {
+        const uint4 a = ldg_nc_u4(src + p * Cs), b = ldg_nc_u4(src + (p + R) * Cs);
+        const uint4 c = ldg_nc_u4(src + (p + 2 * R) * Cs), d = ldg_nc_u4(src + (p + 3 * R) * Cs);
+        apply(a, p); apply(b, p + R); apply(c, p + 2 * R); apply(d, p + 3 * R);
+    }
+    for (; p < p1; p += R) apply(ldg_nc_u4(src + p * Cs), p);
+}
+
+// ------------------------------------------------------------------------------------------
 // LayerNorm (one warp per row), GEGLU, nearest x2 upsample
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
@@ -386,6 +499,38 @@ extern "C" int gg_gn_apply(const void* x1_cl, int32_t C1, const void* x2_cl, int
         gn_apply_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x1_cl), C1,
                                                                   reinterpret_cast<const __nv_bfloat16*>(x2_cl), C2, scale_shift,
                                                                   reinterpret_cast<__nv_bfloat16*>(y_cl), S, cs);
+    return launch_result();
+}
+
+extern "C" int gg_gn_fused(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* gamma, const float* beta,
+                           void* y_cl, int32_t N, int64_t S, int32_t groups, float eps, int32_t silu, gg_stream_t stream) {
+    GG_REQUIRE(x1_cl && y_cl && N > 0 && S > 0 && C1 > 0 && C2 >= 0 && (C2 == 0 || x2_cl) && groups > 0, GG_ERR_BAD_ARG);
+    const int C = C1 + C2;
+    GG_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0 && C <= 2048 && groups <= 256, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(aligned(x1_cl, 16) && aligned(y_cl, 16) && (!x2_cl || aligned(x2_cl, 16)), GG_ERR_ALIGNMENT);
+    const int R = 256 / (C / 8);
+    const size_t smem = (size_t)(R * C + 2 * C) * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    GG_REQUIRE(smem <= 64 * 1024, GG_ERR_UNSUPPORTED);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(N * GNF_CL)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = GNF_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(x1_cl);
+    const __nv_bfloat16* a2 = reinterpret_cast<const __nv_bfloat16*>(x2_cl);
+    __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y_cl);
+    cudaError_t e = silu ? cudaLaunchKernelEx(&cfg, gn_fused_kernel<true>, a1, (int)C1, a2, (int)C2, gamma, beta, yy, S, (int)groups, eps)
+                         : cudaLaunchKernelEx(&cfg, gn_fused_kernel<false>, a1, (int)C1, a2, (int)C2, gamma, beta, yy, S, (int)groups, eps);
+    if (e != cudaSuccess) return (int)e;
     return launch_result();
 }
 

@@ -214,6 +214,22 @@ def gn_apply(x1, x2, scale_shift, silu, out=None):
     return out
 
 
+def gn_fused(x1, x2, gamma, beta, eps=1e-5, silu=False, groups=32, out=None):
+    """GroupNorm32 over th.cat([x1, x2], channel) (+SiLU) in one launch (small, L2-resident tensors)."""
+    _chk(x1, torch.bfloat16)
+    N, C1 = x1.shape[0], x1.shape[-1]
+    S = x1[0].numel() // C1
+    C2 = 0
+    if x2 is not None:
+        _chk(x2, torch.bfloat16)
+        C2 = x2.shape[-1]
+    if out is None:
+        out = torch.empty(tuple(x1.shape[:-1]) + (C1 + C2,), dtype=torch.bfloat16, device=x1.device)
+    _C.check(_C.lib().gg_gn_fused(_C.ptr(x1), C1, _C.ptr(x2), C2, _C.ptr(gamma), _C.ptr(beta), _C.ptr(out), N, S, groups, float(eps),
+                                  int(silu), _C.stream()), "gg_gn_fused")
+    return out
+
+
 def group_norm_cl(x1, x2, gamma, beta, eps=1e-5, silu=False, groups=32, out=None):
     """GroupNorm32 over th.cat([x1, x2], channel) (+SiLU), statistics in fp32/fp64."""
     p1 = gn_partial(x1)

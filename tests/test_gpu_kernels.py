@@ -541,3 +541,28 @@ def test_conv_stride2_asymmetric_pad(ops, sp, C, Cout):
     got = nchw_from_cl(y, Cout)[:, :, 0]
     assert got.shape == want.shape and not torch.isnan(got).any()
     assert rel_err(got, want) <= 6e-3
+
+
+@pytest.mark.parametrize("N,sp,C1,C2,silu", [(16, (64, 64), 320, 0, True), (3, (5, 7, 9), 64, 128, False), (2, (8, 8), 800, 800, True),
+                                             (1, (4, 4, 4), 320, 0, True), (4, (16, 16), 640, 320, True)])
+def test_group_norm_one_launch(ops, N, sp, C1, C2, silu):
+    """gg_gn_fused (cluster per sample, DSMEM reduction) vs the three-kernel GroupNorm and vs torch."""
+    no_tf32()
+    rs = np.random.RandomState(7)
+    sp3 = (1,) * (3 - len(sp)) + tuple(sp)
+    mk = lambda c: torch.from_numpy((rs.standard_normal((N,) + sp3 + (c,)) * 1.5 + 0.4).astype(np.float32)).cuda().to(torch.bfloat16)
+    x1, x2 = mk(C1), (mk(C2) if C2 else None)
+    C = C1 + C2
+    gamma = torch.from_numpy(rs.standard_normal(C).astype(np.float32)).cuda()
+    beta = torch.from_numpy(rs.standard_normal(C).astype(np.float32)).cuda()
+    got = ops.gn_fused(x1, x2, gamma, beta, 1e-6, silu)
+    three = ops.group_norm_cl(x1, x2, gamma, beta, 1e-6, silu)
+    xr = nchw_from_cl(torch.cat([x1, x2], -1) if C2 else x1)
+    want = torch.nn.functional.group_norm(xr, 32, gamma, beta, 1e-6)
+    if silu:
+        want = torch.nn.functional.silu(want)
+    assert rel_err(nchw_from_cl(got), want) <= 6e-3
+    # same formula as the three-kernel path; only the summation order of the statistics differs (last-bit flips)
+    d = (got.float() - three.float()).abs()
+    assert float((d > 0).float().mean()) <= 5e-3 and float(d.max()) <= 2.0 ** -7 * float(three.float().abs().max())
+    assert torch.equal(got, ops.gn_fused(x1, x2, gamma, beta, 1e-6, silu))
