@@ -239,3 +239,29 @@ def test_sample_sharding_over_gloo_world_size_2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_next_row_modules_keep_the_reference_parameter_names():
+    """state_dict contract of the drop-ins added for SURVEY 8f (N1, N3): parameter names / shapes equal the reference
+    modules' (oracle.weights.*_shapes are checked against the live reference in tests/test_oracle_pinning.py); no
+    forward is run here, and a CPU forward must refuse loudly (no fallback)."""
+    import pytest
+    import torch
+    from jointimagegeneration_b200.ccdm import PreloadedBERTEncoder
+    from jointimagegeneration_b200.ldm import PLMSSampler  # noqa: F401  (importable without a GPU)
+    from jointimagegeneration_b200.ldm.autoencoder import AutoencoderKL
+    from oracle import weights
+    dd = dict(ch=128, out_ch=1, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0, in_channels=1,
+              resolution=512, z_channels=4, double_z=True, dims=2)       # ruijin-ldm_from_controlnet_ae.yaml:48-63
+    ae = AutoencoderKL(dd, 4)
+    want = dict(weights.vae_encoder_shapes(128))
+    want.update(weights.vae_decoder_shapes(128))
+    assert weights.shapes_of(ae) == want
+    with pytest.raises(RuntimeError):
+        ae.decode(torch.zeros(1, 4, 8, 8))
+    with pytest.raises(RuntimeError):
+        ae.encode(torch.zeros(1, 1, 64, 64))
+    enc = PreloadedBERTEncoder()                                          # encoder.py:104-105 defaults: 768 / 8 heads / depth 4 / 64
+    assert weights.shapes_of(enc) == weights.encoder_shapes(768, 8, 64, 4)
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(1, 768, 16))
