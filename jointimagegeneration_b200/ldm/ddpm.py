@@ -52,7 +52,8 @@ class DiffusionWrapper(nn.Module):
 class LatentDiffusion(nn.Module):
     def __init__(self, unet: nn.Module, conditioning_key="concat", timesteps=1000, beta_schedule="linear",
                  linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3, given_betas=None, parameterization="eps",
-                 scale_factor=1.0, first_stage_model: Optional[nn.Module] = None):
+                 scale_factor=1.0, first_stage_model: Optional[nn.Module] = None,
+                 cond_stage_model: Optional[nn.Module] = None):
         super().__init__()
         assert parameterization in ["eps", "x0"]
         self.parameterization = parameterization
@@ -61,6 +62,9 @@ class LatentDiffusion(nn.Module):
         self.scale_factor = scale_factor
         # ldm.autoencoder.AutoencoderKL for the `_ae` configuration; None = pixel-space LDM (`__is_no_first_stage__`)
         self.first_stage_model = first_stage_model
+        # conditioning encoder: None = IdentityEncoder (pixel config, modules.py:287-289); the `_ae` configuration puts a
+        # second AutoencoderKL here (cond_stage_config, ruijin-ldm_from_controlnet_ae.yaml:68-90) whose posterior mode is c
+        self.cond_stage_model = cond_stage_model
         self.use_ema = False
         self.v_posterior = 0.
         self.register_schedule(given_betas, beta_schedule, timesteps, linear_start, linear_end, cosine_s)
@@ -162,8 +166,16 @@ class LatentDiffusion(nn.Module):
         yield None
 
     def get_learned_conditioning(self, c):
-        """IdentityEncoder cond stage of the shipped pixel config (modules.py:287-289)."""
-        return c
+        """ddpm.py:560-571 with cond_stage_forward = None: identity for the pixel config; an encoder's output, taking the
+        mode of a posterior (DiagonalGaussianDistribution) when it returns one."""
+        if self.cond_stage_model is None:
+            return c
+        if hasattr(self.cond_stage_model, "encode") and callable(self.cond_stage_model.encode):
+            c = self.cond_stage_model.encode(c)
+            if hasattr(c, "mode") and not isinstance(c, torch.Tensor):
+                c = c.mode()
+            return c
+        return self.cond_stage_model(c)
 
     def apply_model(self, x_noisy, t, cond, return_ids=False):
         """ddpm.py:904-913 + 999-1005."""

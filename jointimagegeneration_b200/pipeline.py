@@ -54,7 +54,12 @@ class GuideGenPipeline:
         _, _, D, H, W = wholemask.shape
         nz = torch.where(wholemask.sum((0, 1, 3, 4)))[0]          # occupied slices (host sync once per volume)
         start_layer, end_layer = int(nz[0]), int(nz[-1])
-        shape = (1, H, W)
+        if model.no_first_stage:
+            shape = (1, H, W)                                      # pixel-space LDM (sample_diffusion.py:203)
+        else:                                                      # `_ae` configuration: the sampler works on latents
+            dec = model.first_stage_model.decoder
+            f = 2 ** (dec.num_resolutions - 1)
+            shape = (dec.z_channels, H // f, W // f)
         samples = torch.zeros((n_samples, 1, D, H, W), dtype=torch.float32, device=dev)
         gen_mask = wholemask.repeat(n_samples, 1, 1, 1, 1)
         scratch = torch.empty(1024, dtype=torch.float32, device=dev)
@@ -64,6 +69,6 @@ class GuideGenPipeline:
                 c = model.get_learned_conditioning(concat_cond)
                 s, _ = self.sampler.sample(S=self.ddim_steps, dims=2, conditioning=c, batch_size=n_samples, shape=shape,
                                            verbose=False, eta=self.ddim_eta, x_T=None if x_T_fn is None else x_T_fn(m_))
-                ds = s                                             # decode_first_stage: identity first stage (pixel config)
+                ds = model.decode_first_stage(s)                   # identity for the pixel config (:219)
                 ops.minmax_normalize(ds.contiguous(), samples[:, 0, m_], scratch)
         return torch.cat([samples, gen_mask], dim=1)

@@ -489,6 +489,40 @@ def test_latent_diffusion_first_stage_glue():
     assert plain.no_first_stage and plain.decode_first_stage(z) is z and plain.encode_first_stage(x) is x
 
 
+def test_pipeline_with_first_and_cond_stage_autoencoders():
+    """The `_ae` configuration through GuideGenPipeline.sample_cond: conditioning = posterior mode of a 2-channel
+    AutoencoderKL over [previous slice, mask slice] (get_learned_conditioning, ddpm.py:560-571), sampling on 4 x H/8 x W/8
+    latents, decode_first_stage per slice (sample_diffusion.py:208-222).  Checked against the same steps composed by hand."""
+    from jointimagegeneration_b200.ldm import DDIMSampler, LatentDiffusion, UNetModel
+    from jointimagegeneration_b200.ldm.autoencoder import AutoencoderKL
+    from jointimagegeneration_b200.pipeline import GuideGenPipeline
+    from oracle import configs, weights
+    dd1 = dict(ch=32, out_ch=1, ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0, in_channels=1,
+               resolution=128, z_channels=4, double_z=True, dims=2)
+    dd2 = dict(dd1, in_channels=2, out_ch=2)
+    first, cond = AutoencoderKL(dd1, 4), AutoencoderKL(dd2, 4)
+    first.load_state_dict(weights.synth_state_dict(weights.shapes_of(first), 31))
+    cond.load_state_dict(weights.synth_state_dict(weights.shapes_of(cond), 32))
+    unet = UNetModel(**configs.LDM_TINY)
+    _load_synth(unet, 11)
+    ld = LatentDiffusion(unet, conditioning_key="concat", first_stage_model=first, cond_stage_model=cond, **configs.LDM_SCHEDULE).cuda().eval()
+    H = W = 128
+    wholemask = torch.zeros(1, 1, 5, H, W, device="cuda")
+    wholemask[:, :, 1:4, 30:90, 40:100] = 3.0 / 255.0
+    noise = {m: weights.normal(100 + m, (2, 4, H // 8, W // 8)).cuda() for m in range(0, 5)}
+    pipe = GuideGenPipeline(ld, None, ddim_steps=4, ddim_eta=0.0)
+    pred = pipe.sample_cond(wholemask, n_samples=2, x_T_fn=lambda m: noise[m])
+    assert pred.shape == (2, 2, 5, H, W) and torch.isfinite(pred).all()
+    assert float(pred[:, 0].min()) >= 0.0 and float(pred[:, 0].max()) <= 1.0
+    # slice 0 by hand: cond = mode(encode([zeros, mask_0])), 4 DDIM steps on latents, decode, min-max normalise
+    cc = torch.cat([torch.zeros(2, 1, H, W, device="cuda"), wholemask[:, 0, 0:1].repeat(2, 1, 1, 1)], 1)
+    c = cond.encode(cc).mode()
+    s, _ = DDIMSampler(ld).sample(S=4, dims=2, conditioning=c, batch_size=2, shape=(4, H // 8, W // 8), verbose=False, eta=0.0, x_T=noise[0])
+    ds = first.decode(s)
+    want0 = (ds - ds.min()) / (ds.max() - ds.min())
+    assert float((pred[:, 0, 0] - want0[:, 0]).abs().max()) <= 1e-5
+
+
 def test_text_context_encoder_vs_reference():
     """ccdm.encoder.PreloadedBERTEncoder against the unmodified reference module's outputs: small instance in
     full, shipped size (768 wide, 8 x 64 heads, depth 4, 512 tokens) sub-sampled.  bf16 blocks vs fp32 reference."""
