@@ -265,3 +265,26 @@ def test_next_row_modules_keep_the_reference_parameter_names():
     assert weights.shapes_of(enc) == weights.encoder_shapes(768, 8, 64, 4)
     with pytest.raises(RuntimeError):
         enc(torch.zeros(1, 768, 16))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU oracle port, rank 0 only): one JSON line with the contract's keys; other ranks
+    print nothing.  BENCH_CPU_BUDGET_S bounds the sample so that the test takes seconds."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, BENCH_CPU_BUDGET_S="1", RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "denoising steps/sec" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["name"] == "ccdm_cfg2"
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
