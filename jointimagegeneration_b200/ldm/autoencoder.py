@@ -20,7 +20,6 @@ sm_100a kernels as the denoiser:
 kernel with tap offset 0; ``AutoencoderKL.encode`` returns the reference's ``DiagonalGaussianDistribution`` (mean / logvar /
 ``mode()`` / ``sample()``) of ``quant_conv(encoder(x))``.  There is no CPU / PyTorch fallback.
 """
-import math
 from typing import Dict, Optional
 
 import torch

@@ -9,8 +9,6 @@ write-back are one fused pair of kernels, and the conditioning of slice m (previ
 mask slice) is assembled by views.  Slices are strictly sequential (slice m conditions on slice m-1);
 parallelism over GPUs comes from independent volumes / samples (``sharding``).
 """
-from typing import Optional
-
 import torch
 
 from . import ops

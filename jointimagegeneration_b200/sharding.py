@@ -6,7 +6,7 @@ collective; the only communication is one gather of the final label volumes / sl
 (SURVEY.md section 8e).  This module is pure host logic and runs identically over ``gloo`` (CPU
 tests) and ``nccl`` (B200).
 """
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist

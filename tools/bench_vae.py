@@ -1,5 +1,5 @@
 """Times AutoencoderKL.encode / .decode at the shipped size (ch 128, mult 1-2-4-4, 512 x 512 slices, n = 2) -- tuning aid."""
-import os, sys, time
+import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
