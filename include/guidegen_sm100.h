@@ -44,7 +44,7 @@ const char* gg_status_string(int status);
 /* 0 when the current device is compute capability 10.x, GG_ERR_NO_DEVICE otherwise */
 int gg_device_check(void);
 /* sizeof() of the argument structs, in header order (gg_cat_args, gg_cat_step_cl_args, gg_ddim_args, gg_plms_args,
- * gg_ddpm_args, gg_gn_finalize_args, gg_conv_src, gg_conv_args, gg_attn_args): lets a binding in another language
+ * gg_ddpm_args, gg_gn_finalize_args, gg_conv_src, gg_conv_args, gg_attn_args, gg_cat_epilogue): lets a binding in another language
  * check its mirror of this header without a GPU.  Writes min(n, 9) entries, returns 9. */
 int gg_abi_sizes(int32_t* out, int n);
 /* number of kernels launched by this library since load / since last reset (host counter) */
@@ -249,6 +249,25 @@ int gg_gn_fused(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, co
  * grid, can be written).  bias / emb rows must be readable up to Cout rounded up to 8, and
  * the output row must hold that many channels (padding channels receive bias only).
  * ---------------------------------------------------------------------------------------- */
+/* Sampler epilogue of the output head conv (gg_conv_args.cat; depth-rolling kernel, Cout <= 16): the accumulator row of
+ * a voxel holds all its class logits, so the whole reverse step of ccdm/ddpm/models/diffusion_denoising.py:203-224 --
+ * Softmax (unet.py:720) -> theta_post_prob (:105-139) -> clamp (:216) -> OneHotCategoricalBCHW.sample()
+ * (one_hot_categorical.py:25-31) -> next network input th.cat([x, condition]) (unet.py:775) -- runs in the conv's epilogue:
+ * no logits tensor is written or read back and no separate per-voxel kernel is launched.  Same arithmetic and the same
+ * Philox stream as gg_cat_step_cl's production path (labels are identical for identical accumulators). */
+typedef struct {
+    const uint8_t* labels_in;   /* [N*V] x_t as class indices                                          */
+    uint8_t* labels_out;        /* [N*V] drawn x_{t-1} (8-byte aligned)                                */
+    void* next_x;               /* bf16 [N*V, Cin_pad] = one-hot(C) | cond | zero padding, or NULL     */
+    const void* cond;           /* bf16 [N*V, n_cond] condition channels or NULL (zeros)               */
+    const float* coef;          /* [N, 2] (alpha_t, cumalpha_{t-1}) per sample                         */
+    int32_t C, n_cond, Cin_pad;
+    int32_t mode;               /* GG_CAT_SAMPLE                                                       */
+    float clamp_min;
+    uint64_t seed, offset;      /* Philox key / counter base                                           */
+    int64_t vox_base;           /* global index of this launch's first voxel (multiple of 4)           */
+} gg_cat_epilogue;
+
 typedef struct {
     const void* x;          /* CL bf16 [N, D, H, W, C] */
     int32_t C;              /* multiple of 8 */
@@ -314,6 +333,8 @@ typedef struct {
      * planes that hold a neighbour's data). */
     const float* src_ss[4];
     int32_t ss_stride, xf_silu, xf_z_lo, xf_z_hi;
+    /* NULL, or (algo 4, Cout <= 16): replace the output store by the sampler epilogue above; y is not written. */
+    const gg_cat_epilogue* cat;
 } gg_conv_args;
 
 /* N tile (accumulator columns) the kernel uses for a given Cout */

@@ -71,6 +71,12 @@ class PlmsArgs(C.Structure):
                 ("e_cur", C.c_void_p), ("e_prime", C.c_void_p), ("n", C.c_int64), ("order", C.c_int32), ("guidance_scale", C.c_float)]
 
 
+class CatEpilogue(C.Structure):
+    _fields_ = [("labels_in", C.c_void_p), ("labels_out", C.c_void_p), ("next_x", C.c_void_p), ("cond", C.c_void_p),
+                ("coef", C.c_void_p), ("C", C.c_int32), ("n_cond", C.c_int32), ("Cin_pad", C.c_int32), ("mode", C.c_int32),
+                ("clamp_min", C.c_float), ("seed", C.c_uint64), ("offset", C.c_uint64), ("vox_base", C.c_int64)]
+
+
 class ConvSrc(C.Structure):
     _fields_ = [("x", C.c_void_p), ("C", C.c_int32), ("centre_only", C.c_int32), ("d_shift", C.c_int32), ("reserved", C.c_int32)]
 
@@ -88,7 +94,7 @@ class ConvArgs(C.Structure):
                 ("gn_partial", C.c_void_p), ("gn_chunk_base", C.c_int32), ("gn_nchunks_total", C.c_int32),
                 ("stats_d_min", C.c_int32), ("algo", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p),
                 ("src_ss", C.c_void_p * 4), ("ss_stride", C.c_int32), ("xf_silu", C.c_int32),
-                ("xf_z_lo", C.c_int32), ("xf_z_hi", C.c_int32)]
+                ("xf_z_lo", C.c_int32), ("xf_z_hi", C.c_int32), ("cat", C.POINTER(CatEpilogue))]
 
 
 class AttnArgs(C.Structure):
@@ -101,7 +107,7 @@ class AttnArgs(C.Structure):
 
 
 # the ctypes mirrors above, in the order gg_abi_sizes() reports the C structs
-ABI_STRUCTS = [CatArgs, CatStepCLArgs, DdimArgs, PlmsArgs, DdpmArgs, GnFinalizeArgs, ConvSrc, ConvArgs, AttnArgs]
+ABI_STRUCTS = [CatArgs, CatStepCLArgs, DdimArgs, PlmsArgs, DdpmArgs, GnFinalizeArgs, ConvSrc, ConvArgs, AttnArgs, CatEpilogue]
 
 # every symbol include/guidegen_sm100.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float

@@ -118,7 +118,17 @@ class DenoisingModel(nn.Module):
         self.loop = loop                 # "interface" | "resident"
         self.use_cuda_graph = False      # capture the UNet forward of the loop in a CUDA graph
         self.q_noise = None              # optional injected noise: indexable [step] -> fp32 [B*V, C]
-        self.philox_seed = 0
+        # Key of the in-kernel Philox noise of the resident loop.  None (default): every forward_denoising call draws a
+        # fresh key from torch's default generator -- so torch.manual_seed governs the result and successive calls
+        # (an evaluator looping over volumes, repeated samples) get independent noise, as the reference's
+        # torch.multinomial does by advancing the global RNG.  An int pins the key (reproducible runs, tests).
+        self.philox_seed: Optional[int] = None
+        # global index of this process' first chain when a batch is sharded over ranks (sharding.shard_range): the
+        # Philox counter is the GLOBAL voxel index, so results do not depend on the number of ranks
+        self.chain_base = 0
+        # resident loop: draw inside the head conv's epilogue (no logits tensor, no separate per-voxel launch) whenever the
+        # plan offers it (depth-rolling head conv) and the noise is the in-kernel Philox stream
+        self.fuse_head = True
         self.record = None               # optional list: receives the uint8 label volume after every step
 
     @property
@@ -174,6 +184,7 @@ class DenoisingModel(nn.Module):
         V = int(math.prod(spatial))
         coefs = self.diffusion.step_coef_tensor(torch.tensor(t_values)).to(dev)          # [steps, 2]
         coefs = coefs[:, None, :].expand(-1, B, -1).contiguous()                          # [steps, B, 2]
+        slab = getattr(getattr(self.unet, "_engine", None), "slab", None)
         if self.loop == "resident" and len(t_values) > 1:
             xt = self._resident_steps(xt, cond, context, t_values[:-1], coefs, spatial)
             t_values, coefs, step0 = t_values[-1:], coefs[-1:], len(t_values) - 1
@@ -192,12 +203,17 @@ class DenoisingModel(nn.Module):
             ops.nchw_to_cl(xt, cond, c_pad=unet.in_channels_padded, out=plan.inputs["x"])
             plan.inputs["t"].fill_(float(t))
             plan.run()
-            ops.cl_to_nchw(plan.outputs["head"], Cc, spatial, softmax=True, out=probs_x0)
+            ops.cl_to_nchw(plan.outputs["head"], Cc, spatial, softmax=bool(unet.sofmtax_output), out=probs_x0)
             # probs = theta_post_prob(xt, x0pred, t_); clamp(1e-12); sample / argmax / probs   (:209-224)
             if t > 1:
                 q = None
                 if self.q_noise is not None:
                     q = self.q_noise[step0 + i].to(dev, torch.float32).contiguous()
+                elif slab is not None and slab.world > 1:
+                    # depth slabs: every rank draws the noise field of the WHOLE volume from its (identically seeded)
+                    # generator and keeps its own rows -- the slabs then see different noise, and the same noise as an
+                    # unsplit run from the same generator state
+                    q = torch.empty((slab.world, B * V, Cc), dtype=torch.float32, device=dev).exponential_(1)[slab.rank].contiguous()
                 else:
                     q = torch.empty((B * V, Cc), dtype=torch.float32, device=dev).exponential_(1)
                 nxt = torch.empty_like(xt)
@@ -236,6 +252,11 @@ class DenoisingModel(nn.Module):
         B, Cc = xt.shape[:2]
         spatial = tuple(xt.shape[2:])
         V = int(math.prod(spatial))
+        if not unet.sofmtax_output:
+            raise NotImplementedError("the resident loop applies the head softmax in its fused per-voxel kernel; a network built with "
+                                      "softmax_output=False (raw head output fed to theta_post_prob) must use loop='interface'")
+        if not bool(((xt.amax(1) == 1) & (xt.sum(1) == 1)).all()):
+            raise ValueError("the resident loop keeps x_t as uint8 labels: x must be one-hot over dim 1 (use loop='interface' for soft x_t)")
         plan = unet.plan_for(B, spatial, context)
         if "context" in plan.inputs:
             plan.inputs["context"].copy_(unet._ctx_cl(context, B))
@@ -249,20 +270,67 @@ class DenoisingModel(nn.Module):
         n_cond = cond.shape[1] if cond is not None else 0
         cond_cl = ops.nchw_to_cl(cond, None, c_pad=8)[..., :n_cond].contiguous() if cond is not None else None
         slab = unet.engine.slab
-        vox_base = slab.rank * V if slab is not None else 0      # slabs are equal-sized, contiguous in depth
+        # global voxel index of this process' first voxel: slabs are equal-sized and contiguous in depth (one volume);
+        # sharded batches start at chain `chain_base` of the global batch
+        vox_base = slab.rank * V if slab is not None else self.chain_base * V
+        seed = self.philox_seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            if slab is not None and slab.world > 1:
+                seed = slab.broadcast_int(seed)          # one volume, one key
+        fused = bool(self.fuse_head and plan.fused_head is not None and self.q_noise is None)
+        if fused and self.use_cuda_graph:
+            plan.capture_body()
         return dict(plan=plan, xin=xin, lab_a=lab_a, lab_b=lab_b, cond_cl=cond_cl, n_cond=n_cond, B=B, C=Cc, V=V,
-                    spatial=spatial, vox_base=vox_base)
+                    spatial=spatial, vox_base=vox_base, seed=seed, fused_head=fused)
 
     def resident_step(self, st: dict, t: int, coef: Tensor, q: Optional[Tensor] = None, offset: int = 0):
         """One reverse step t -> t-1 (t > 1): UNet forward, then ONE fused kernel: softmax over the
         head logits + posterior + clamp + draw + next UNet input (one-hot | condition) in place."""
         plan = st["plan"]
         plan.inputs["t"].fill_(float(t))
+        if st.get("fused_head") and q is None:
+            plan.run_body()
+            self._launch_fused_head(st, coef, offset)
+            st["lab_a"], st["lab_b"] = st["lab_b"], st["lab_a"]
+            return
         plan.run()
         ops.cat_step_cl(plan.outputs["head"], st["lab_a"], coef, st["lab_b"], st["B"], st["V"], st["C"], mode=ops.CAT_SAMPLE,
-                        q=q, cond=st["cond_cl"], n_cond=st["n_cond"], next_x=st["xin"], seed=self.philox_seed, offset=offset,
+                        q=q, cond=st["cond_cl"], n_cond=st["n_cond"], next_x=st["xin"], seed=st["seed"], offset=offset,
                         vox_base=st["vox_base"])
         st["lab_a"], st["lab_b"] = st["lab_b"], st["lab_a"]
+
+    def _launch_fused_head(self, st: dict, coef: Tensor, offset: int):
+        """The head conv with softmax + posterior + clamp + draw + next-input write in its epilogue (gg_conv_args.cat)."""
+        import ctypes as C
+        from .. import _C
+        fa, cat = st["plan"].fused_head
+        cat.labels_in, cat.labels_out = st["lab_a"].data_ptr(), st["lab_b"].data_ptr()
+        cat.next_x = st["xin"].data_ptr()
+        cat.cond = st["cond_cl"].data_ptr() if st["cond_cl"] is not None else None
+        cat.coef = coef.data_ptr()
+        cat.C, cat.n_cond, cat.Cin_pad, cat.mode = st["C"], st["n_cond"], st["xin"].shape[-1], ops.CAT_SAMPLE
+        cat.clamp_min, cat.seed, cat.offset, cat.vox_base = 1e-12, int(st["seed"]), int(offset), int(st["vox_base"])
+        ref = C.byref(fa)
+        _C.check(_C.lib().gg_conv_fwd(ref, _C.stream()), "gg_conv_fwd (sampler epilogue)")
+        return (ref,)
+
+    def launches_per_step(self, plan) -> int:
+        """libguidegen_sm100 launches of one resident step."""
+        return plan.num_launches if (self.fuse_head and plan.fused_head is not None and self.q_noise is None) else plan.num_launches + 1
+
+    def resident_tail_launcher(self, st: dict, coef: Tensor, offset: int = 0):
+        """For per-launch timing (bench.py): (plan steps to run, [(name, launch)]) that together make one resident step."""
+        plan = st["plan"]
+        if st.get("fused_head"):
+            return plan.steps[:-1], [("gg_conv_fwd", lambda: self._launch_fused_head(st, coef, offset))]
+
+        def cat_step():
+            ops.cat_step_cl(plan.outputs["head"], st["lab_a"], coef, st["lab_b"], st["B"], st["V"], st["C"], mode=ops.CAT_SAMPLE,
+                            cond=st["cond_cl"], n_cond=st["n_cond"], next_x=st["xin"], seed=st["seed"], offset=offset,
+                            vox_base=st["vox_base"])
+            return ()
+        return plan.steps, [("gg_cat_step_cl", cat_step)]
 
     def resident_end(self, st: dict) -> Tensor:
         return ops.cl_to_nchw(st["xin"], st["C"], st["spatial"])

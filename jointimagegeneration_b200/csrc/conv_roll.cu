@@ -27,15 +27,34 @@
 #include <vector>
 
 #include "halo_common.cuh"
+#include "cat_row.cuh"
 
 namespace gg {
 
-constexpr int R_MAX_SA = 4, R_MAX_SB = 8;
+constexpr int R_MAX_SA = 6, R_MAX_SB = 8;
 constexpr int R_THREADS = 352;      // warps 0, 1, 6 = producers / MMA; warps 2..5 drain brick 0, warps 7..10 drain brick 1
-constexpr int R_THREADS_XF = 480;   // + warps 11..14: GroupNorm/SiLU transform of the landed halo planes
+// XFORM adds warps 11..: GroupNorm/SiLU transform of the landed halo planes (RollThreads below)
+// Transform warps.  Wide outputs (3 x 64 stacked columns) spend ~3500 clocks of MMAs per plane and four warps keep up;
+// the 16-column head conv (64 -> 12 classes) spends ~900, so its planes wait for the transform: eight warps there.
+template <int BNS> struct XfWarps { static constexpr int value = BNS == 16 ? 8 : 4; };
+template <int BNS, bool XFORM> struct RollThreads { static constexpr int value = XFORM ? R_THREADS + 32 * XfWarps<BNS>::value : R_THREADS; };
 constexpr int R_STAGE_BYTES = 16384; // 128 rows x 128 B output / residual staging tile
 constexpr int XB = 4;               // rows a transform thread handles per batch (6 measured the same)
 constexpr int R_SS_BYTES = 4096;    // (scale, shift) table: up to 512 channels over all sources
+
+// Tuning knobs (environment), read ONCE at first use: the launch path itself never calls getenv.
+struct RollKnobs {
+    int no_tma_epi, g, sa, dbg, skip_first;
+    RollKnobs() {
+        auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+        no_tma_epi = getenv("GG_ROLL_NO_TMA_EPI") != nullptr;
+        g = geti("GG_ROLL_G", 0);
+        sa = geti("GG_ROLL_SA", 0);
+        dbg = getenv("GG_ROLL_DBG") != nullptr;
+        skip_first = geti("GG_ROLL_SKIP_FIRST", 1);
+    }
+};
+static const RollKnobs& roll_knobs() { static const RollKnobs k; return k; }
 
 struct RollSeg {
     int nchunks, centre;
@@ -57,6 +76,7 @@ struct alignas(64) RollParams {
     int tma_epi;                   // bf16 64-channel outputs leave (and residuals arrive) through a staging tile + TMA
     RollSeg seg[H_MAX_SEGS];
     int nseg, BNs, SA, SB;
+    int order[H_MAX_SEGS];         // sequence in which a step walks the sources (1x1x1 sources first, see conv_roll_fwd)
     uint32_t a_stage_bytes, b_stage_bytes, b_unit_bytes;
     int No, Do, Ho, Wo;
     int thp, twp, nsd, Lseg, total_items;      // brick pairs along h / w, depth segments and their length
@@ -73,6 +93,17 @@ struct alignas(64) RollParams {
     int gn_chunk_base, gn_nchunks_total;
     int ss_stride, xf_silu, z_lo, z_hi, ss_entries;      // XFORM (fused GroupNorm + SiLU on the input planes)
     unsigned long long* dbg;       // tuning aid (GG_ROLL_DBG=1): per leader CTA, clocks the MMA issuer spent in each wait
+    // sampler epilogue (gg_conv_args.cat, 16-column head conv only): the accumulator row of a voxel holds all its class
+    // logits, so softmax + posterior + clamp + draw + next-input row happen here and no logits tensor is written
+    int cat_on, cat_C, cat_ncond, cat_cin_pad;
+    const uint8_t* cat_lab_in;
+    uint8_t* cat_lab_out;
+    uint16_t* cat_next_x;
+    const uint16_t* cat_cond;
+    const float* cat_coef;
+    float cat_clamp;
+    unsigned long long cat_seed, cat_offset;
+    long long cat_vox_base;
 };
 
 __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
@@ -182,7 +213,8 @@ __device__ __forceinline__ uint32_t xf_pair(uint32_t w, float4 q, bool silu) {
 }
 
 template <int G, bool STATS, int BNS, bool XFORM>
-__global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll_kernel(const __grid_constant__ RollParams p) {
+__global__ void __launch_bounds__(RollThreads<BNS, XFORM>::value, 1) conv_roll_kernel(const __grid_constant__ RollParams p) {
+    constexpr int XW = XfWarps<BNS>::value, XT = 32 * XW;        // transform warps / threads
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -212,7 +244,7 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 8); }
+            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 2 * XW); }
             for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&step_done[i], 1); mbar_init(&slot_free[i], 8); mbar_init(&res_full[i], 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -238,7 +270,8 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
             for (int t = 0; t < it.L + 2; ++t)
                 for (int wi = 0; wi < 2; ++wi) {
                     const int h0 = (2 * it.ihp + wi) * H_BH, z = it.d0 - 1 + t;
-                    for (int s = 0; s < p.nseg; ++s) {
+                    for (int si = 0; si < p.nseg; ++si) {
+                        const int s = p.order[si];
                         const RollSeg sg = p.seg[s];
                         if (sg.centre && (t == 0 || t == it.L + 1)) continue;     // would only feed planes outside the segment
                         for (int j = 0; j < sg.nchunks; ++j) {
@@ -275,7 +308,8 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
             const RollItem it = roll_item(p, item);
             for (int t = 0; t < it.L + 2; ++t)
                 for (int wi = 0; wi < 2; ++wi)
-                    for (int s = 0; s < p.nseg; ++s) {
+                    for (int si = 0; si < p.nseg; ++si) {
+                        const int s = p.order[si];
                         const RollSeg sg = p.seg[s];
                         if (sg.centre && (t == 0 || t == it.L + 1)) continue;
                         for (int j = 0; j < sg.nchunks; ++j) {
@@ -336,7 +370,8 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
                         phf[wi] ^= 1u;
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)(wi * 3 * BNs);
-                        for (int s = 0; s < p.nseg; ++s) {
+                        for (int si = 0; si < p.nseg; ++si) {
+                            const int s = p.order[si];
                             const RollSeg sg = p.seg[s];
                             if (sg.centre && (t == 0 || t == it.L + 1)) continue;
                             const uint64_t a_tmpl = make_sw128_desc_sbo(0, (uint32_t)sg.pitch * 128u);
@@ -407,7 +442,7 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
         // ================================================================ transform (warps 11..14): GroupNorm (+ SiLU) in place
         // on each landed halo plane.  Rows are 128 B = 64 channels, SWIZZLE_128B: the 16-byte chunk at physical
         // slot jp of stage row r holds channels 8 (jp ^ (r & 7)) .. +7.  Rows outside the tensor stay zero.
-        const int xt = (int)threadIdx.x - R_THREADS;        // 0..127
+        const int xt = (int)threadIdx.x - R_THREADS;        // 0..XT-1
         int sa = 0, cur_n = -1;
         uint32_t pha = 0;
         const bool silu = p.xf_silu != 0;
@@ -415,25 +450,27 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
         for (int item = item0; item < p.total_items; item += istep) {
             const RollItem it = roll_item(p, item);
             if (it.n != cur_n) {        // (scale, shift) of this sample; uniform over the four warps
-                asm volatile("bar.sync 3, 128;" ::: "memory");
-                for (int s = 0; s < p.nseg; ++s) {
+                asm volatile("bar.sync 3, %0;" ::"n"(XT) : "memory");
+                for (int si = 0; si < p.nseg; ++si) {
+                    const int s = p.order[si];
                     const RollSeg sg = p.seg[s];
                     if (sg.ss_off < 0) continue;
                     const float4* src = reinterpret_cast<const float4*>(sg.ss + (long long)it.n * p.ss_stride);
                     const float k = silu ? 0.5f : 1.f;
-                    for (int c = xt; c < sg.nchunks * (BK / 2); c += 128) {
+                    for (int c = xt; c < sg.nchunks * (BK / 2); c += XT) {
                         const float4 v = 2 * c < sg.C ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);      // (s0, b0, s1, b1)
                         ss_tab[(sg.ss_off >> 1) + c] = make_float4(k * v.x, k * v.z, k * v.y, k * v.w);
                     }
                 }
-                asm volatile("bar.sync 3, 128;" ::: "memory");
+                asm volatile("bar.sync 3, %0;" ::"n"(XT) : "memory");
                 cur_n = it.n;
             }
             const int w0 = (2 * it.iwp + rank) * H_BW;
             for (int t = 0; t < it.L + 2; ++t)
                 for (int wi = 0; wi < 2; ++wi) {
                     const int h0 = (2 * it.ihp + wi) * H_BH, z = it.d0 - 1 + t;
-                    for (int s = 0; s < p.nseg; ++s) {
+                    for (int si = 0; si < p.nseg; ++si) {
+                        const int s = p.order[si];
                         const RollSeg sg = p.seg[s];
                         if (sg.centre && (t == 0 || t == it.L + 1)) continue;
                         for (int j = 0; j < sg.nchunks; ++j) {
@@ -451,13 +488,13 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
                                 // XB rows per batch, loads first: a lone warp per scheduler needs the ILP (a per-row
                                 // branch would serialise LDS -> FMA -> MUFU -> FMA -> STS chains)
 #pragma unroll 1
-                                for (int r0 = xt >> 3; r0 < nrow; r0 += 16 * XB) {
+                                for (int r0 = xt >> 3; r0 < nrow; r0 += (XT / 8) * XB) {
                                     uint4 v[XB];
                                     uint4* ptr[XB];
                                     bool ok[XB];
 #pragma unroll
                                     for (int u = 0; u < XB; ++u) {
-                                        const int r = r0 + 16 * u, rc = min(r, nrow - 1);
+                                        const int r = r0 + (XT / 8) * u, rc = min(r, nrow - 1);
                                         const int hh = (int)(((uint32_t)rc * (uint32_t)sg.inv_pitch) >> 16), ww = rc - hh * sg.pitch;    // rc < 2^10
                                         const int gh = h0 + sg.oh + hh, gw = w0 + sg.ow + ww;
                                         ok[u] = r < nrow && gh >= 0 && gh < p.Ho && gw >= 0 && gw < p.Wo;      // stride 1: input extent = output extent
@@ -506,6 +543,7 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
         int cur_n = -1;
         float4 st = make_float4(0.f, 0.f, 0.f, 0.f);       // STATS: (sum, sum sq) of columns 2 lane, 2 lane + 1 over this warp's rows
         int stat_n = -1;
+        CatRowCoef cat_cf = {};
         auto flush = [&](int n) {        // one partial row per (CTA, epilogue warp): written once per sample, fixed order
             *reinterpret_cast<float4*>(p.gn_partial + (((long long)n * p.gn_nchunks_total + p.gn_chunk_base + (long long)blockIdx.x * 8 + wi * 4 + q) * 64) * 2 +
                                        4 * lane) = st;
@@ -526,6 +564,9 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + wi) : "memory");
                 cur_n = n;
+                if constexpr (BNS == 16) {
+                    if (p.cat_on) cat_cf = cat_row_coef(__ldg(p.cat_coef + 2 * n), __ldg(p.cat_coef + 2 * n + 1), p.cat_C);
+                }
             }
             if constexpr (STATS) {
                 if (n != stat_n) {
@@ -562,6 +603,10 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
                             rr[g] = (p.residual != nullptr && valid && 8 * g < p.Cout8) ? ldg_nc_u4(p.residual + lin * p.res_stride + 8 * g)
                                                                                         : make_uint4(0, 0, 0, 0);
                     }
+                    int cat_lab = 0;
+                    if constexpr (BNS == 16) {      // x_t's label of this voxel: requested before the accumulator is waited for
+                        if (p.cat_on && valid) cat_lab = (int)__ldg(p.cat_lab_in + lin);
+                    }
                     mbar_wait(&step_done[wi], phd);
                     phd ^= 1u;
                     tc_fence_after();
@@ -595,6 +640,53 @@ __global__ void __launch_bounds__(XFORM ? R_THREADS_XF : R_THREADS, 1) conv_roll
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic writes -> TMA store reads
                             asm volatile("bar.sync %0, 128;" ::"r"(1 + wi) : "memory");
                             if (etid == 0) tma_store_5d(&p.ymap, stage, 0, wb, hb, d, n);
+                        } else if (BNS == 16 && p.cat_on) {
+                            if constexpr (BNS == 16) {
+                                // ---- sampler epilogue: this thread's 16 accumulator columns are the class logits of voxel `lin`
+                                float lg[16];
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) lg[c] = __uint_as_float(r[c]) + bvec[c] + 0.f;     // as finish_row (no residual)
+                                const unsigned long long gv = (unsigned long long)lin + (unsigned long long)p.cat_vox_base;
+                                const unsigned long long gq = gv >> 2;             // one Philox call per group of 4 voxels (pervoxel.cu)
+                                const uint4 rr4 = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), (uint32_t)p.cat_offset,
+                                                                           (uint32_t)(p.cat_offset >> 32)),
+                                                                make_uint2((uint32_t)p.cat_seed, (uint32_t)(p.cat_seed >> 32)));
+                                const uint32_t sel = (uint32_t)gv & 3u;
+                                const uint32_t rbits = sel == 0 ? rr4.x : sel == 1 ? rr4.y : sel == 2 ? rr4.z : rr4.w;
+                                const int bi = cat_row_draw(lg, p.cat_C, cat_lab, cat_cf, p.cat_clamp, rbits);
+                                // labels: the 8 lanes of a brick row hold 8 w-consecutive voxels -> one 8-byte store per row
+                                uint32_t pk = (uint32_t)bi;
+                                pk |= __shfl_down_sync(0xffffffffu, pk, 1) << 8;
+                                pk |= __shfl_down_sync(0xffffffffu, pk, 2) << 16;
+                                const uint32_t hi = __shfl_down_sync(0xffffffffu, pk, 4);
+                                const bool row_full = (2 * it.iwp + rank) * H_BW + H_BW <= p.Wo && (p.Wo & 7) == 0;
+                                if (row_full) {
+                                    if (rw == 0 && valid) *reinterpret_cast<uint2*>(p.cat_lab_out + lin) = make_uint2(pk, hi);
+                                } else if (valid) {
+                                    p.cat_lab_out[lin] = (uint8_t)bi;
+                                }
+                                if (valid && p.cat_next_x != nullptr) {
+                                    // next UNet input row: one-hot(C) | condition channel(s) | zero padding, bf16
+                                    uint16_t* rowp = p.cat_next_x + lin * p.cat_cin_pad;
+                                    for (int c0 = 0; c0 < p.cat_cin_pad; c0 += 8) {
+                                        uint32_t wv[4];
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const int c = c0 + 2 * e;
+                                            uint32_t bits = (c == (bi & ~1)) ? ((bi & 1) ? 0x3F800000u : 0x3F80u) : 0u;
+                                            if (c + 1 >= p.cat_C && p.cat_cond != nullptr) {
+#pragma unroll
+                                                for (int z = 0; z < 2; ++z) {
+                                                    const int cc = c + z - p.cat_C;
+                                                    if (cc >= 0 && cc < p.cat_ncond) bits |= (uint32_t)p.cat_cond[lin * p.cat_ncond + cc] << (16 * z);
+                                                }
+                                            }
+                                            wv[e] = bits;
+                                        }
+                                        *reinterpret_cast<uint4*>(rowp + c0) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                                    }
+                                }
+                            }
                         } else {
                             const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw;
                             void* y_row = p.y_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.y) + yoff)
@@ -642,7 +734,7 @@ static int launch_roll(const RollParams& p, int grid, size_t smem, cudaStream_t 
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(XFORM ? R_THREADS_XF : R_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(RollThreads<BNS, XFORM>::value); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -739,7 +831,8 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
     p.tma_epi = (g.BNs == 64 && !a->y_is_f32 && p.Cout8 == 64 && aligned(a->y, 16) && a->y_sw % 8 == 0 && a->y_sh % 8 == 0 &&
                  a->y_sd % 8 == 0 && a->y_sn % 8 == 0 && (a->residual == nullptr || (aligned(a->residual, 16) && a->res_stride % 8 == 0)))
                     ? 1 : 0;
-    if (getenv("GG_ROLL_NO_TMA_EPI")) p.tma_epi = 0;       // tuning knob
+    const RollKnobs& knobs = roll_knobs();
+    if (knobs.no_tma_epi) p.tma_epi = 0;
     if (p.tma_epi) {
         const int64_t dim[4] = {a->Wo, a->Ho, a->Do, a->N};
         const int box[4] = {H_BW, H_BH, 1, 1};
@@ -762,8 +855,22 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
     bool has_centre = false;
     for (int s = 0; s < a->nsrc; ++s) has_centre = has_centre || a->src[s].centre_only;
     int G = has_centre ? 1 : 3;
-    if (const char* e = getenv("GG_ROLL_G")) { const int v = atoi(e); if (v == 1 || v == 3) G = v; }     // tuning knob
-    int SA = (xform || has_centre) ? 4 : 3;
+    if (knobs.g == 1 || knobs.g == 3) G = knobs.g;
+    // Order of the sources within a step.  With the 1x1x1 sources LAST their planes sit in the ring behind the step's
+    // big plane: the ring is full while that plane's 36 MMAs run, nothing of the next step can be requested, and the
+    // tensor core then waits a whole TMA latency (+ transform) per step (measured: tensor pipe 37-42 % active).  With
+    // them FIRST and five plane stages, their stages drain within a few hundred clocks and the whole next step (its
+    // small planes and its big plane) is in flight while the current big plane is being multiplied.
+    const bool skip_first = has_centre && knobs.skip_first != 0;
+    {
+        int n = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int s2 = 0; s2 < a->nsrc; ++s2) {
+                const bool c = a->src[s2].centre_only != 0;
+                if (skip_first ? (c == (pass == 0)) : (pass == 0)) p.order[n++] = s2;
+            }
+    }
+    int SA = skip_first ? 5 : (xform || has_centre) ? 4 : 3;
     int SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes);
     if (SB < 3 && SA > 3) { SA = 3; SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes); }
     GG_REQUIRE(SB >= 2, GG_ERR_UNSUPPORTED);
@@ -771,8 +878,8 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
         SA = std::min(R_MAX_SA, (avail - R_MAX_SB * G * tap_bytes) / (int)p.a_stage_bytes);
         SB = R_MAX_SB;
     }
-    if (const char* e = getenv("GG_ROLL_SA")) {       // tuning knob: plane stages (weight stages take the rest)
-        const int sa = atoi(e), sb = (avail - sa * (int)p.a_stage_bytes) / (G * tap_bytes);
+    if (knobs.sa > 0) {       // plane stages (weight stages take the rest)
+        const int sa = knobs.sa, sb = (avail - sa * (int)p.a_stage_bytes) / (G * tap_bytes);
         if (sa >= 2 && sa <= R_MAX_SA && sb >= 2) { SA = sa; SB = std::min(sb, R_MAX_SB); }
     }
     p.b_stage_bytes = (uint32_t)(G * tap_bytes);
@@ -784,9 +891,24 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.res_stride = a->res_stride;
     p.y = a->y; p.y_sn = a->y_sn; p.y_sd = a->y_sd; p.y_sh = a->y_sh; p.y_sw = a->y_sw; p.y_is_f32 = a->y_is_f32;
 
+    if (a->cat != nullptr) {
+        const gg_cat_epilogue& c = *a->cat;
+        GG_REQUIRE(g.BNs == 16 && a->gn_partial == nullptr && a->residual == nullptr, GG_ERR_UNSUPPORTED);
+        GG_REQUIRE(c.labels_in && c.labels_out && c.coef && c.C >= 2 && c.C <= 16 && c.C <= a->Cout && c.mode == GG_CAT_SAMPLE, GG_ERR_BAD_ARG);
+        GG_REQUIRE(aligned(c.labels_out, 8) && c.vox_base % 4 == 0 && ((int64_t)a->Do * a->Ho * a->Wo) % 4 == 0, GG_ERR_ALIGNMENT);
+        if (c.next_x) GG_REQUIRE(c.Cin_pad % 8 == 0 && c.Cin_pad >= c.C + c.n_cond && aligned(c.next_x, 16), GG_ERR_BAD_ARG);
+        p.cat_on = 1; p.cat_C = c.C; p.cat_ncond = c.n_cond; p.cat_cin_pad = c.Cin_pad;
+        p.cat_lab_in = c.labels_in; p.cat_lab_out = c.labels_out;
+        p.cat_next_x = reinterpret_cast<uint16_t*>(c.next_x); p.cat_cond = reinterpret_cast<const uint16_t*>(c.cond);
+        p.cat_coef = c.coef; p.cat_clamp = c.clamp_min; p.cat_seed = c.seed; p.cat_offset = c.offset; p.cat_vox_base = c.vox_base;
+    }
+
     static unsigned long long* dbg_buf = nullptr;
-    const bool dbg = getenv("GG_ROLL_DBG") != nullptr;
+    const bool dbg = knobs.dbg != 0;
     if (dbg) {
+        // the debug path allocates and synchronises: refuse it while the stream is being captured into a CUDA graph
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return GG_ERR_UNSUPPORTED;
         if (!dbg_buf && cudaMalloc(&dbg_buf, 4096 * sizeof(unsigned long long)) != cudaSuccess) return GG_ERR_DRIVER;
         cudaMemsetAsync(dbg_buf, 0, 4096 * sizeof(unsigned long long), stream);
         p.dbg = dbg_buf;

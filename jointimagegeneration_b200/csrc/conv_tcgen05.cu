@@ -525,6 +525,7 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
     if (a->bias) GG_REQUIRE(aligned(a->bias, 16), GG_ERR_ALIGNMENT);
     if (a->emb) GG_REQUIRE(aligned(a->emb, 16) && a->emb_stride % 4 == 0, GG_ERR_ALIGNMENT);
     if (!encode_fn()) return GG_ERR_DRIVER;
+    if (a->cat != nullptr) GG_REQUIRE(a->algo == 4, GG_ERR_UNSUPPORTED);      // sampler epilogue: depth-rolling kernel only
     if (a->algo >= 1 && a->algo <= 3) return conv_halo_fwd(a, as_stream(stream));
     if (a->algo == 4) return conv_roll_fwd(a, as_stream(stream));
 

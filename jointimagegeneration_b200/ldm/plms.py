@@ -108,6 +108,7 @@ class PLMSSampler(DDIMSampler):
         # sigma = 0 (eta = 0): the noise term sigma * noise_like(...) * temperature of :208 vanishes exactly
         if len(old_eps) == 0:
             # first step (:219-223): a DDIM step with e_t, a second prediction at (x_prev, t_next), then the average
+            self.noise_fn(x.shape, x.device, repeat_noise)       # drawn (and multiplied by sigma = 0) by the reference: :208
             x_prev0, _ = ops.ddim_update(x, e_t, coef, None, temperature, e_uncond=e_u, guidance_scale=unconditional_guidance_scale)
             e_next, e_un = model_output(x_prev0, t_next)
             if guided:
@@ -117,5 +118,8 @@ class PLMSSampler(DDIMSampler):
             order = min(len(old_eps), 3)
             e_cur, e_prime = ops.plms_eps(e_t, old_eps[::-1][:order], order, e_uncond=e_u,
                                           guidance_scale=unconditional_guidance_scale)
+        # the reference draws noise_like(x.shape) in every get_x_prev_and_pred_x0 call (:208) although sigma = 0: keep
+        # torch's RNG stream in the same position so that seeded runs interleave with other draws as the reference's do
+        self.noise_fn(x.shape, x.device, repeat_noise)
         x_prev, pred_x0 = ops.ddim_update(x, e_prime, coef, None, temperature)
         return x_prev, pred_x0, e_cur

@@ -47,15 +47,14 @@ def gather_batch(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
 
 
 def slab_ranges(depth: int, world: int, multiple: int = 16) -> List[Tuple[int, int]]:
-    """Depth slabs for a single large volume (config 5): contiguous planes, each slab a multiple of
-    `multiple` planes (the UNet halves D four times) while planes remain."""
-    units = depth // multiple
-    assert units * multiple == depth, f"depth {depth} must be a multiple of {multiple}"
-    out = []
-    for r in range(world):
-        lo, hi = shard_range(units, r, world)
-        out.append((lo * multiple, hi * multiple))
-    return out
+    """Depth slabs for a single large volume (config 5): `world` EQUAL contiguous slabs, each a multiple of `multiple`
+    planes (the UNet halves D four times).  Equal because the GroupNorm combine (S * R), the key/value gather
+    (all_gather_into_tensor) and the global voxel index of the Philox counter (rank * V) all assume rank r holds
+    planes [r D/R, (r+1) D/R); an uneven split would hang or give silently wrong statistics, so it is refused."""
+    if depth % (multiple * world) != 0:
+        raise ValueError(f"depth {depth} does not split into {world} equal slabs that are multiples of {multiple} planes")
+    per = depth // world
+    return [(r * per, (r + 1) * per) for r in range(world)]
 
 
 def global_minmax(x: torch.Tensor, group=None) -> Tuple[float, float]:
@@ -118,6 +117,14 @@ class SlabComm:
     def _peer(self, group_rank: int) -> int:
         return group_rank if self.group is None else dist.get_global_rank(self.group, group_rank)
 
+    def broadcast_int(self, value: int) -> int:
+        """rank 0's value on every rank (host-side scalar: the per-call Philox key of the sampler loop)."""
+        if self.world == 1:
+            return int(value)
+        box = [int(value)]
+        dist.broadcast_object_list(box, src=self._peer(0), group=self.group)
+        return int(box[0])
+
     def all_gather(self, out: torch.Tensor, inp: torch.Tensor):
         """out (flattened) = concatenation over ranks of inp (flattened)."""
         self.n_gathers += 1
@@ -125,3 +132,86 @@ class SlabComm:
             out.view(-1).copy_(inp.reshape(-1))
             return
         dist.all_gather_into_tensor(out.view(-1), inp.reshape(-1), group=self.group)
+
+
+class _LocalComm:
+    """One virtual rank of a LocalSlabGroup: carries (rank, world) and the counters of SlabComm; its collectives are
+    executed by LocalSlabGroup.run, which sees the buffers of every rank."""
+
+    def __init__(self, group, rank: int):
+        self.group_obj, self.rank, self.world = group, rank, group.world
+        self.bytes_sent = self.n_exchanges = self.n_gathers = 0
+
+    def exchange_halo(self, *a, **k):
+        raise RuntimeError("virtual rank: run the plans of all ranks through LocalSlabGroup.run")
+
+    all_gather = exchange_halo
+
+    def broadcast_int(self, value: int) -> int:
+        return int(value)
+
+
+class LocalSlabGroup:
+    """R VIRTUAL ranks of the depth-slab decomposition on ONE device: the R plans (built with comms[r] as their
+    SlabComm) are executed in lock step on the current stream and every collective step is carried out directly on
+    the R sets of buffers.  The plans, kernels, halo layout, GroupNorm combine, K/V gather and voxel indexing are
+    exactly those of the multi-GPU run -- only the transport differs -- so slab parity at world 2/4/8 can be checked
+    on a single GPU (tests/test_gpu_models.py) and a volume larger than one plan's arena can be walked slab by slab."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self.comms = [_LocalComm(self, r) for r in range(world)]
+
+    def run(self, plans):
+        from . import _C
+        R = self.world
+        assert len(plans) == R and len({len(p.steps) for p in plans}) == 1, "virtual ranks must hold identical plans"
+        s = _C.stream()
+        for i in range(len(plans[0].steps)):
+            fn0 = plans[0].steps[i][0]
+            if not hasattr(fn0, "fn"):
+                for p in plans:
+                    fn, args = p.steps[i]
+                    st = fn(*args, s)
+                    if st != 0:
+                        _C.check(st, fn.__name__)
+                continue
+            name = fn0.fn.__name__
+            argv = [p.steps[i][1] for p in plans]
+            assert all(p.steps[i][0].fn.__name__ == name for p in plans)
+            if name == "exchange_halo":
+                self._exchange(argv)
+            elif name == "all_gather":
+                self._gather(argv)
+            else:
+                raise NotImplementedError(name)
+
+    def _exchange(self, argv):
+        R = self.world
+        for r in range(R):
+            t, lead, depth, need_lo, need_hi = argv[r]
+            c = self.comms[r]
+            c.n_exchanges += 1
+            if need_lo:
+                if r > 0:
+                    tp, lp, dp = argv[r - 1][:3]
+                    t[0, lead - 1].copy_(tp[0, lp + dp - 1])
+                    c.bytes_sent += t[0, lead].numel() * t.element_size()
+                else:
+                    t[0, lead - 1].zero_()
+            if need_hi:
+                if r < R - 1:
+                    tn, ln = argv[r + 1][:2]
+                    t[0, lead + depth].copy_(tn[0, ln])
+                    c.bytes_sent += t[0, lead].numel() * t.element_size()
+                else:
+                    t[0, lead + depth].zero_()
+
+    def _gather(self, argv):
+        R = self.world
+        for r in range(R):
+            out = argv[r][0].view(-1)
+            n = argv[r][1].numel()
+            self.comms[r].n_gathers += 1
+            for q in range(R):
+                out[q * n:(q + 1) * n].copy_(argv[q][1].reshape(-1))

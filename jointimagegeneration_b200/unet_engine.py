@@ -114,8 +114,11 @@ class Plan:
         self.inputs: Dict[str, torch.Tensor] = {}
         self.outputs: Dict[str, torch.Tensor] = {}
         self.graph = None
+        self.graph_body = None
         self.arena_bytes = 0
         self.flops = 0        # 2 * MACs actually issued by conv / attention launches
+        # (gg_conv_args copy, gg_cat_epilogue) of the head conv with the sampler in its epilogue (CCDM resident loop), or None
+        self.fused_head = None
 
     def add(self, fn, *args):
         self.steps.append((fn, args))
@@ -137,6 +140,33 @@ class Plan:
             st = fn(*args, s)
             if st != 0:
                 _C.check(st, fn.__name__)
+
+    def run_body(self):
+        """Everything but the last step (the head conv): the caller launches the head itself -- with the sampler epilogue
+        whose per-step arguments (coefficients, Philox offset, label buffers) change from step to step."""
+        if self.graph_body is not None:
+            self.graph_body.replay()
+            return
+        s = _C.stream()
+        for fn, args in self.steps[:-1]:
+            if isinstance(fn, _PyStep):
+                fn.fn(*args)
+                continue
+            st = fn(*args, s)
+            if st != 0:
+                _C.check(st, fn.__name__)
+
+    def capture_body(self):
+        if self.has_py or self.graph_body is not None:
+            return
+        self.run_body()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            s = _C.stream()
+            for fn, args in self.steps[:-1]:
+                _C.check(fn(*args, s), fn.__name__)
+        self.graph_body = g
 
     def capture(self):
         """Capture the forward into a CUDA graph (after one eager warm-up run).  Plans with collectives
@@ -407,6 +437,13 @@ class UNetEngine:
         if algo == 0 and self.use_split_k and a.gn_partial is None:
             # few output tiles, long reduction (low-resolution layers): spread K ranges over the idle SMs
             tiles, nkb = int(self.lib.gg_conv_num_tiles(C.byref(a))), kexp // ops.BLOCK_K
+            if self.slab is not None:
+                # the split factor fixes the summation order of the reduction: take the decision the UNSPLIT plan takes
+                # for this layer (global depth, no halo planes), so that slab results differ from the unsplit ones only
+                # through the order in which GroupNorm partial sums are combined
+                g = _C.ConvArgs.from_buffer_copy(a)
+                g.D, g.Do = D * self.slab.world, out_spatial[0] * self.slab.world
+                tiles = int(self.lib.gg_conv_num_tiles(C.byref(g)))
             S = min(16, self.num_sms // max(tiles, 1), nkb // 6)
             if tiles * 2 <= self.num_sms and S >= 2:
                 ws = ar.alloc((S, N * int(math.prod(kernel_out_sp)), cout8), torch.float32)
@@ -759,6 +796,14 @@ class UNetEngine:
                              dims=oc.dims, bias=_C.ptr(b), f32_out=f32_head)
         self._free(ar, h)
         plan.outputs["head"] = head.interior
+        ha = plan.steps[-1][1][0]._obj
+        if kind_ccdm_head(m) and int(ha.algo) == 4 and oc.out_channels <= 16 and f32_head and N * int(math.prod(sp3)) % 4 == 0:
+            # the same launch with the categorical sampler in its epilogue (gg_conv_args.cat): used by the resident loop
+            cat = _C.CatEpilogue()
+            fa = _C.ConvArgs.from_buffer_copy(ha)
+            fa.cat = C.pointer(cat)
+            plan.fused_head = (fa, cat)
+            plan.keep.append((fa, cat))
         plan.keep.extend([emb_all, emb, e1, temb])
         plan.keep.append(ar.stores)      # kernels hold raw pointers into these: they must outlive the plan
         plan.arena_bytes = ar.total
@@ -769,6 +814,11 @@ class UNetEngine:
         if key not in self.plans:
             self.plans[key] = self.build_plan(N, tuple(spatial), in_ch_pad, ctx_shape)
         return self.plans[key]
+
+
+def kind_ccdm_head(m) -> bool:
+    """The sampler epilogue applies to the CCDM network (softmax head over classes, unet.py:715-721), dims 3."""
+    return bool(getattr(m, "sofmtax_output", False)) and getattr(m, "dims", 0) == 3
 
 
 def _fold_upsample_weight(w: torch.Tensor, dims: int, parity) -> torch.Tensor:

@@ -71,7 +71,7 @@ def theta_post_prob_literal(alphas: Tensor, cumalphas: Tensor, num_classes: int,
     cumalphas_tm1 = cumalphas[t - 1][(...,) + (None,) * (nsp + 2)].clone()
     alphas_t[t == 0] = 0.0
     cumalphas_tm1[t == 0] = 1.0
-    x0 = torch.eye(num_classes)[(None, slice(None), slice(None)) + (None,) * nsp]
+    x0 = torch.eye(num_classes, device=xt.device)[(None, slice(None), slice(None)) + (None,) * nsp]
     theta_xt_xtm1 = alphas_t * xt + (1 - alphas_t) / num_classes
     theta_xtm1_x0 = cumalphas_tm1 * x0 + (1 - cumalphas_tm1) / num_classes
     aux = theta_xt_xtm1[:, :, None] * theta_xtm1_x0

@@ -1,15 +1,14 @@
 """Parity at BASELINE config 2's FULL per-sample size (CCDM `params.yml` network, 12 classes, 64 x 128 x 128 voxels).
 
-The CPU oracle cannot finish a forward at this size in test time, so the checks here are the size-independent
-properties of the path, plus a same-GPU fp32 torch restatement for the floating-point per-voxel kernel:
-
-* the network output is a probability vector per voxel (finite, >= 0, sums to 1);
-* two runs give bit-identical results (fixed summation orders, no atomics in the statistics);
-* samples do not interact (GroupNorm / attention are per sample): sample 0 of a batch of two equals the same volume
-  run alone, up to the summation order of the GroupNorm partial rows;
-* the kernel choices agree: depth-rolling conv with fused GroupNorm == same conv behind a separate gn_apply, bit for
-  bit; the halo-padded depth-slab layout (world size 1) reproduces the plain plan to rounding level, uniformly in depth;
-* the per-voxel posterior + draw kernel on the full [B, 12, 64, 128, 128] tensors equals a torch fp32 evaluation of
+* ONE full-size sample through the GPU network and through the fp32 CPU oracle of the reference forward
+  (oracle.nets.unet_forward; ~5-20 s of CPU time): probabilities within the bf16-network tolerance (rel-to-max <= 3e-2,
+  PSNR >= 40 dB), first-step labels for the same injected noise >= 0.97 equal, and BIT-EXACT labels when the per-voxel
+  kernel is fed the oracle's own probabilities (test_cfg2_full_size_forward_and_first_step_vs_oracle);
+* size-independent properties of the path: the network output is a probability vector per voxel; two runs give
+  bit-identical results (fixed summation orders, no atomics in the statistics); samples do not interact (GroupNorm /
+  attention are per sample); the kernel choices agree (depth-rolling conv with fused GroupNorm == same conv behind a
+  separate gn_apply, bit for bit; the halo-padded depth-slab layout at world size 1 reproduces the plain plan);
+* the per-voxel posterior + draw kernel on full [B, 12, 64, 128, 128] tensors equals a torch fp32 evaluation of
   theta_post_prob (diffusion_denoising.py:105-139) on the same GPU, and its draw is the arg-max of p / q
   (one_hot_categorical.py:25-50 with torch.multinomial == argmax(p / q), q ~ Exp(1));
 * the resident sampler loop is reproducible for a fixed Philox seed and keeps every class reachable.
@@ -30,6 +29,42 @@ def _model(T=1000, seed_w=5):
                     "majority", dims=3)
     m.unet.load_state_dict(weights.synth_state_dict(weights.shapes_of(m.unet), seed_w), strict=False)
     return m.cuda().eval()
+
+
+def test_cfg2_full_size_forward_and_first_step_vs_oracle():
+    """BASELINE config 2 at its own per-sample size against the CPU oracle (diffusion_denoising.py:203-224,
+    unet.py:758-823): one UNet forward + one posterior / categorical draw with injected Exp(1) noise."""
+    import math
+    from jointimagegeneration_b200 import ops
+    from oracle import diffusion, nets, weights
+    m = _model()
+    sd = weights.synth_state_dict(weights.shapes_of(m.unet), 5)
+    V = int(np.prod(SPATIAL))
+    x = weights.uniform_one_hot(3, 1, C, SPATIAL)
+    cond = torch.zeros(1, 1, *SPATIAL)
+    T_STEP = 700
+    t = torch.full((1,), float(T_STEP))
+    probs = m.unet(x.cuda(), cond.cuda(), None, t.cuda())["diffusion_out"].float()
+    orc = nets.unet_forward(sd, x, t, input_condition=cond, softmax_output=True, num_head_channels=32)
+    got, want = probs.cpu().numpy().astype(np.float64), orc.numpy().astype(np.float64)
+    rel = np.abs(got - want).max() / np.abs(want).max()
+    psnr = 10 * math.log10(np.abs(want).max() ** 2 / max(((got - want) ** 2).mean(), 1e-30))
+    # one reverse step from identical x_t with identical injected noise
+    q = weights.exp_noise(11, (V, C))
+    a, g = diffusion.step_coefficients(m.diffusion.alphas.cpu(), m.diffusion.cumalphas.cpu(), T_STEP)
+    coef = torch.tensor([[a, g]], dtype=torch.float32).cuda()
+    post = diffusion.theta_post_prob_closed(a, g, x[0].reshape(C, V).numpy(), orc[0].reshape(C, V).numpy())
+    idx = diffusion.categorical_sample(post, q, clamp=1e-12).astype(np.uint8)
+    labels = torch.empty((1, V), dtype=torch.uint8, device="cuda")
+    qd = torch.from_numpy(q).cuda()
+    ops.cat_posterior_sample(probs.contiguous(), x.cuda(), coef, ops.CAT_SAMPLE, q=qd, labels=labels)
+    agree = float((labels.cpu().numpy()[0] == idx).mean())
+    print(f"config 2 full size vs fp32 oracle: probs rel-to-max {rel:.3e}, PSNR {psnr:.1f} dB, first-step label agreement {agree:.5f}")
+    assert rel <= 3e-2 and psnr >= 40.0
+    assert agree >= 0.97
+    # identical probabilities in -> identical labels out, on all 2^20 voxels
+    ops.cat_posterior_sample(orc.cuda().contiguous(), x.cuda(), coef, ops.CAT_SAMPLE, q=qd, labels=labels)
+    assert np.array_equal(labels.cpu().numpy()[0], idx), "labels are not bit-exact given the oracle's probabilities"
 
 
 def test_network_properties_at_full_size():

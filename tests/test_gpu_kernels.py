@@ -394,6 +394,55 @@ def test_conv_roll_fused_groupnorm(ops, N, sp, C1, C2, Cskip, Cout, silu):
     assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
 
 
+@pytest.mark.parametrize("N,sp,silu", [(2, (6, 32, 16), True), (1, (5, 40, 24), True), (3, (4, 48, 20), False)])
+def test_conv_roll_sampler_epilogue_equals_logits_plus_per_voxel_kernel(ops, N, sp, silu):
+    """gg_conv_args.cat: the 64 -> 12 head conv with softmax + posterior + clamp + Philox draw + next-input row in its
+    epilogue must draw EXACTLY the labels (and write exactly the next-input rows) that the same conv writing fp32 logits
+    followed by gg_cat_step_cl's production kernel gives -- same accumulators, same arithmetic, same random words.
+    Shapes cover full bricks, bricks cut in h and w (partial rows take the byte-store path) and whole CTAs out of range."""
+    import ctypes as C_
+    from jointimagegeneration_b200 import _C
+    no_tf32()
+    rs = np.random.RandomState(11)
+    Cin, Cout, Cin_pad = 64, 12, 16
+    V = sp[0] * sp[1] * sp[2]
+    assert V % 4 == 0
+    x = torch.from_numpy(rs.standard_normal((N,) + sp + (Cin,)).astype(np.float32) * 1.3 + 0.2).cuda().to(torch.bfloat16)
+    gamma = torch.from_numpy(rs.standard_normal(Cin).astype(np.float32)).cuda()
+    beta = torch.from_numpy(rs.standard_normal(Cin).astype(np.float32)).cuda()
+    ss = ops.gn_finalize(ops.gn_partial(x), None, gamma, beta, V, 1e-5)
+    w = torch.from_numpy((rs.standard_normal((Cout, Cin, 3, 3, 3)) * 4.0 / math.sqrt(Cin * 27)).astype(np.float32)).cuda()
+    b_pad = ops.pad_vec(torch.from_numpy(rs.standard_normal(Cout).astype(np.float32)).cuda(), Cout)
+    wp = ops.pack_conv_weight(w, [Cin], chunk_major=True)
+    logits = torch.full((N,) + sp + (16,), float("nan"), dtype=torch.float32, device="cuda")
+
+    def args():
+        return ops.make_conv_args([(x, False)], wp, Cout, logits, dims=3, ksize=3, stride=1, bias=b_pad, algo=4, src_ss=[ss.data_ptr()],
+                                  ss_stride=2 * Cin, xf_silu=silu)
+    ops.conv_fwd(args())
+    lab_in = torch.from_numpy(rs.randint(0, Cout, size=N * V).astype(np.uint8)).cuda()
+    coef = torch.tensor([[0.93, 0.41], [0.5, 0.9], [0.999, 0.02]][:N], dtype=torch.float32).cuda()
+    cond = torch.from_numpy(rs.standard_normal((N * V, 1)).astype(np.float32)).cuda().to(torch.bfloat16)
+    want_lab = torch.empty(N * V, dtype=torch.uint8, device="cuda")
+    want_nx = torch.full((N * V, Cin_pad), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.cat_step_cl(logits, lab_in, coef, want_lab, N, V, Cout, cond=cond, n_cond=1, next_x=want_nx, seed=21, offset=5, vox_base=4 * V)
+    got_lab = torch.full((N * V,), 255, dtype=torch.uint8, device="cuda")
+    got_nx = torch.full((N * V, Cin_pad), float("nan"), dtype=torch.bfloat16, device="cuda")
+    cat = _C.CatEpilogue(lab_in.data_ptr(), got_lab.data_ptr(), got_nx.data_ptr(), cond.data_ptr(), coef.data_ptr(), Cout, 1, Cin_pad,
+                         ops.CAT_SAMPLE, 1e-12, 21, 5, 4 * V)
+    a = args()
+    a.cat = C_.pointer(cat)
+    logits.fill_(float("nan"))
+    ops.conv_fwd(a)
+    torch.cuda.synchronize()
+    assert torch.isnan(logits).all(), "the sampler epilogue must not write the logits tensor"
+    assert int((got_lab == 255).sum()) == 0
+    assert torch.equal(got_lab, want_lab), f"{int((got_lab != want_lab).sum())} of {N * V} labels differ"
+    assert torch.equal(got_nx.view(torch.int16), want_nx.view(torch.int16))
+    hist = torch.bincount(got_lab.long(), minlength=Cout)
+    assert int((hist > 0).sum()) >= Cout - 2          # a real draw, not a constant
+
+
 # -------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,H,T,d", [(2, 4, 64, 32), (1, 8, 2048, 32), (2, 10, 256, 32), (3, 2, 16, 32), (1, 5, 100, 32),
                                      (1, 2, 130, 64)])
