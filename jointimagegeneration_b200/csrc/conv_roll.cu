@@ -36,22 +36,21 @@ constexpr int R_THREADS = 352;      // warps 0, 1, 6 = producers / MMA; warps 2.
 // XFORM adds warps 11..: GroupNorm/SiLU transform of the landed halo planes (RollThreads below)
 // Transform warps.  Wide outputs (3 x 64 stacked columns) spend ~3500 clocks of MMAs per plane and four warps keep up;
 // the 16-column head conv (64 -> 12 classes) spends ~900, so its planes wait for the transform: eight warps there.
-template <int BNS> struct XfWarps { static constexpr int value = BNS == 16 ? 8 : 4; };
-template <int BNS, bool XFORM> struct RollThreads { static constexpr int value = XFORM ? R_THREADS + 32 * XfWarps<BNS>::value : R_THREADS; };
+template <int XWARPS> struct RollThreads { static constexpr int value = R_THREADS + 32 * XWARPS; };       // XWARPS = 0: no transform
 constexpr int R_STAGE_BYTES = 16384; // 128 rows x 128 B output / residual staging tile
-constexpr int XB = 4;               // rows a transform thread handles per batch (6 measured the same)
 constexpr int R_SS_BYTES = 4096;    // (scale, shift) table: up to 512 channels over all sources
 
 // Tuning knobs (environment), read ONCE at first use: the launch path itself never calls getenv.
 struct RollKnobs {
-    int no_tma_epi, g, sa, dbg, skip_first;
+    int no_tma_epi, g, sa, dbg, skip_first, xw;
     RollKnobs() {
         auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
         no_tma_epi = getenv("GG_ROLL_NO_TMA_EPI") != nullptr;
         g = geti("GG_ROLL_G", 0);
         sa = geti("GG_ROLL_SA", 0);
         dbg = getenv("GG_ROLL_DBG") != nullptr;
-        skip_first = geti("GG_ROLL_SKIP_FIRST", 1);
+        skip_first = geti("GG_ROLL_SKIP_FIRST", 0);
+        xw = geti("GG_ROLL_XW", 0);
     }
 };
 static const RollKnobs& roll_knobs() { static const RollKnobs k; return k; }
@@ -126,8 +125,7 @@ __device__ __forceinline__ void load_slot(uint32_t t_addr, uint32_t (&r)[BNS]) {
     for (int c = 0; c < BNS; c += 16) tmem_ld16_nowait(t_addr + c, r + c);
     tmem_ld_wait();
 }
-// bias / embedding / residual / rounding / store of one output row from registers.  STATS: r[] is left holding the
-// stored (bf16-rounded) values as floats, zeros for rows outside the tensor, for warp_colsum64.
+// bias / embedding / residual / rounding / store of one output row from registers.
 template <int BNS, bool STATS>
 __device__ __forceinline__ void finish_row(uint32_t (&r)[BNS], const uint4 (&rr)[BNS / 8], int ncols, const float* __restrict__ bvec,
                                            void* y_row, int y_is_f32, bool valid, bool to_stage = false, int swz = 0) {
@@ -147,34 +145,34 @@ __device__ __forceinline__ void finish_row(uint32_t (&r)[BNS], const uint4 (&rr)
             }
         } else {
             const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            // to_stage: the row goes to the swizzled staging tile (every row, TMA clips), else straight to global memory
-            if (to_stage) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_row) + 8 * (g ^ swz)) = pk;
+            // to_stage: the row goes to the swizzled staging tile (every row, TMA clips), else straight to global memory.
+            // STATS: the column sums are taken from the staged tile, so rows outside the tensor are staged as zeros
+            if (to_stage) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_row) + 8 * (g ^ swz)) =
+                              (!STATS || valid) ? pk : make_uint4(0u, 0u, 0u, 0u);
             else if (valid && 8 * g < ncols) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y_row) + 8 * g) = pk;
-            if constexpr (STATS) {
-                const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    r[8 * g + 2 * e] = valid ? __float_as_uint(bf16_lo(w[e])) : 0u;
-                    r[8 * g + 2 * e + 1] = valid ? __float_as_uint(bf16_hi(w[e])) : 0u;
-                }
-            }
         }
     }
 }
-// column sums over the 32 rows a warp holds (one row of 64 values per lane): butterfly reduce-scatter, 62 shuffles;
-// lane l returns the sums of columns 2l and 2l+1.  Destroys a[].
-__device__ __forceinline__ float2 warp_colsum64(float (&a)[64], int lane) {
+// The same for a row that lives in the swizzled staging tile (bf16, 64 columns): the residual chunk is read from the tile
+// where TMA put it and the result overwrites it in place -- no residual registers (the 64 accumulator values are the
+// only large live range, so the kernel fits 96 registers when more transform warps share the SM).
+// STATS: rows outside the tensor are staged as zeros (the column sums are taken from the tile).
+template <bool STATS>
+__device__ __forceinline__ void finish_row_staged(const uint32_t (&r)[64], bool has_res, const float* __restrict__ bvec, uint8_t* srow, int swz,
+                                                  bool valid) {
 #pragma unroll
-    for (int half = 32; half >= 2; half >>= 1) {
-        const int m = half >> 1;
-        const bool up = (lane & m) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const float keep = up ? a[i + half] : a[i], send = up ? a[i] : a[i + half];
-            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-        }
+    for (int g = 0; g < 8; ++g) {
+        uint4* slot = reinterpret_cast<uint4*>(srow + ((g ^ swz) << 4));
+        const uint4 rr = has_res ? *slot : make_uint4(0u, 0u, 0u, 0u);
+        const float4 b0 = *reinterpret_cast<const float4*>(bvec + 8 * g), b1 = *reinterpret_cast<const float4*>(bvec + 8 * g + 4);
+        float v[8];
+        v[0] = __uint_as_float(r[8 * g + 0]) + b0.x + bf16_lo(rr.x); v[1] = __uint_as_float(r[8 * g + 1]) + b0.y + bf16_hi(rr.x);
+        v[2] = __uint_as_float(r[8 * g + 2]) + b0.z + bf16_lo(rr.y); v[3] = __uint_as_float(r[8 * g + 3]) + b0.w + bf16_hi(rr.y);
+        v[4] = __uint_as_float(r[8 * g + 4]) + b1.x + bf16_lo(rr.z); v[5] = __uint_as_float(r[8 * g + 5]) + b1.y + bf16_hi(rr.z);
+        v[6] = __uint_as_float(r[8 * g + 6]) + b1.z + bf16_lo(rr.w); v[7] = __uint_as_float(r[8 * g + 7]) + b1.w + bf16_hi(rr.w);
+        const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        *slot = (!STATS || valid) ? pk : make_uint4(0u, 0u, 0u, 0u);
     }
-    return make_float2(a[0], a[1]);
 }
 
 struct RollItem { int n, d0, L, ihp, iwp; };
@@ -212,9 +210,13 @@ __device__ __forceinline__ uint32_t xf_pair(uint32_t w, float4 q, bool silu) {
     return pack_bf16(h0, h1);
 }
 
-template <int G, bool STATS, int BNS, bool XFORM>
-__global__ void __launch_bounds__(RollThreads<BNS, XFORM>::value, 1) conv_roll_kernel(const __grid_constant__ RollParams p) {
-    constexpr int XW = XfWarps<BNS>::value, XT = 32 * XW;        // transform warps / threads
+template <int G, bool STATS, int BNS, int XW>
+__global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(const __grid_constant__ RollParams p) {
+    constexpr bool XFORM = XW > 0;
+    constexpr int XT = 32 * (XW > 0 ? XW : 1);        // transform threads
+    // rows a transform thread handles per batch: a plane has 180 rows, a pass of all transform threads covers XT / 8
+    // of them -> 4 warps: 3 batches of 4 x 16 rows; 5 warps: 3 batches of 3 x 20 (exact); 8 warps: 2 batches of 3 x 32
+    constexpr int XB = XW == 4 ? 4 : 3;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(RollThreads<BNS, XFORM>::value, 1) conv_roll_k
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 2 * XW); }
+            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 2 * (XW > 0 ? XW : 1)); }
             for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&step_done[i], 1); mbar_init(&slot_free[i], 8); mbar_init(&res_full[i], 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -541,13 +543,16 @@ __global__ void __launch_bounds__(RollThreads<BNS, XFORM>::value, 1) conv_roll_k
         if (lane == 0) mbar_arrive_remote(free_r);
         uint32_t phd = 0, ph_res = 0;
         int cur_n = -1;
-        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);       // STATS: (sum, sum sq) of columns 2 lane, 2 lane + 1 over this warp's rows
+        // STATS: thread (q, lane) owns column (q & 1) * 32 + lane over rows (q >> 1) * 64 .. + 63 of every staged brick:
+        // (sum, sum of squares) of the STORED (bf16-rounded) values, accumulated in a fixed order
+        float2 st = make_float2(0.f, 0.f);
+        const int st_col = (q & 1) * 32 + lane, st_row0 = (q >> 1) * 64;
         int stat_n = -1;
         CatRowCoef cat_cf = {};
-        auto flush = [&](int n) {        // one partial row per (CTA, epilogue warp): written once per sample, fixed order
-            *reinterpret_cast<float4*>(p.gn_partial + (((long long)n * p.gn_nchunks_total + p.gn_chunk_base + (long long)blockIdx.x * 8 + wi * 4 + q) * 64) * 2 +
-                                       4 * lane) = st;
-            st = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto flush = [&](int n) {        // one partial row per (CTA, epilogue warp), its 32 columns (the rest stays zero): once per sample
+            *reinterpret_cast<float2*>(p.gn_partial + (((long long)n * p.gn_nchunks_total + p.gn_chunk_base + (long long)blockIdx.x * 8 + wi * 4 + q) * 64) * 2 +
+                                       2 * st_col) = st;
+            st = make_float2(0.f, 0.f);
         };
         for (int item = item0; item < p.total_items; item += istep) {
             const RollItem it = roll_item(p, item);
@@ -587,17 +592,17 @@ __global__ void __launch_bounds__(RollThreads<BNS, XFORM>::value, 1) conv_roll_k
                     uint8_t* stage = smem_c + wi * R_STAGE_BYTES;
                     const int hb = (2 * it.ihp + wi) * H_BH, wb = (2 * it.iwp + rank) * H_BW;
                     // the residual is requested before waiting for the accumulator: its latency hides behind the MMAs
-                    uint4 rr[BNS / 8];
+                    uint4 rr[BNS == 64 ? 1 : BNS / 8];      // 64-column rows that are not staged (rare) prefetch per chunk instead
                     if (tma_epi) {
-                        if (store) {
+                        if (store && p.residual != nullptr) {
                             if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous brick left the tile
                             asm volatile("bar.sync %0, 128;" ::"r"(1 + wi) : "memory");
-                            if (p.residual != nullptr && etid == 0) {
+                            if (etid == 0) {
                                 mbar_expect_tx(&res_full[wi], R_STAGE_BYTES);
                                 tma_load_5d(stage, &p.rmap, &res_full[wi], 0, wb, hb, d, n);
                             }
                         }
-                    } else {
+                    } else if constexpr (BNS != 64) {
 #pragma unroll
                         for (int g = 0; g < BNS / 8; ++g)
                             rr[g] = (p.residual != nullptr && valid && 8 * g < p.Cout8) ? ldg_nc_u4(p.residual + lin * p.res_stride + 8 * g)
@@ -625,21 +630,22 @@ __global__ void __launch_bounds__(RollThreads<BNS, XFORM>::value, 1) conv_roll_k
                     if (lane == 0) mbar_arrive_remote(free_r);
                     if (store) {
                         if (tma_epi) {
+                          if constexpr (BNS == 64) {
                             // row `row` of the tile is 128 bytes; SWIZZLE_128B puts its 16-byte chunk g at slot g ^ (row & 7)
                             uint8_t* srow = stage + row * 128;
                             if (p.residual != nullptr) {
                                 mbar_wait(&res_full[wi], ph_res);
                                 ph_res ^= 1u;
-#pragma unroll
-                                for (int g = 0; g < BNS / 8; ++g) rr[g] = *reinterpret_cast<const uint4*>(srow + ((g ^ (row & 7)) << 4));
                             } else {
-#pragma unroll
-                                for (int g = 0; g < BNS / 8; ++g) rr[g] = make_uint4(0, 0, 0, 0);
+                                // no residual: the tile is first touched here, AFTER the slot went back to the tensor core
+                                if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous brick left the tile
+                                asm volatile("bar.sync %0, 128;" ::"r"(1 + wi) : "memory");
                             }
-                            finish_row<BNS, STATS>(r, rr, p.Cout8, bvec, srow, 0, valid, true, row & 7);
+                            finish_row_staged<STATS>(r, p.residual != nullptr, bvec, srow, row & 7, valid);
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic writes -> TMA store reads
                             asm volatile("bar.sync %0, 128;" ::"r"(1 + wi) : "memory");
                             if (etid == 0) tma_store_5d(&p.ymap, stage, 0, wb, hb, d, n);
+                          }
                         } else if (BNS == 16 && p.cat_on) {
                             if constexpr (BNS == 16) {
                                 // ---- sampler epilogue: this thread's 16 accumulator columns are the class logits of voxel `lin`
@@ -691,17 +697,33 @@ __global__ void __launch_bounds__(RollThreads<BNS, XFORM>::value, 1) conv_roll_k
                             const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw;
                             void* y_row = p.y_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.y) + yoff)
                                                      : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff);
-                            finish_row<BNS, STATS>(r, rr, p.Cout8, bvec, y_row, p.y_is_f32, valid);
+                            if constexpr (BNS == 64) {
+                                uint4 rq[8];
+#pragma unroll
+                                for (int g = 0; g < 8; ++g)
+                                    rq[g] = (p.residual != nullptr && valid && 8 * g < p.Cout8) ? ldg_nc_u4(p.residual + lin * p.res_stride + 8 * g)
+                                                                                                : make_uint4(0, 0, 0, 0);
+                                finish_row<64, false>(r, rq, p.Cout8, bvec, y_row, p.y_is_f32, valid);
+                            } else {
+                                finish_row<BNS, false>(r, rr, p.Cout8, bvec, y_row, p.y_is_f32, valid);
+                            }
                         }
-                        if constexpr (STATS) {       // squares first: the reduction destroys its input
-                            float b[64];
-#pragma unroll
-                            for (int i = 0; i < 64; ++i) b[i] = __uint_as_float(r[i]) * __uint_as_float(r[i]);
-                            const float2 sb = warp_colsum64(b, lane);
-#pragma unroll
-                            for (int i = 0; i < 64; ++i) b[i] = __uint_as_float(r[i]);
-                            const float2 sa = warp_colsum64(b, lane);
-                            st.x += sa.x; st.y += sb.x; st.z += sa.y; st.w += sb.y;
+                        if constexpr (STATS) {
+                            // column sums from the staged tile (complete after the bar.sync above; the TMA store only reads
+                            // it, and the next brick is written after the group's next bar.sync): 64 two-byte loads per
+                            // thread, 32 consecutive columns of one row per warp -> conflict-free, and no accumulator
+                            // registers beyond the row itself
+                            const uint8_t* colp = stage + ((st_col & 7) << 1);
+                            const int chunk = st_col >> 3;
+                            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                            for (int i = 0; i < 64; ++i) {
+                                const int rw2 = st_row0 + i;
+                                const float f = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(colp + rw2 * 128 + ((chunk ^ (rw2 & 7)) << 4))) << 16);
+                                s1 += f;
+                                s2 = fmaf(f, f, s2);
+                            }
+                            st.x += s1; st.y += s2;
                         }
                     }
                 }
@@ -723,9 +745,9 @@ __global__ void __launch_bounds__(RollThreads<BNS, XFORM>::value, 1) conv_roll_k
 }
 
 // ---------------------------------------------------------------------------------------- host
-template <int G, bool STATS, int BNS, bool XFORM>
+template <int G, bool STATS, int BNS, int XW>
 static int launch_roll(const RollParams& p, int grid, size_t smem, cudaStream_t stream) {
-    auto* fn = conv_roll_kernel<G, STATS, BNS, XFORM>;
+    auto* fn = conv_roll_kernel<G, STATS, BNS, XW>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
@@ -734,7 +756,7 @@ static int launch_roll(const RollParams& p, int grid, size_t smem, cudaStream_t 
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(RollThreads<BNS, XFORM>::value); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(RollThreads<XW>::value); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -742,6 +764,17 @@ static int launch_roll(const RollParams& p, int grid, size_t smem, cudaStream_t 
     cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
     if (e != cudaSuccess) return (int)e;
     return launch_result();
+}
+
+template <bool STATS, int BNS>
+static int dispatch_roll(int G, int xw, const RollParams& p, int grid, size_t smem, cudaStream_t stream) {
+#define GG_ROLL_CASE(g_, xw_) if (G == g_ && xw == xw_) return launch_roll<g_, STATS, BNS, xw_>(p, grid, smem, stream)
+    GG_ROLL_CASE(1, 0); GG_ROLL_CASE(3, 0);
+    GG_ROLL_CASE(1, 4); GG_ROLL_CASE(3, 4);
+    GG_ROLL_CASE(1, 5); GG_ROLL_CASE(3, 5);
+    GG_ROLL_CASE(1, 8); GG_ROLL_CASE(3, 8);
+#undef GG_ROLL_CASE
+    return GG_ERR_UNSUPPORTED;
 }
 
 // geometry shared with gg_conv_stats_chunks: brick pairs, depth segmentation, grid
@@ -854,13 +887,20 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
     // MMAs: those convs take single-tap weight stages (G = 1) and spend the shared memory on a fourth plane stage.
     bool has_centre = false;
     for (int s = 0; s < a->nsrc; ++s) has_centre = has_centre || a->src[s].centre_only;
-    int G = has_centre ? 1 : 3;
+    // Ring shapes (measured on B200, N = 8 x 64 x 128 x 128, tools/bench_conv.py; profiles/r2_conv_roll_tuning.md).
+    // A weight stage = one kw row of stacked tap tiles (G = 3: 12 MMAs per issue-loop iteration -- with single-tap
+    // stages the loop itself, ~450 clocks per iteration, is slower than its four MMAs).  Plane stages: three, or four
+    // when the transform adds a hop between "landed" and "usable".  With fused 1x1x1 skip sources every step pushes
+    // 2-3 more (small) planes through the plane ring, each held for a whole TMA latency but only four MMAs: five plane
+    // stages and two weight stages (2.60 -> 2.28 ms on the 64 + 192 -> 64 layer; four plane stages + eight single-tap
+    // weight stages, the round-1 choice: 2.43-2.60 ms).
+    int G = 3;
     if (knobs.g == 1 || knobs.g == 3) G = knobs.g;
-    // Order of the sources within a step.  With the 1x1x1 sources LAST their planes sit in the ring behind the step's
-    // big plane: the ring is full while that plane's 36 MMAs run, nothing of the next step can be requested, and the
-    // tensor core then waits a whole TMA latency (+ transform) per step (measured: tensor pipe 37-42 % active).  With
-    // them FIRST and five plane stages, their stages drain within a few hundred clocks and the whole next step (its
-    // small planes and its big plane) is in flight while the current big plane is being multiplied.
+    // transform warps (0 = no fused input normalisation): wide outputs keep up with four; the 16-column head conv spends
+    // few clocks of MMAs per plane and the skip-source convs have the shallowest look-ahead -> eight; GG_ROLL_XW overrides
+    int xw = xform ? ((g.BNs == 16 || has_centre) ? 8 : 4) : 0;
+    if (xform && (knobs.xw == 4 || knobs.xw == 5 || knobs.xw == 8)) xw = knobs.xw;
+    // order of the sources within a step: as given, or (GG_ROLL_SKIP_FIRST=1, measured slower) 1x1x1 sources first
     const bool skip_first = has_centre && knobs.skip_first != 0;
     {
         int n = 0;
@@ -870,9 +910,10 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
                 if (skip_first ? (c == (pass == 0)) : (pass == 0)) p.order[n++] = s2;
             }
     }
-    int SA = skip_first ? 5 : (xform || has_centre) ? 4 : 3;
+    int SA = has_centre ? 5 : xform ? 4 : 3;
     int SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes);
-    if (SB < 3 && SA > 3) { SA = 3; SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes); }
+    if (SB < 3 && SA > 3 && !has_centre) { SA = 3; SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes); }
+    if (SB < 2 && SA > 3) { SA = 4; SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes); }       // no transform table / staging: smaller budget
     GG_REQUIRE(SB >= 2, GG_ERR_UNSUPPORTED);
     if (SB > R_MAX_SB) {
         SA = std::min(R_MAX_SA, (avail - R_MAX_SB * G * tap_bytes) / (int)p.a_stage_bytes);
@@ -932,7 +973,7 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
         }
     } dbg_print{dbg, g.grid / 2, stream, dbg_buf};
     if (a->gn_partial != nullptr) {
-        GG_REQUIRE(g.BNs == 64 && p.Cout8 == 64 && !a->y_is_f32, GG_ERR_UNSUPPORTED);
+        GG_REQUIRE(g.BNs == 64 && p.Cout8 == 64 && !a->y_is_f32 && p.tma_epi, GG_ERR_UNSUPPORTED);   // statistics are read from the staged tile
         GG_REQUIRE(aligned(a->gn_partial, 16) && a->gn_chunk_base >= 0 && a->gn_chunk_base + g.grid * 8 <= a->gn_nchunks_total, GG_ERR_BAD_ARG);
         p.gn_partial = a->gn_partial; p.gn_chunk_base = a->gn_chunk_base; p.gn_nchunks_total = a->gn_nchunks_total;
         {   // one 2-D memset: this launch's rows of every sample
@@ -941,15 +982,10 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
                                               (size_t)(g.grid * 8) * row_bytes, (size_t)a->N, stream);
             if (e != cudaSuccess) return (int)e;
         }
-        if (G == 1) return xform ? launch_roll<1, true, 64, true>(p, g.grid, smem, stream) : launch_roll<1, true, 64, false>(p, g.grid, smem, stream);
-        return xform ? launch_roll<3, true, 64, true>(p, g.grid, smem, stream) : launch_roll<3, true, 64, false>(p, g.grid, smem, stream);
+        return dispatch_roll<true, 64>(G, xw, p, g.grid, smem, stream);
     }
-    if (g.BNs == 16) {
-        if (G == 1) return xform ? launch_roll<1, false, 16, true>(p, g.grid, smem, stream) : launch_roll<1, false, 16, false>(p, g.grid, smem, stream);
-        return xform ? launch_roll<3, false, 16, true>(p, g.grid, smem, stream) : launch_roll<3, false, 16, false>(p, g.grid, smem, stream);
-    }
-    if (G == 1) return xform ? launch_roll<1, false, 64, true>(p, g.grid, smem, stream) : launch_roll<1, false, 64, false>(p, g.grid, smem, stream);
-    return xform ? launch_roll<3, false, 64, true>(p, g.grid, smem, stream) : launch_roll<3, false, 64, false>(p, g.grid, smem, stream);
+    if (g.BNs == 16) return dispatch_roll<false, 16>(G, xw, p, g.grid, smem, stream);
+    return dispatch_roll<false, 64>(G, xw, p, g.grid, smem, stream);
 }
 
 }  // namespace gg

@@ -145,7 +145,8 @@ class _LocalComm:
     def exchange_halo(self, *a, **k):
         raise RuntimeError("virtual rank: run the plans of all ranks through LocalSlabGroup.run")
 
-    all_gather = exchange_halo
+    def all_gather(self, *a, **k):
+        raise RuntimeError("virtual rank: run the plans of all ranks through LocalSlabGroup.run")
 
     def broadcast_int(self, value: int) -> int:
         return int(value)

@@ -83,9 +83,31 @@ def test_ccdm_tiny_unet_posterior_chain_vs_reference():
     final = res.argmax(1).cpu().numpy().astype(np.uint8)
     agree = (final == g["final_labels"]).mean()
     print(f"ccdm_tiny: first-step agreement {agree0:.4f}, final agreement {agree:.4f}")
-    # the chain re-samples every voxel at every step from near-flat synthetic probabilities, so a first-step difference
-    # of 1 - agree0 compounds over the T steps; the final arg-max labels still have to agree far above the 1/C chance level
-    assert agree >= 0.80, f"final label agreement {agree}"
+    # The FREE-RUNNING chains drift apart: a label that differs at a near-tie changes the next network input, and the
+    # synthetic network's probabilities are nearly flat (measured 0.999 after step 1, 0.55 after all T steps; chance is
+    # 1/C = 0.25).  The free-running final labels only have to stay well above chance ...
+    assert agree >= 0.40, f"final label agreement {agree}"
+    # ... the per-step parity claim is the TEACHER-FORCED one: every step restarted from the reference's own previous
+    # label volume (identical inputs, identical injected noise) must reproduce the reference's next volume
+    sl = g["step_labels"]
+    n_steps = sl.shape[0]
+    for i in range(1, n_steps + 1):
+        t_i = T - i
+        xt = torch.nn.functional.one_hot(torch.from_numpy(sl[i - 1].astype(np.int64)), C).permute(0, 4, 1, 2, 3).float().contiguous().cuda()
+        tt = torch.full((B,), float(t_i))
+        pr = m.unet(xt, cond.cuda(), None, tt.cuda())["diffusion_out"].float().contiguous()
+        coef = m.diffusion.step_coef_tensor(torch.full((B,), t_i)).cuda()
+        lab = torch.empty((B, V), dtype=torch.uint8, device="cuda")
+        if t_i > 1:
+            from jointimagegeneration_b200 import ops
+            ops.cat_posterior_sample(pr, xt, coef, ops.CAT_SAMPLE, q=q[i].cuda().contiguous(), labels=lab)
+            want = sl[i]
+        else:
+            from jointimagegeneration_b200 import ops
+            ops.cat_posterior_sample(pr, xt, coef, ops.CAT_ARGMAX, labels=lab)
+            want = g["final_labels"]
+        a_i = (lab.cpu().numpy().reshape(want.shape) == want).mean()
+        assert a_i >= 0.97, f"teacher-forced step t={t_i}: label agreement {a_i}"
 
 
 def test_ccdm_chain_bit_exact_given_identical_logits():
@@ -378,7 +400,7 @@ def test_resident_loop_noise_key_per_call_and_chain_base():
     the GLOBAL chain index: chains 1.. of a batch of 3 run alone with chain_base = 1 reproduce the batched labels."""
     from jointimagegeneration_b200 import ops
     from oracle import configs, weights
-    T, B, C, spatial = 6, 3, 4, (8, 8, 8)
+    T, B, C, spatial = 6, 3, 12, (8, 8, 8)
     m, _ = _ccdm(configs.CCDM_TINY, T, C, spatial, 3, loop="resident")
     x = weights.uniform_one_hot(5, B, C, spatial).cuda()
     cond = torch.zeros(B, 1, *spatial).cuda()

@@ -52,6 +52,18 @@ def main():
                 a = ops.make_conv_args(srcs, wpk, Cout, y, dims=3, ksize=3, stride=1, bias=bp,
                                        residual=res if "res" in variant else None, algo=algo,
                                        src_ss=ssl, ss_stride=2 * Cin)
+                if "cat" in variant:        # sampler epilogue of the head conv
+                    if algo != 4 or Cout > 16:
+                        continue
+                    V = D * H * W
+                    lab_in = torch.randint(0, Cout, (N * V,), device=dev, dtype=torch.uint8)
+                    lab_out = torch.empty_like(lab_in)
+                    nx = torch.empty((N * V, 16), device=dev, dtype=torch.bfloat16)
+                    coef = torch.tensor([[0.9, 0.5]] * N, device=dev)
+                    cat = _C.CatEpilogue(lab_in.data_ptr(), lab_out.data_ptr(), nx.data_ptr(), None, coef.data_ptr(), Cout, 1, 16, 1, 1e-12, 7, 3, 0)
+                    y = torch.empty((N, D, H, W, 16), device=dev, dtype=torch.float32)
+                    a = ops.make_conv_args(srcs, wpk, Cout, y, dims=3, ksize=3, stride=1, bias=bp, algo=algo, src_ss=ssl, ss_stride=2 * Cin)
+                    a.cat = C.pointer(cat)
                 part = None
                 if "stats" in variant:
                     per = int(_C.lib().gg_conv_stats_chunks(C.byref(a)))
