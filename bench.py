@@ -534,6 +534,76 @@ def run_ours_ldm(args, workload, K=None, W=None):
     return line if rank == 0 else None
 
 
+# ===================================================================== BASELINE config 4: one whole volume, both stages
+def run_pipeline_cfg4(args, chain_steps=1000, n_samples=1):
+    """Full GuideGen pipeline for ONE volume through jointimagegeneration_b200.pipeline.GuideGenPipeline:
+    stage 1 (CCDM mask sampler, 128x128x64, `chain_steps` reverse steps) -> bridge (argmax labels -> scipy-rule zoom to
+    64 x 512 x 512, / 255) -> stage 2 (pixel-space LDM, every slice: 50 DDIM steps at 512^2 conditioned on the previous
+    generated slice and the mask slice, min-max normalise).  sample_diffusion.py:196-224.  Synthetic weights."""
+    import torch
+    from jointimagegeneration_b200.ldm import LatentDiffusion, UNetModel
+    from jointimagegeneration_b200.pipeline import GuideGenPipeline
+    rank, local, world, dev = dist_setup(args)
+    wl2 = WORKLOADS["ccdm_cfg2"]
+    sp, Cc = wl2["spatial"], wl2["C"]
+    torch.manual_seed(777 + rank)
+    mask_model = _ccdm_model(1000, sp, Cc, dev)
+    mask_model.loop, mask_model.use_cuda_graph = "resident", True
+    unet = UNetModel(**LDM_PIXEL_NET)
+    randomize_zero_modules(unet, 7)
+    ld = LatentDiffusion(unet, conditioning_key="concat", **LDM_SCHEDULE).to(dev).eval()
+    unet.use_cuda_graph = True
+    pipe = GuideGenPipeline(ld, mask_model, ddim_steps=50, ddim_eta=0.0)
+    lab0 = torch.randint(0, Cc, (1,) + sp, device=dev)
+    x_T = torch.zeros((1, Cc) + sp, device=dev).scatter_(1, lab0[:, None], 1.0)
+    cond = torch.zeros((1, 1) + sp, device=dev)
+    # warm both stages once (plans, graphs) -- a service generates many volumes with the same plans
+    pipe.generate_mask(x_T, cond, init_t=10000 + 2)
+    wm = torch.zeros((1, 1, 4, 512, 512), device=dev)
+    wm[:, :, 1:3] = 0.01
+    pipe.sample_cond(wm, n_samples=n_samples)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    labels = pipe.generate_mask(x_T, cond, init_t=None if chain_steps >= 1000 else 10000 + chain_steps)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    wholemask = pipe.mask_to_ct_grid(labels[0], size=(512, 512))
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    pred = pipe.sample_cond(wholemask, n_samples=n_samples)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    D = wholemask.shape[2]
+    nz = torch.where(wholemask.sum((0, 1, 3, 4)))[0]
+    n_slices = int(nz[-1]) - int(nz[0]) + 2
+    # device time of one steady-state DDIM step at this batch (graph replay + fused update), for the host-gap figure
+    sampler = pipe.sampler
+    x = torch.randn((n_samples, 1, 512, 512), device=dev)
+    c = torch.randn((n_samples, 2, 512, 512), device=dev)
+    ts = torch.full((n_samples,), 501, device=dev, dtype=torch.long)
+    for _ in range(3):
+        sampler.p_sample_ddim(x, c, ts, 2, index=25)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        sampler.p_sample_ddim(x, c, ts, 2, index=25)
+    b.record()
+    torch.cuda.synchronize()
+    step_ms = a.elapsed_time(b) / 10
+    total = t3 - t0
+    out = {"metric": "volumes/sec (full pipeline, one 512x512x64 CT volume)", "value": 1.0 / total, "unit": "volumes/s", "seconds_per_volume": total,
+           "stage1_s": t1 - t0, "stage1_steps": chain_steps, "stage1_ms_per_step": (t1 - t0) / chain_steps * 1e3,
+           "bridge_ms": (t2 - t1) * 1e3, "stage2_s": t3 - t2, "slices": n_slices, "ddim_steps": 50, "n_samples": n_samples,
+           "ms_per_slice": (t3 - t2) / n_slices * 1e3, "device_ms_per_ddim_step": step_ms,
+           "host_gap_ms_per_slice": (t3 - t2) / n_slices * 1e3 - 50 * step_ms,
+           "output_shape": list(pred.shape), "finite": bool(torch.isfinite(pred).all()),
+           "config": {"workload": "Full GuideGen pipeline: mask sampler (128x128x64, 12 classes, %d steps) -> zoom/slice bridge -> autoregressive "
+                                  "pixel-space LDM CT 512x512x64 (50 DDIM steps per slice, n_samples %d)" % (chain_steps, n_samples), "name": "pipeline_cfg4"}}
+    del pipe, ld, unet, mask_model, pred, wholemask
+    torch.cuda.empty_cache()
+    return out
+
+
 # ======================================================= the same torch modules on the SAME GPU (BASELINE.md section 4)
 def gpu_eager_baseline(workload, dev, budget_s=25.0):
     """The oracle port's torch functions (F.conv3d / group_norm / softmax / the reference's O(C^2) theta_post_prob einsum /
@@ -807,13 +877,18 @@ def main():
     args = ap.parse_args()
     # stdout carries ONE JSON line.  NCCL's INFO lines (the driver counts ranks in them) go to stderr instead of being
     # silenced: NCCL_DEBUG is left as the caller set it (INIT-level INFO by default at N > 1)
-    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", 1)) > 1:
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args)
         return
+    json_fd = 1
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # NCCL writes its INFO lines to fd 1: point fd 1 at stderr for the whole process and keep a private duplicate of
+        # the real stdout for the one JSON line
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank, local, world, dev = dist_setup(args)
@@ -823,7 +898,8 @@ def main():
     def emit():
         with lock:
             if rank == 0 and state["line"] is not None and not state["printed"]:
-                print(json.dumps(state["line"]), flush=True)
+                sys.stdout.flush()
+                os.write(json_fd, (json.dumps(state["line"]) + "\n").encode())
                 state["printed"] = True
 
     line = run_ours(args)
@@ -840,6 +916,11 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line["workloads"][name] = {"error": repr(e)[:300]}
                 torch.cuda.empty_cache()
+        try:
+            line["workloads"]["pipeline_cfg4"] = run_pipeline_cfg4(args)
+        except Exception as e:  # noqa: BLE001
+            line["workloads"]["pipeline_cfg4"] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
         try:
             line["gpu_eager_baseline"] = gpu_eager_baseline(args.workload, dev)
             if "ms_per_step" in line["gpu_eager_baseline"]:

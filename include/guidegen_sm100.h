@@ -185,6 +185,11 @@ int gg_ddpm_update(const gg_ddpm_args* a, gg_stream_t stream);
 /* mask[d, h, w] = labels[d, h / fh, w / fw] / divisor   (uint8 [D, H, W] -> fp32 [D, H*fh, W*fw]) */
 int gg_labels_to_mask(const uint8_t* labels, float* mask, int32_t D, int32_t H, int32_t W, int32_t fh, int32_t fw, float divisor,
                       gg_stream_t stream);
+/* mask[d, h, w] = labels[idx_d[d], idx_h[h], idx_w[w]] / divisor  (uint8 [D, H, W] -> fp32 [Do, Ho, Wo]); the int32 device
+ * index tables carry the resampling rule -- scipy.ndimage.zoom(order=0) as sample_diffusion.py:200 calls it maps output
+ * index o to input floor(o * (n_in - 1) / (n_out - 1) + 0.5), which is NOT block replication */
+int gg_labels_gather(const uint8_t* labels, float* mask, int32_t D, int32_t H, int32_t W, int32_t Do, int32_t Ho, int32_t Wo,
+                     const int32_t* idx_d, const int32_t* idx_h, const int32_t* idx_w, float divisor, gg_stream_t stream);
 /* y[b, 0:per_sample] = (x[b] - min(x)) / (max(x) - min(x)); x dense fp32 [B, per_sample]; row b of y starts at
  * y + b * y_batch_stride (a slice of a [B, 1, D, H, W] volume); scratch: fp32 [1024] device workspace */
 int gg_minmax_normalize(const float* x, float* y, float* scratch, int32_t B, int64_t per_sample, int64_t y_batch_stride,

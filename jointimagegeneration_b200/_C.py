@@ -124,6 +124,7 @@ SYMBOLS = {
     "gg_ddpm_update": (C.c_int, [C.POINTER(DdpmArgs), _vp]),
     "gg_plms_eps": (C.c_int, [C.POINTER(PlmsArgs), _vp]),
     "gg_labels_to_mask": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "gg_labels_gather": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp]),
     "gg_minmax_normalize": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _vp]),
     "gg_nchw_to_cl": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i32, _i64, _vp]),
     "gg_cl_to_nchw": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i32, _vp]),

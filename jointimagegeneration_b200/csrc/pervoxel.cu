@@ -598,6 +598,17 @@ __global__ void __launch_bounds__(256) labels_to_mask_kernel(const uint8_t* __re
     out[i] = __fdiv_rn((float)lab[((int64_t)d * H + h / fh) * W + w / fw], divisor);
 }
 
+// general nearest-neighbour resampling: out[d, h, w] = lab[id[d], ih[h], iw[w]] / divisor with host-computed index tables
+// (the tables carry scipy.ndimage.zoom(order=0)'s coordinate rule, see ops.zoom_index)
+__global__ void __launch_bounds__(256) labels_gather_kernel(const uint8_t* __restrict__ lab, float* __restrict__ out, int H, int W, int Do,
+                                                            int Ho, int Wo, const int32_t* __restrict__ id, const int32_t* __restrict__ ih,
+                                                            const int32_t* __restrict__ iw, float divisor) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Do * Ho * Wo) return;
+    const int w = (int)(i % Wo), h = (int)((i / Wo) % Ho), d = (int)(i / ((int64_t)Wo * Ho));
+    out[i] = __fdiv_rn((float)lab[((int64_t)__ldg(id + d) * H + __ldg(ih + h)) * W + __ldg(iw + w)], divisor);
+}
+
 __device__ __forceinline__ void block_minmax(float& mn, float& mx) {
     __shared__ float smn[8], smx[8];
 #pragma unroll
@@ -769,6 +780,14 @@ extern "C" int gg_labels_to_mask(const uint8_t* labels, float* mask, int32_t D, 
     GG_REQUIRE(labels && mask && D > 0 && H > 0 && W > 0 && fh > 0 && fw > 0 && divisor != 0.f, GG_ERR_BAD_ARG);
     const int64_t n = (int64_t)D * H * fh * W * fw;
     labels_to_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(labels, mask, D, H, W, fh, fw, divisor);
+    return launch_result();
+}
+
+extern "C" int gg_labels_gather(const uint8_t* labels, float* mask, int32_t D, int32_t H, int32_t W, int32_t Do, int32_t Ho, int32_t Wo,
+                                const int32_t* idx_d, const int32_t* idx_h, const int32_t* idx_w, float divisor, gg_stream_t stream) {
+    GG_REQUIRE(labels && mask && idx_d && idx_h && idx_w && D > 0 && H > 0 && W > 0 && Do > 0 && Ho > 0 && Wo > 0 && divisor != 0.f, GG_ERR_BAD_ARG);
+    const int64_t n = (int64_t)Do * Ho * Wo;
+    labels_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(labels, mask, H, W, Do, Ho, Wo, idx_d, idx_h, idx_w, divisor);
     return launch_result();
 }
 

@@ -29,6 +29,17 @@ class DDIMSampler(object):
         setattr(self, name, attr)
 
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
+        # sample() calls this once per call -- once per SLICE in sample_cond (64 x per volume), each time with a
+        # device->host read of alphas_cumprod; the tables only depend on (steps, discretisation, eta) and the model's
+        # schedule, so an identical request reuses them
+        key = (int(ddim_num_steps), str(ddim_discretize), float(ddim_eta), id(self.model.alphas_cumprod))
+        if getattr(self, "_schedule_key", None) == key:
+            return
+        self._schedule_key = None
+        self._make_schedule(ddim_num_steps, ddim_discretize, ddim_eta, verbose)
+        self._schedule_key = key
+
+    def _make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
         self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
                                                   num_ddpm_timesteps=self.ddpm_num_timesteps, verbose=verbose)
         alphas_cumprod = self.model.alphas_cumprod

@@ -125,6 +125,30 @@ def labels_to_mask(labels, fh, fw, divisor=255.0, out=None):
     return out
 
 
+def zoom_index(n_in: int, n_out: int):
+    """Input index of every output index under scipy.ndimage.zoom(order=0, mode='constant', grid_mode=False) -- the call of
+    sample_diffusion.py:200: output o samples input coordinate o * (n_in - 1) / (n_out - 1) (corner-aligned) and order 0
+    takes floor(c + 0.5).  Double arithmetic as in scipy's NI_ZoomShift; int32 numpy array [n_out]."""
+    import numpy as np
+    if n_out == 1 or n_in == 1:
+        return np.zeros(n_out, dtype=np.int32)
+    c = np.arange(n_out, dtype=np.float64) * (np.float64(n_in - 1) / np.float64(n_out - 1))
+    return np.clip(np.floor(c + 0.5), 0, n_in - 1).astype(np.int32)
+
+
+def labels_zoom(labels, out_shape, divisor=255.0, out=None):
+    """uint8 labels [D, H, W] -> fp32 [Do, Ho, Wo] = scipy.ndimage.zoom(labels, out_shape / shape, order=0) / divisor."""
+    _chk(labels, torch.uint8)
+    D, H, W = labels.shape
+    Do, Ho, Wo = (int(v) for v in out_shape)
+    idx = [torch.from_numpy(zoom_index(n, m)).to(labels.device) for n, m in ((D, Do), (H, Ho), (W, Wo))]
+    if out is None:
+        out = torch.empty((Do, Ho, Wo), dtype=torch.float32, device=labels.device)
+    _C.check(_C.lib().gg_labels_gather(_C.ptr(labels), _C.ptr(out), D, H, W, Do, Ho, Wo, _C.ptr(idx[0]), _C.ptr(idx[1]), _C.ptr(idx[2]),
+                                       float(divisor), _C.stream()), "gg_labels_gather")
+    return out
+
+
 def minmax_normalize(x, y_view, scratch):
     """y_view[b] = (x[b] - x.min()) / (x.max() - x.min()); y_view: [B, ...] whose rows are contiguous blocks."""
     _chk(x, torch.float32)

@@ -34,12 +34,21 @@ class GuideGenPipeline:
         return labels.view((B,) + tuple(out.shape[2:]))
 
     @torch.no_grad()
-    def mask_to_ct_grid(self, labels: torch.Tensor, size=(512, 512)) -> torch.Tensor:
-        """uint8 [D, h, w] -> fp32 whole-mask [1, 1, D, H, W] (order-0 zoom, / 255; sample_diffusion.py:199-201)."""
+    def mask_to_ct_grid(self, labels: torch.Tensor, size=(512, 512), depth=None, rot90_k: int = 0, mode: str = "scipy") -> torch.Tensor:
+        """uint8 [D, h, w] -> fp32 whole-mask [1, 1, D', H, W]: the stage bridge of sample_diffusion.py:199-201,
+        ``rot90(zoom(labels, out / in, order=0), k=3, dims=(1, 2)) / 255``.  mode "scipy" reproduces scipy.ndimage.zoom's
+        corner-aligned nearest rule exactly (ops.zoom_index; pinned against scipy in tests/test_gpu_models.py), "block" is
+        plain integer-factor replication.  ``depth`` resamples the slice axis too (the reference zooms to 96 slices)."""
         D, h, w = labels.shape
-        assert size[0] % h == 0 and size[1] % w == 0, "nearest zoom by integer factors"
-        m = ops.labels_to_mask(labels.contiguous(), size[0] // h, size[1] // w, 255.0)
-        return m.view(1, 1, D, size[0], size[1])
+        Do = D if depth is None else int(depth)
+        if mode == "block":
+            assert size[0] % h == 0 and size[1] % w == 0 and Do == D, "block replication needs integer in-plane factors"
+            m = ops.labels_to_mask(labels.contiguous(), size[0] // h, size[1] // w, 255.0)
+        else:
+            m = ops.labels_zoom(labels.contiguous(), (Do, size[0], size[1]), 255.0)
+        if rot90_k % 4:
+            m = torch.rot90(m, k=rot90_k, dims=(1, 2)).contiguous()      # a view permutation of the finished mask (once per volume)
+        return m.view(1, 1, Do, m.shape[1], m.shape[2])
 
     # ---- stage 2 ----------------------------------------------------------------------------------
     @torch.no_grad()

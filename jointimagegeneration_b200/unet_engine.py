@@ -204,7 +204,10 @@ class UNetEngine:
         self.use_roll_conv = True
         # one-launch GroupNorm for L2-resident tensors (gg_gn_fused): measured SLOWER on config 3 (7.24 vs 4.85 ms per step:
         # 8 CTAs per sample leave too few loads in flight), so off; kept as a tested kernel + knob
-        self.fused_small_gn = os.environ.get("GG_FUSED_SMALL_GN", "0") != "0"
+        self.fused_small_gn = os.environ.get("GG_FUSED_SMALL_GN", "1") != "0"
+        # ... per SAMPLE: a cluster of 8 CTAs walks one sample, so the one-launch form wins only while a sample's slice per
+        # CTA is a few tens of KB (deep levels); larger samples keep the three-kernel form with its 64 KB chunks
+        self.fused_gn_max_bytes = int(os.environ.get("GG_FUSED_GN_MAX_KB", "384")) * 1024
         self.separate_skip = os.environ.get("GG_SEPARATE_SKIP", "0") != "0"     # see _resblock (measured: no gain, off)
         # GroupNorm + SiLU applied inside the depth-rolling conv (no separate pass); GG_FUSED_GN=0 is a tuning knob
         self.fused_gn_apply = os.environ.get("GG_FUSED_GN", "1") != "0"
@@ -299,7 +302,8 @@ class UNetEngine:
     def _gn(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm, silu: bool) -> Act:
         """GroupNorm (+SiLU) over cat([x1, x2], channel) as a materialised tensor."""
         C1, C2 = x1.C, (x2.C if x2 is not None else 0)
-        if (self.fused_small_gn and self.slab is None and x1.N * x1.S * (C1 + C2) * 2 <= (48 << 20) and C1 + C2 <= 2048):
+        if (self.fused_small_gn and self.slab is None and x1.S * (C1 + C2) * 2 <= self.fused_gn_max_bytes and C1 + C2 <= 2048
+                and (256 // ((C1 + C2) // 8)) * (C1 + C2) * 8 + 16 * (C1 + C2) <= 64 * 1024 and (C1 + C2) // 8 <= 256):
             # L2-resident tensor: statistics + apply in one launch (a cluster per sample) instead of three dependent ones
             y = self._new_act(ar, x1.N, x1.sp, C1 + C2)
             plan.add(self.lib.gg_gn_fused, x1.ip, C1, x2.ip if x2 is not None else 0, C2, _C.ptr(self._f32(norm.weight)),

@@ -448,6 +448,26 @@ def test_resident_loop_fused_head_equals_separate_per_voxel_kernel():
         assert torch.equal(runs["separate"][1], runs[name][1])
 
 
+def test_stage_bridge_matches_scipy_zoom_order0():
+    """The stage-1 -> stage-2 bridge of sample_diffusion.py:199-201, ``rot90(zoom(labels, out / in, order=0), k=3) / 255``:
+    GuideGenPipeline.mask_to_ct_grid must reproduce scipy.ndimage.zoom's corner-aligned nearest rule exactly (it is not
+    block replication), incl. the slice-axis resampling 64 -> 96 the reference line uses."""
+    from scipy.ndimage import zoom
+    from jointimagegeneration_b200.pipeline import GuideGenPipeline
+    rs = np.random.RandomState(3)
+    pipe = GuideGenPipeline.__new__(GuideGenPipeline)
+    for shp, out in (((64, 128, 128), (64, 512, 512)), ((64, 128, 128), (96, 512, 512)), ((7, 9, 5), (11, 31, 6))):
+        lab = rs.randint(0, 12, size=shp).astype(np.uint8)
+        want = np.rot90(zoom(lab, np.array(out) / np.array(shp), order=0), k=3, axes=(1, 2)).astype(np.float32) / np.float32(255)
+        got = pipe.mask_to_ct_grid(torch.from_numpy(lab).cuda(), size=out[1:], depth=out[0], rot90_k=3)
+        assert tuple(got.shape) == (1, 1) + want.shape
+        assert np.array_equal(got[0, 0].cpu().numpy(), want), shp
+    # block replication (integer factors) differs from scipy's rule away from the corners -- documented, not hidden
+    lab = rs.randint(0, 12, size=(4, 16, 16)).astype(np.uint8)
+    blk = pipe.mask_to_ct_grid(torch.from_numpy(lab).cuda(), size=(64, 64), mode="block")[0, 0].cpu().numpy()
+    assert np.array_equal(blk, np.repeat(np.repeat(lab, 4, 1), 4, 2).astype(np.float32) / np.float32(255))
+
+
 def test_no_fallback_when_library_missing(monkeypatch):
     """The product path must fail loudly without the CUDA library."""
     from jointimagegeneration_b200 import _C
@@ -708,7 +728,7 @@ def test_two_stage_pipeline_vs_oracle():
     rs = np.random.RandomState(0)
     labels = np.zeros((6, 8, 8), dtype=np.uint8)
     labels[1:5] = rs.randint(0, 12, size=(4, 8, 8))
-    mask = pipe.mask_to_ct_grid(torch.from_numpy(labels).cuda(), size=(32, 32))
+    mask = pipe.mask_to_ct_grid(torch.from_numpy(labels).cuda(), size=(32, 32), mode="block")
     want_mask = np.repeat(np.repeat(labels, 4, 1), 4, 2).astype(np.float32) / 255.0
     assert np.array_equal(mask[0, 0].cpu().numpy(), want_mask.astype(np.float32))
     n = 2
