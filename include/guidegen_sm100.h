@@ -370,7 +370,14 @@ typedef struct {
     int32_t q_hs, k_hs, v_hs, o_hs;                            /* head strides              */
     int32_t B, H, Tq, Tk, d;
     float scale;                                               /* applied to q.k before softmax */
+    /* Device scratch of >= gg_attention_workspace_bytes() bytes (128-byte aligned) or NULL.  With it, shapes the
+     * tensor-core kernel takes (d 32 / 64, Tq, Tk >= 64: attention_tc.cu -- tcgen05.mma for Q K^T and P V with TMEM
+     * accumulators, TMA operands, V^T [B, H, d, Tk] staged in the scratch) run there; without it, or for other
+     * shapes, the mma.sync kernel of attention.cu runs.  Same arguments, same result up to bf16 rounding of P. */
+    void* workspace;
+    int64_t workspace_bytes;
 } gg_attn_args;
+int64_t gg_attention_workspace_bytes(const gg_attn_args* a);      /* 0: the tensor-core kernel does not take this shape */
 int gg_attention_fwd(const gg_attn_args* a, gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

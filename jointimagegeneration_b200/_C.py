@@ -103,7 +103,7 @@ class AttnArgs(C.Structure):
                 ("q_rs", C.c_int32), ("k_rs", C.c_int32), ("v_rs", C.c_int32), ("o_rs", C.c_int32),
                 ("q_hs", C.c_int32), ("k_hs", C.c_int32), ("v_hs", C.c_int32), ("o_hs", C.c_int32),
                 ("B", C.c_int32), ("H", C.c_int32), ("Tq", C.c_int32), ("Tk", C.c_int32), ("d", C.c_int32),
-                ("scale", C.c_float)]
+                ("scale", C.c_float), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 # the ctypes mirrors above, in the order gg_abi_sizes() reports the C structs
@@ -138,6 +138,7 @@ SYMBOLS = {
     "gg_conv_num_tiles": (_i32, [C.POINTER(ConvArgs)]),
     "gg_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "gg_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "gg_attention_workspace_bytes": (_i64, [C.POINTER(AttnArgs)]),
     "gg_attention_fwd": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "gg_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
     "gg_small_linear": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -4,6 +4,8 @@
 // One CTA = 128 query rows of one (batch, head); 8 warps x 16 rows; K/V streamed in 64-key tiles through
 // double-buffered shared memory (cp.async); S = QK^T and O += PV on mma.sync.m16n8k16 (bf16, fp32 acc).
 // Attention is ~0.3 % of the step's FLOPs at the reference shapes.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gg {
@@ -176,10 +178,28 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const gg_attn_ar
 
 using namespace gg;
 
+namespace gg {
+bool attention_tc_ok(const gg_attn_args* a);                    // attention_tc.cu
+int64_t attention_tc_workspace(const gg_attn_args* a);
+int attention_tc_fwd(const gg_attn_args* a, cudaStream_t stream);
+static bool attn_tc_enabled() {
+    static const bool on = [] { const char* e = getenv("GG_ATTN_TC"); return !(e && e[0] == '0'); }();     // tuning knob, read once
+    return on;
+}
+}  // namespace gg
+
+extern "C" int64_t gg_attention_workspace_bytes(const gg_attn_args* a) {
+    if (!a || a->B <= 0 || a->H <= 0 || a->Tq <= 0 || a->Tk <= 0 || !attn_tc_enabled()) return 0;
+    return attention_tc_workspace(a);
+}
+
 extern "C" int gg_attention_fwd(const gg_attn_args* a, gg_stream_t stream) {
     GG_REQUIRE(a && a->q && a->k && a->v && a->o, GG_ERR_BAD_ARG);
     GG_REQUIRE(a->B > 0 && a->H > 0 && a->Tq > 0 && a->Tk > 0, GG_ERR_BAD_ARG);
     GG_REQUIRE(a->d == 32 || a->d == 64, GG_ERR_UNSUPPORTED);
+    GG_REQUIRE(a->H <= 65535 && a->B <= 65535, GG_ERR_UNSUPPORTED);
+    if (a->workspace != nullptr && attn_tc_enabled() && aligned(a->q, 16) && aligned(a->k, 16) && attention_tc_ok(a))
+        return attention_tc_fwd(a, as_stream(stream));
     GG_REQUIRE(aligned(a->q, 16) && aligned(a->k, 16) && aligned(a->v, 16) && aligned(a->o, 4), GG_ERR_ALIGNMENT);
     GG_REQUIRE(a->q_rs % 8 == 0 && a->k_rs % 8 == 0 && a->v_rs % 8 == 0 && a->o_rs % 2 == 0, GG_ERR_ALIGNMENT);
     GG_REQUIRE(a->q_hs % 8 == 0 && a->k_hs % 8 == 0 && a->v_hs % 8 == 0 && a->o_hs % 2 == 0, GG_ERR_ALIGNMENT);

@@ -1,0 +1,422 @@
+// attention_tc.cu -- flash-style softmax(Q K^T * scale) V on the 5th-generation tensor cores
+//
+// Replaces QKVAttentionLegacy (ccdm/ddpm/models/unet_openai/unet.py:334-360, ldm openaimodel.py:350-379) and CrossAttention
+// (ldm/modules/attention.py:152-193) for head dims 32 / 64.  The first-generation kernel (attention.cu) issues mma.sync
+// from every warp and is bound by that; here the two contractions are tcgen05.mma streams issued by one thread with
+// TMEM accumulators, K / V / Q arrive by TMA, and the CUDA cores are left with what only they can do: the exponentials.
+//
+// One CTA = one (batch, head) and TWO 128-row query tiles A and B ("ping-pong": while the eight softmax warps of one tile
+// exponentiate, the tensor core computes the other tile's scores), walking the keys in tiles of 128:
+//
+//     S_g(j) = Q_g K_j^T                M = 128, N = 128, K = d        -> TMEM, 128 columns per tile g
+//     P_g(j) = exp2(S_g(j) c - m_g)     softmax warps: TMEM -> registers -> bf16 -> shared memory (K-major, SWIZZLE_128B)
+//     O_g   += P_g(j) V_j               M = 128, N = d,   K = 128      -> TMEM, d columns per tile g
+//
+// * Operands are the K-major SWIZZLE_128B tiles the convolution kernels use.  Q and K rows are loaded as 64-element
+//   (128-byte) boxes whose channel extent is d: for d = 32 the upper half is TMA zero fill and the MMAs simply stop at
+//   K = 32.  V is needed with the KEYS contiguous (B operand of P V), so a small pre-pass writes V^T [B, H, d, Tk] into a
+//   caller-provided workspace (8 MB for the largest site of config 5) and its [d x 64-key] boxes are ordinary K-major tiles.
+// * Online softmax with LAZY rescaling: a row keeps the maximum it last rescaled to and only when a new tile raises it by
+//   more than 2^8 are l and the O accumulator (tcgen05.ld / st) rescaled; P stays <= 256, exact in fp32 / bf16 terms.
+// * K_j / V_j^T are loaded once per CTA and feed both query tiles (256 queries per key tile).
+//
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = softmax of tile A, warps 6..9 = tile B
+// (warp w touches TMEM lanes 32 (w % 4) ..).  The exponentials bound the kernel: 16 MUFU / clock / SM.
+#include <cstdlib>
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace gg {
+
+constexpr int AT_BM = 128, AT_BN = 128, AT_ST = 3, AT_THREADS = 320;
+constexpr int AT_TILE = 16384;              // 128 rows x 128 B
+
+struct alignas(64) AttnTcParams {
+    CUtensorMap qmap, kmap, vtmap;
+    __nv_bfloat16* o;
+    long long o_bs;
+    int o_rs, o_hs;
+    int H, Tq, Tk, n_kt;
+    float scale_log2;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+// V [B, Tk, H, d] (strided) -> V^T [B, H, d, Tkp] with the keys contiguous (Tkp = Tk rounded up to 8; pad columns zero)
+template <int D>
+__global__ void __launch_bounds__(256) attn_vt_kernel(const __nv_bfloat16* __restrict__ v, long long v_bs, int v_rs, int v_hs,
+                                                      __nv_bfloat16* __restrict__ vt, int H, int Tk, int Tkp) {
+    __shared__ __nv_bfloat16 tile[64][D + 2];
+    const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 64;
+    const __nv_bfloat16* src = v + (long long)b * v_bs + (long long)h * v_hs;
+    for (int i = threadIdx.x; i < 64 * (D / 2); i += 256) {
+        const int key = i / (D / 2), c2 = i % (D / 2);
+        uint32_t w = 0;
+        if (k0 + key < Tk) w = *reinterpret_cast<const uint32_t*>(src + (long long)(k0 + key) * v_rs + 2 * c2);
+        *reinterpret_cast<uint32_t*>(&tile[key][2 * c2]) = w;
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = vt + ((long long)b * H + h) * D * Tkp;
+    for (int i = threadIdx.x; i < D * 32; i += 256) {
+        const int c = i / 32, kp = i % 32;              // two keys per thread
+        const int key = k0 + 2 * kp;
+        if (key < Tkp) {
+            __nv_bfloat162 o;
+            o.x = tile[2 * kp][c];
+            o.y = tile[2 * kp + 1][c];
+            *reinterpret_cast<__nv_bfloat162*>(dst + (long long)c * Tkp + key) = o;
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    constexpr int VT_BYTES = 2 * D * 128;                // two 64-key chunks of [D rows x 128 B]
+    constexpr int KV_BYTES = AT_TILE + VT_BYTES;
+    uint8_t* smem_q = smem;                              // [2][128 x 128 B]
+    uint8_t* smem_kv = smem_q + 2 * AT_TILE;             // [AT_ST][K tile | V^T chunks]
+    uint8_t* smem_p = smem_kv + AT_ST * KV_BYTES;        // [2][2 chunks x 128 x 128 B]
+    uint64_t* q_full = reinterpret_cast<uint64_t*>(smem_p + 4 * AT_TILE);
+    uint64_t* kv_full = q_full + 1;
+    uint64_t* kv_empty = kv_full + AT_ST;
+    uint64_t* s_full = kv_empty + AT_ST;                 // [2]
+    uint64_t* p_full = s_full + 2;                       // [2]
+    uint64_t* pv_done = p_full + 2;                      // [2]
+    uint64_t* s_free = pv_done + 2;                      // [2]  the softmax warps hold S_g(j) in registers: its TMEM columns may be rewritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (2 * AT_BM);
+    const int n_kt = p.n_kt;
+    if (warp == 0 && lane == 0) { prefetch_tmap(&p.qmap); prefetch_tmap(&p.kmap); prefetch_tmap(&p.vtmap); }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(q_full, 1);
+            for (int i = 0; i < AT_ST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&s_free[i], 4); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: S_A [0, 128), S_B [128, 256), O_A [256, 256 + D), O_B [320, 320 + D)
+    constexpr uint32_t COL_S = 0, COL_O = 256, O_STRIDE = 64;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (elect_one()) {
+            mbar_expect_tx(q_full, 2 * AT_TILE);
+            tma_load_4d(smem_q, &p.qmap, q_full, 0, h, q0, b);
+            tma_load_4d(smem_q + AT_TILE, &p.qmap, q_full, 0, h, q0 + AT_BM, b);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_kt; ++j) {
+            const int st = j % AT_ST;
+            mbar_wait(&kv_empty[st], (((uint32_t)(j / AT_ST)) & 1u) ^ 1u);
+            if (elect_one()) {
+                uint8_t* dst = smem_kv + (size_t)st * KV_BYTES;
+                mbar_expect_tx(&kv_full[st], KV_BYTES);
+                tma_load_4d(dst, &p.kmap, &kv_full[st], 0, h, j * AT_BN, b);
+                tma_load_4d(dst + AT_TILE, &p.vtmap, &kv_full[st], j * AT_BN, 0, h, b);
+                tma_load_4d(dst + AT_TILE + D * 128, &p.vtmap, &kv_full[st], j * AT_BN + 64, 0, h, b);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BN >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+        const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+        const uint64_t qd[2] = {make_sw128_desc(smem_u32(smem_q)), make_sw128_desc(smem_u32(smem_q + AT_TILE))};
+        auto issue_s = [&](int g, int st) {
+            const uint64_t kd = make_sw128_desc(smem_u32(smem_kv + (size_t)st * KV_BYTES));
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) umma_bf16(tmem_base + COL_S + (uint32_t)g * AT_BN, qd[g] + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[g]);
+        };
+        auto issue_pv = [&](int g, int st, int j) {
+            const uint8_t* vt = smem_kv + (size_t)st * KV_BYTES + AT_TILE;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const uint64_t pd = make_sw128_desc(smem_u32(smem_p + (size_t)(2 * g + c) * AT_TILE));
+                const uint64_t vd = make_sw128_desc(smem_u32(vt + (size_t)c * D * 128));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + COL_O + (uint32_t)g * O_STRIDE, pd + 2 * k, vd + 2 * k, idesc_pv, (j > 0 || c > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&pv_done[g]);
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        if (elect_one()) { issue_s(0, 0); issue_s(1, 0); }
+        __syncwarp();
+        for (int j = 0; j < n_kt; ++j) {
+            const int st = j % AT_ST, stn = (j + 1) % AT_ST;
+            const uint32_t ph = (uint32_t)j & 1u;
+            const bool more = j + 1 < n_kt;
+            // ---- next scores first: a tile's S columns are free as soon as its softmax warps have pulled S(j) into registers,
+            // long before they finish exponentiating it, so S(j + 1) is waiting for them when they do
+            if (more) mbar_wait(&kv_full[stn], ((uint32_t)((j + 1) / AT_ST)) & 1u);
+            mbar_wait(&s_free[0], ph);
+            tc_fence_after();
+            if (more) { if (elect_one()) issue_s(0, stn); __syncwarp(); }
+            mbar_wait(&s_free[1], ph);
+            tc_fence_after();
+            if (more) { if (elect_one()) issue_s(1, stn); __syncwarp(); }
+            // ---- O_g += P_g(j) V_j once P_g(j) is in shared memory
+            mbar_wait(&p_full[0], ph);
+            tc_fence_after();
+            if (elect_one()) issue_pv(0, st, j);
+            __syncwarp();
+            mbar_wait(&p_full[1], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                issue_pv(1, st, j);
+                umma_commit(&kv_empty[st]);          // every MMA that reads this K / V^T stage has been issued before this commit
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================================================================ softmax + output: warps 2..5 tile A, 6..9 tile B
+        const int g = warp >= 6 ? 1 : 0;
+        const int qd4 = warp & 3;
+        const int row = qd4 * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(qd4 * 32) << 16);
+        const uint32_t s_addr = lane_base + COL_S + (uint32_t)g * AT_BN, o_addr = lane_base + COL_O + (uint32_t)g * O_STRIDE;
+        uint8_t* prow = smem_p + (size_t)(2 * g) * AT_TILE + row * 128;
+        const int swz = row & 7;
+        const float sl2 = p.scale_log2;
+        float m_used = -INFINITY, l = 0.f;
+        for (int j = 0; j < n_kt; ++j) {
+            const uint32_t ph = (uint32_t)j & 1u;
+            mbar_wait(&s_full[g], ph);
+            tc_fence_after();
+            const int key0 = j * AT_BN;
+            const bool tail = key0 + AT_BN > p.Tk;
+            // ---- the whole score row into registers (one TMEM round trip per tile), then hand the S columns back
+            uint32_t r[128];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) tmem_ld16_nowait(s_addr + 16 * c, r + 16 * c);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[g]);
+            if (tail) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (key0 + i >= p.Tk) r[i] = 0xff800000u;       // -inf: never the maximum, exp2 = 0
+            }
+            // ---- row maximum (the scale is positive: maximum of the raw scores, scaled once; four independent three-input chains)
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < 64; ++i) mx4[i & 3] = max3(mx4[i & 3], __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+            const float m_new = fmaxf(m_used, mx);
+            const bool need = m_new > m_used + 8.0f;           // first tile: m_used = -inf
+            bool waited = false;
+            if (__any_sync(0xffffffffu, need)) {
+                const float alpha = need ? ex2_fast(m_used - m_new) : 1.0f;
+                if (need) { m_used = m_new; l *= alpha; }
+                if (j > 0) {        // O_g += ... of tile j - 1 must have landed before it is rescaled (j = 0: PV overwrites)
+                    mbar_wait(&pv_done[g], ph ^ 1u);
+                    tc_fence_after();
+                    waited = true;
+#pragma unroll
+                    for (int c = 0; c < D / 16; ++c) {
+                        uint32_t o16[16];
+                        tmem_ld16(o_addr + 16 * c, o16);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o16[i] = __float_as_uint(__uint_as_float(o16[i]) * alpha);
+                        tmem_st16(o_addr + 16 * c, o16);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
+            }
+            // ---- P = exp2(s c - m_used) as bf16.  Packed f32x2 arithmetic: per PAIR of scores one FMA, two MUFU.EX2, one pack and
+            // one add (the row sum, kept in independent partial sums); the packed P words replace the scores in place
+            const uint64_t sl2x2 = pack_f32x2(sl2, sl2), negm = pack_f32x2(-m_used, -m_used);
+            uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const uint64_t x = fma_f32x2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sl2x2, negm);
+                float x0, x1;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+                const float e0 = ex2_fast(x0), e1 = ex2_fast(x1);
+                r[i] = pack_bf16(e0, e1);
+                ls2[i & 3] = add_f32x2(ls2[i & 3], pack_f32x2(e0, e1));
+            }
+            if (j > 0 && !waited) {          // P_g(j - 1) is being read by its MMAs until they complete
+                mbar_wait(&pv_done[g], ph ^ 1u);
+                tc_fence_after();
+            }
+            // keys 8 q .. 8 q + 7 of this row = 16-byte piece q & 7 of chunk tile q >> 3 (64 keys per tile), swizzled by the row
+#pragma unroll
+            for (int q16 = 0; q16 < 16; ++q16) {
+                uint8_t* base = prow + (size_t)(q16 >> 3) * AT_TILE;
+                *reinterpret_cast<uint4*>(base + (((q16 & 7) ^ swz) << 4)) = make_uint4(r[4 * q16], r[4 * q16 + 1], r[4 * q16 + 2], r[4 * q16 + 3]);
+            }
+            float lsum;
+            {
+                float a0, a1, b0, b1, c0, c1, d0, d1;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ls2[0]));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(ls2[1]));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(ls2[2]));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(ls2[3]));
+                lsum = ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
+            }
+            l += lsum;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic writes -> tensor-core reads
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[g]);
+        }
+        // ---- output: O / l
+        mbar_wait(&pv_done[g], ((uint32_t)(n_kt - 1)) & 1u);
+        tc_fence_after();
+        const int t = q0 + g * AT_BM + row;
+        const float inv = 1.0f / l;
+        __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)t * p.o_rs + (long long)h * p.o_hs;
+#pragma unroll
+        for (int c = 0; c < D / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld16(o_addr + 16 * c, r);
+            tmem_ld_wait();
+            if (t < p.Tq) {
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
+                *reinterpret_cast<uint4*>(orow + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(orow + 16 * c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host
+static bool encode_map4(CUtensorMap* m, const void* base, const int64_t dim[4], const int64_t stride_el[3], const int box[4]) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[4] = {(cuuint64_t)dim[0], (cuuint64_t)dim[1], (cuuint64_t)dim[2], (cuuint64_t)dim[3]};
+    cuuint64_t gstr[3] = {(cuuint64_t)stride_el[0] * 2, (cuuint64_t)stride_el[1] * 2, (cuuint64_t)stride_el[2] * 2};
+    cuuint32_t bx[4] = {(cuuint32_t)box[0], (cuuint32_t)box[1], (cuuint32_t)box[2], (cuuint32_t)box[3]};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static inline int64_t attn_tkp(const gg_attn_args* a) { return ((int64_t)a->Tk + 7) / 8 * 8; }
+
+// shapes the tensor-core kernel takes; everything else stays on attention.cu's kernel
+bool attention_tc_ok(const gg_attn_args* a) {
+    if (!(a->d == 32 || a->d == 64)) return false;
+    // measured (tools/bench_attn.py, B200): 1.25-1.45x the mma.sync kernel from 1024 keys up; below that the V^T pre-pass
+    // and the 256-query CTA granularity cost more than the tensor core saves (T = 256: 0.025 vs 0.015 ms)
+    static const int min_tk = [] { const char* e = getenv("GG_ATTN_TC_MIN_TK"); return e ? atoi(e) : 1024; }();
+    if (a->Tk < min_tk || a->Tk < 64 || a->Tq < 64) return false;
+    if (!aligned(a->o, 16) || a->o_rs % 8 || a->o_hs % 8 || a->o_bs % 8) return false;
+    if (a->q_rs % 8 || a->k_rs % 8 || a->q_hs % 8 || a->k_hs % 8 || a->q_bs % 8 || a->k_bs % 8) return false;
+    if (a->v_rs % 2 || a->v_hs % 2 || a->v_bs % 2 || !aligned(a->v, 4)) return false;
+    // TMA: the smallest stride of each map must be the element stride of the next dimension up; heads before rows
+    return true;
+}
+int64_t attention_tc_workspace(const gg_attn_args* a) { return attention_tc_ok(a) ? (int64_t)a->B * a->H * a->d * attn_tkp(a) * 2 : 0; }
+
+template <int D>
+static int launch_attention_tc(const gg_attn_args* a, cudaStream_t stream) {
+    AttnTcParams p;
+    memset(&p, 0, sizeof(p));
+    const int64_t Tkp = attn_tkp(a);
+    {   // Q / K: (channel [extent d, box 64: zero fill above d], head, token, batch)
+        const int box[4] = {64, 1, AT_BM, 1};
+        const int64_t qdim[4] = {a->d, a->H, a->Tq, a->B}, qstr[3] = {a->q_hs, a->q_rs, a->q_bs};
+        const int64_t kdim[4] = {a->d, a->H, a->Tk, a->B}, kstr[3] = {a->k_hs, a->k_rs, a->k_bs};
+        if (!encode_map4(&p.qmap, a->q, qdim, qstr, box) || !encode_map4(&p.kmap, a->k, kdim, kstr, box)) return GG_ERR_DRIVER;
+        // V^T workspace: (key, channel, head, batch)
+        const int vbox[4] = {64, D, 1, 1};
+        const int64_t vdim[4] = {Tkp, a->d, a->H, a->B}, vstr[3] = {Tkp, (int64_t)a->d * Tkp, (int64_t)a->H * a->d * Tkp};
+        if (!encode_map4(&p.vtmap, a->workspace, vdim, vstr, vbox)) return GG_ERR_DRIVER;
+    }
+    p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.o_bs = a->o_bs; p.o_rs = a->o_rs; p.o_hs = a->o_hs;
+    p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk; p.n_kt = (a->Tk + AT_BN - 1) / AT_BN;
+    p.scale_log2 = a->scale * 1.4426950408889634f;
+    {
+        const dim3 grid((unsigned)((a->Tk + 63) / 64), (unsigned)a->H, (unsigned)a->B);
+        attn_vt_kernel<D><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->v), a->v_bs, a->v_rs, a->v_hs,
+                                                    reinterpret_cast<__nv_bfloat16*>(a->workspace), a->H, a->Tk, (int)Tkp);
+        const int st = launch_result();
+        if (st != GG_OK) return st;
+    }
+    constexpr size_t smem = 1024 + 2 * AT_TILE + AT_ST * (AT_TILE + 2 * D * 128) + 4 * AT_TILE + 256;
+    auto* fn = attention_tc_kernel<D>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const dim3 grid((unsigned)((a->Tq + 2 * AT_BM - 1) / (2 * AT_BM)), (unsigned)a->H, (unsigned)a->B);
+    fn<<<grid, AT_THREADS, smem, stream>>>(p);
+    return launch_result();
+}
+
+int attention_tc_fwd(const gg_attn_args* a, cudaStream_t stream) {
+    if (!encode_fn()) return GG_ERR_DRIVER;
+    GG_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= attention_tc_workspace(a) && aligned(a->workspace, 128), GG_ERR_BAD_ARG);
+    return a->d == 32 ? launch_attention_tc<32>(a, stream) : launch_attention_tc<64>(a, stream);
+}
+
+}  // namespace gg

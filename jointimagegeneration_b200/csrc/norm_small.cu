@@ -247,24 +247,32 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __re
         csum[c] = make_float2(a, b);
     }
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    // ---- group statistics: fp64 over the cluster's CTAs (rank order) and the group's channels
+    // ---- group statistics: fp64 over the cluster's CTAs and the group's channels.  A WARP per group: its lanes stride over the
+    // (rank, channel) pairs -- independent DSMEM loads in flight instead of one thread walking GNF_CL * cpg dependent ones
+    // (that walk alone cost ~10 us per launch) -- then a fixed-order butterfly in fp64: identical in every CTA of the cluster.
     const int cpg = C / groups;
-    for (int g = threadIdx.x; g < groups; g += 256) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < groups; g += 8) {
         double s = 0.0, q = 0.0;
-        for (int r = 0; r < GNF_CL; ++r) {
+        const uint32_t local = (uint32_t)__cvta_generic_to_shared(csum + g * cpg);
+        for (int e = lane; e < GNF_CL * cpg; e += 32) {
+            const int r = e / cpg, c = e - r * cpg;
             uint32_t remote;
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(csum + g * cpg)), "r"(r));
-            for (int c = 0; c < cpg; ++c) {
-                float2 v;
-                asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(remote + 8u * (uint32_t)c));
-                s += (double)v.x; q += (double)v.y;
-            }
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+            float2 v;
+            asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(remote + 8u * (uint32_t)c));
+            s += (double)v.x; q += (double)v.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
         }
         const double cnt = (double)S * cpg, mean = s / cnt;
         double var = q / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
         const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
             const float sc = (gamma ? __ldg(gamma + c) : 1.0f) * rstd;
             ssm[c] = make_float2(sc, (beta ? __ldg(beta + c) : 0.0f) - (float)mean * sc);
         }

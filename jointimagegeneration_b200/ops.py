@@ -395,11 +395,26 @@ def make_attn_args(q, k, v, o, B, H, Tq, Tk, d, scale, q_str, k_str, v_str, o_st
     """*_str = (batch stride, row stride, head stride) in elements."""
     return _C.AttnArgs(_C.ptr(q), _C.ptr(k), _C.ptr(v), _C.ptr(o), q_str[0], k_str[0], v_str[0], o_str[0],
                        q_str[1], k_str[1], v_str[1], o_str[1], q_str[2], k_str[2], v_str[2], o_str[2],
-                       B, H, Tq, Tk, d, float(scale))
+                       B, H, Tq, Tk, d, float(scale), None, 0)
 
 
-def attention_fwd(a: _C.AttnArgs):
+def attention_workspace(a: _C.AttnArgs, device) -> Optional[torch.Tensor]:
+    """Scratch the tensor-core attention kernel wants for this shape (V^T staging), attached to `a`; None if it does not
+    take the shape.  The caller keeps the tensor alive until the launch has run."""
+    n = int(_C.lib().gg_attention_workspace_bytes(C.byref(a)))
+    if n <= 0:
+        return None
+    ws = torch.empty(n, dtype=torch.uint8, device=device)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), n
+    return ws
+
+
+def attention_fwd(a: _C.AttnArgs, device=None):
+    ws = None
+    if device is not None and not a.workspace:
+        ws = attention_workspace(a, device)
     _C.check(_C.lib().gg_attention_fwd(C.byref(a), _C.stream()), "gg_attention_fwd")
+    return ws
 
 
 def attention_legacy(qkv_cl, n_heads, out=None):
@@ -415,7 +430,7 @@ def attention_legacy(qkv_cl, n_heads, out=None):
     a = _C.AttnArgs(base, base + ch * es, base + 2 * ch * es, _C.ptr(out),
                     T * W3, T * W3, T * W3, T * (W3 // 3), W3, W3, W3, W3 // 3, 3 * ch, 3 * ch, 3 * ch, ch,
                     B, n_heads, T, T, ch, 1.0 / math.sqrt(ch))
-    attention_fwd(a)
+    attention_fwd(a, qkv_cl.device)
     return out
 
 

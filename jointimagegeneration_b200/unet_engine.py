@@ -204,7 +204,7 @@ class UNetEngine:
         self.use_roll_conv = True
         # one-launch GroupNorm for L2-resident tensors (gg_gn_fused): measured SLOWER on config 3 (7.24 vs 4.85 ms per step:
         # 8 CTAs per sample leave too few loads in flight), so off; kept as a tested kernel + knob
-        self.fused_small_gn = os.environ.get("GG_FUSED_SMALL_GN", "1") != "0"
+        self.fused_small_gn = os.environ.get("GG_FUSED_SMALL_GN", "0") != "0"
         # ... per SAMPLE: a cluster of 8 CTAs walks one sample, so the one-launch form wins only while a sample's slice per
         # CTA is a few tens of KB (deep levels); larger samples keep the three-kernel form with its 64 KB chunks
         self.fused_gn_max_bytes = int(os.environ.get("GG_FUSED_GN_MAX_KB", "384")) * 1024
@@ -520,6 +520,16 @@ class UNetEngine:
         self._free(ar, h1)
         return out
 
+    def _attn_workspace(self, plan, ar, aa):
+        """V^T staging of the tensor-core attention kernel (gg_attn_args.workspace); released right after the launch is
+        planned (stream order: nothing planned later can write it before this launch has read it)."""
+        n = int(self.lib.gg_attention_workspace_bytes(C.byref(aa)))
+        if n > 0:
+            ws = ar.alloc((n,), torch.uint8)
+            aa.workspace, aa.workspace_bytes = ws.data_ptr(), n
+            plan.keep.append(ws)
+            ar.release(ws)
+
     def _heads(self, ch):
         return self.num_heads if self.num_head_channels == -1 else ch // self.num_head_channels
 
@@ -544,7 +554,8 @@ class UNetEngine:
             plan.add_py(self.slab.all_gather, gathered, qkv.interior)
             kbase, Tk = gathered.data_ptr(), R * S
         aa = _C.AttnArgs(qbase, kbase + d * 2, kbase + 2 * d * 2, o.ip, S * W3, Tk * W3, Tk * W3, S * Cc, W3, W3, W3, Cc,
-                         3 * d, 3 * d, 3 * d, d, N, H, S, Tk, d, 1.0 / math.sqrt(d))
+                         3 * d, 3 * d, 3 * d, d, N, H, S, Tk, d, 1.0 / math.sqrt(d), None, 0)
+        self._attn_workspace(plan, ar, aa)
         plan.keep.append(aa)
         plan.add(self.lib.gg_attention_fwd, C.byref(aa))
         plan.flops += 4 * N * H * S * Tk * d
@@ -586,7 +597,8 @@ class UNetEngine:
             bufs = [q.t, kv.t]
         o = self._new_act(ar, N, xq.sp, inner)
         aa = _C.AttnArgs(qp, kp, vp, o.ip, q_str[0], k_str[0], k_str[0], Tq * inner, q_str[1], k_str[1], k_str[1], inner,
-                         d, d, d, d, N, H, Tq, Tk, d, float(ca.scale))
+                         d, d, d, d, N, H, Tq, Tk, d, float(ca.scale), None, 0)
+        self._attn_workspace(plan, ar, aa)
         plan.keep.append(aa)
         plan.add(self.lib.gg_attention_fwd, C.byref(aa))
         plan.flops += 4 * N * H * Tq * Tk * d

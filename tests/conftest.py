@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# the tensor-core attention kernel normally takes >= 1024 keys (where it wins); the tests push every shape it CAN take
+# (>= 64 keys) through it, so the small networks of the parity tests exercise it too
+os.environ.setdefault("GG_ATTN_TC_MIN_TK", "64")
 
 
 def pytest_configure(config):

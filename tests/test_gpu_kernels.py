@@ -474,6 +474,32 @@ def test_attention_cross(ops):
     assert rel_err(heads_of(o, H), want) <= 1e-2
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,d", [(2, 5, 300, 77, 64), (1, 8, 1024, 512, 64), (2, 3, 200, 333, 32), (1, 8, 4096, 4096, 32),
+                                         (1, 2, 64, 2000, 32)])
+def test_attention_tensor_core_kernel(ops, B, H, Tq, Tk, d):
+    """attention_tc.cu (tcgen05 Q K^T and P V, TMEM accumulators, TMA operands, lazy online-softmax rescaling) through
+    gg_attention_fwd with a workspace: cross-attention shapes (separate q / kv tensors, ragged Tq / Tk, key-tail masking,
+    d = 32 and 64) and a long self-attention, against fp32 softmax attention.  Large score ranges exercise the rescaling."""
+    from jointimagegeneration_b200 import _C
+    import ctypes as C_
+    no_tf32()
+    rs = np.random.RandomState(7)
+    W = H * d
+    q = torch.from_numpy((rs.standard_normal((B, Tq, W)) * 2.0).astype(np.float32)).cuda().to(torch.bfloat16)
+    kv = torch.from_numpy((rs.standard_normal((B, Tk, 2 * W)) * 2.0).astype(np.float32)).cuda().to(torch.bfloat16)
+    o = torch.full((B, Tq, W), float("nan"), dtype=torch.bfloat16, device="cuda")
+    a = ops.make_attn_args(q, kv, kv[..., W:], o, B, H, Tq, Tk, d, d ** -0.5, (Tq * W, W, d), (Tk * 2 * W, 2 * W, d),
+                           (Tk * 2 * W, 2 * W, d), (Tq * W, W, d))
+    a.v = kv.data_ptr() + W * 2
+    assert int(_C.lib().gg_attention_workspace_bytes(C_.byref(a))) > 0, "the tensor-core kernel should take this shape"
+    ws = ops.attention_fwd(a, q.device)
+    assert ws is not None
+    torch.cuda.synchronize()
+    assert not torch.isnan(o.float()).any()
+    want = attention_ref(heads_of(q, H), heads_of(kv[..., :W], H), heads_of(kv[..., W:], H), d ** -0.5)
+    assert rel_err(heads_of(o, H), want) <= 1e-2
+
+
 # ------------------------------------------------------------------------------ small pieces
 def test_timestep_embedding_and_small_linear(ops):
     from oracle import nets
