@@ -688,7 +688,22 @@ def slab_section(args):
     x = torch.zeros((1, Cc) + spatial, device=dev).scatter_(1, lab[:, None], 1.0)
     cond = torch.zeros((1, 1) + spatial, device=dev)
     rec = slab_check.unsplit_chain(m, x, cond, [13, 12, 11], seed=5)
-    comm = SlabComm()
+    # transport: gg_peer_exchange kernels over NVLink peer memory (graph-capturable, no NCCL on the data path); if the
+    # cudaIpc mapping is not available on this box, the host-enqueued NCCL transport of round 1
+    comm, why = None, None
+    if os.environ.get("GG_SLAB_TRANSPORT", "peer") == "peer":
+        try:
+            from jointimagegeneration_b200.sharding import PeerSlabComm
+            comm = PeerSlabComm(arena_bytes=int(os.environ.get("GG_SLAB_ARENA_MB", "3072")) << 20)
+        except Exception as e:  # noqa: BLE001
+            comm, why = None, repr(e)[:200]
+    ok = torch.tensor([1.0 if comm is not None else 0.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok) == 0.0:
+        if comm is not None:
+            comm.close()
+        comm = SlabComm()
+        out["transport_fallback_reason"] = why or "a peer rank could not map the arenas"
     res = slab_check.reduce_over_ranks(slab_check.slab_vs_unsplit(m, rec, world, comm), dev)
     out.update(parity_volume=list(spatial), parity_max_abs=res["parity_max_abs"], bit_equal=res["bit_equal"],
                label_agreement_teacher_forced=res["agree"],
@@ -731,25 +746,33 @@ def slab_section(args):
     torch.cuda.empty_cache()
     lo, hi = slab_ranges(full[0], world)[rank]
     model.unet.enable_slab(comm)
-    model.use_cuda_graph = False
+    model.use_cuda_graph = bool(getattr(comm, "peer", False))     # kernels only -> the slab forward replays as a CUDA graph
     e0, g0, b0 = comm.n_exchanges, comm.n_gathers, comm.bytes_sent
     st = model.resident_begin(x_T[:, :, lo:hi].contiguous(), cond[:, :, lo:hi].contiguous())
     n_warm, n = 2, 5
     msN = timed(st, n_warm, n)
     nf = n_warm + n
+    peer = bool(getattr(comm, "peer", False))
+    nfp = 1 if peer else nf           # the peer transport counts at PLAN time (one plan), the NCCL one at every call
     out.update(volume=list(full), slabs=world, ms_per_step=msN, ms_per_step_n1=ms1, steps_per_sec=1e3 / msN,
                speedup_vs_n1=ms1 / msN, efficiency=ms1 / msN / world,
-               halo_exchanges_per_forward=(comm.n_exchanges - e0) / nf, gathers_per_forward=(comm.n_gathers - g0) / nf,
-               nvlink_bytes_sent_per_forward=(comm.bytes_sent - b0) / nf, transport=getattr(comm, "transport", "nccl"))
-    # communication share: CUDA-event time around the host-enqueued collective steps of one forward
+               halo_exchanges_per_forward=(comm.n_exchanges - e0) / nfp, gathers_per_forward=(comm.n_gathers - g0) / nfp,
+               nvlink_bytes_sent_per_forward=(comm.bytes_sent - b0) / nfp, transport=getattr(comm, "transport", "nccl"),
+               cuda_graph=bool(model.use_cuda_graph))
+    # communication share: CUDA-event time around the collective steps of one forward (eager; includes waiting for the peers)
     kinds, _ = instrument_plan(st["plan"], reps=2)
-    cm = {k: round(_max_over_ranks(v[0], dev, world), 3) for k, v in kinds.items() if k in ("all_gather", "exchange_halo")}
+    cm = {k: round(_max_over_ranks(v[0], dev, world), 3) for k, v in kinds.items()
+          if k in ("all_gather", "exchange_halo", "gg_peer_exchange", "gg_peer_epoch_inc")}
     out["comm_ms"] = cm
     out["comm_frac_of_step"] = sum(cm.values()) / msN if cm else None
     del st
     model.unet.invalidate()
     model.unet.enable_slab(None)
     del model
+    torch.cuda.synchronize()
+    dist.barrier()
+    if hasattr(comm, "close"):
+        comm.close()
     torch.cuda.empty_cache()
     return out
 

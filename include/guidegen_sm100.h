@@ -405,6 +405,40 @@ int gg_geglu(const void* x, void* y, int64_t rows, int32_t inner, gg_stream_t st
 int gg_softmax_rows(const float* x, void* y, int64_t rows, int32_t n, float scale, gg_stream_t stream);
 int gg_transpose_bf16(const void* x, void* y, int32_t R, int32_t C, gg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Depth-slab collectives over NVLink peer memory (BASELINE config 5).  The reference has no
+ * multi-GPU inference path; the semantics are those of its single-device forward (unet.py:758-823): every conv sees
+ * its neighbours' boundary planes, every GroupNorm the statistics of the whole volume, every attention site all keys.
+ * Each rank owns a peer-visible arena (gg_peer_alloc; exported with gg_peer_export, mapped by the peers with
+ * gg_peer_open -- cudaIpc handles exchanged by the host language's own means, e.g. torch.distributed) laid out
+ * identically on every rank.  gg_peer_exchange is ONE kernel per collective site:
+ *   phase 1: copy src[i] -> dst[i] (dst = addresses inside PEER arenas), system fence, then store *epoch into
+ *            flag_out[i] (addresses inside peer arenas);
+ *   phase 2: wait until every flag_in[i] (my arena) has reached *epoch, then csrc[i] -> cdst[i] local copies
+ *            (staging slot -> halo plane) and zero fills (halo planes at the ends of the volume).
+ * phase = 3 does both (the multi-process case); 1 / 2 let a single process emulate R ranks on one device by running
+ * phase 1 of every rank before phase 2 of any (tests).  *epoch is bumped once per forward by gg_peer_epoch_inc.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t nsend;
+    const void* src[8]; void* dst[8]; int64_t bytes[8];
+    int32_t nflag_out; uint32_t* flag_out[8];
+    int32_t nflag_in; const uint32_t* flag_in[8];
+    int32_t ncopy; const void* csrc[4]; void* cdst[4]; int64_t cbytes[4];
+    int32_t nzero; void* zdst[2]; int64_t zbytes[2];
+    const uint32_t* epoch;          /* device counter of this rank                                              */
+    unsigned int* done_counter;     /* device word, 0 between launches (last-CTA detection)                      */
+    int32_t phase;                  /* 1, 2 or 3                                                                 */
+    int32_t ctas;                   /* 0 = by payload size                                                        */
+} gg_peer_xchg_args;
+int gg_peer_alloc(int64_t bytes, void** out);                 /* cudaMalloc'd, zero-filled                       */
+int gg_peer_free(void* p);
+int gg_peer_export(void* p, uint8_t* handle64);                /* 64-byte cudaIpcMemHandle_t                      */
+int gg_peer_open(const uint8_t* handle64, void** out);
+int gg_peer_close(void* p);
+int gg_peer_epoch_inc(uint32_t* epoch, gg_stream_t stream);
+int gg_peer_exchange(const gg_peer_xchg_args* a, gg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,8 +106,18 @@ class AttnArgs(C.Structure):
                 ("scale", C.c_float), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
+class PeerXchgArgs(C.Structure):
+    _fields_ = [("nsend", C.c_int32), ("src", C.c_void_p * 8), ("dst", C.c_void_p * 8), ("bytes", C.c_int64 * 8),
+                ("nflag_out", C.c_int32), ("flag_out", C.c_void_p * 8),
+                ("nflag_in", C.c_int32), ("flag_in", C.c_void_p * 8),
+                ("ncopy", C.c_int32), ("csrc", C.c_void_p * 4), ("cdst", C.c_void_p * 4), ("cbytes", C.c_int64 * 4),
+                ("nzero", C.c_int32), ("zdst", C.c_void_p * 2), ("zbytes", C.c_int64 * 2),
+                ("epoch", C.c_void_p), ("done_counter", C.c_void_p), ("phase", C.c_int32), ("ctas", C.c_int32)]
+
+
 # the ctypes mirrors above, in the order gg_abi_sizes() reports the C structs
-ABI_STRUCTS = [CatArgs, CatStepCLArgs, DdimArgs, PlmsArgs, DdpmArgs, GnFinalizeArgs, ConvSrc, ConvArgs, AttnArgs, CatEpilogue]
+ABI_STRUCTS = [CatArgs, CatStepCLArgs, DdimArgs, PlmsArgs, DdpmArgs, GnFinalizeArgs, ConvSrc, ConvArgs, AttnArgs, CatEpilogue,
+               PeerXchgArgs]
 
 # every symbol include/guidegen_sm100.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -147,6 +157,13 @@ SYMBOLS = {
     "gg_geglu": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "gg_softmax_rows": (C.c_int, [_vp, _vp, _i64, _i32, _f32, _vp]),
     "gg_transpose_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "gg_peer_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p)]),
+    "gg_peer_free": (C.c_int, [_vp]),
+    "gg_peer_export": (C.c_int, [_vp, C.c_char_p]),
+    "gg_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "gg_peer_close": (C.c_int, [_vp]),
+    "gg_peer_epoch_inc": (C.c_int, [_vp, _vp]),
+    "gg_peer_exchange": (C.c_int, [C.POINTER(PeerXchgArgs), _vp]),
 }
 
 

@@ -10,13 +10,13 @@ extern "C" {
 int gg_version(void) { return 200; }
 
 int gg_abi_sizes(int32_t* out, int n) {
-    const int32_t sz[10] = {(int32_t)sizeof(gg_cat_args), (int32_t)sizeof(gg_cat_step_cl_args), (int32_t)sizeof(gg_ddim_args),
+    const int32_t sz[11] = {(int32_t)sizeof(gg_cat_args), (int32_t)sizeof(gg_cat_step_cl_args), (int32_t)sizeof(gg_ddim_args),
                            (int32_t)sizeof(gg_plms_args), (int32_t)sizeof(gg_ddpm_args), (int32_t)sizeof(gg_gn_finalize_args),
                            (int32_t)sizeof(gg_conv_src), (int32_t)sizeof(gg_conv_args), (int32_t)sizeof(gg_attn_args),
-                            (int32_t)sizeof(gg_cat_epilogue)};
-    for (int i = 0; i < 10 && i < n; ++i)
+                            (int32_t)sizeof(gg_cat_epilogue), (int32_t)sizeof(gg_peer_xchg_args)};
+    for (int i = 0; i < 11 && i < n; ++i)
         if (out) out[i] = sz[i];
-    return 10;
+    return 11;
 }
 
 const char* gg_status_string(int status) {

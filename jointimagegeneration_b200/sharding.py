@@ -216,3 +216,243 @@ class LocalSlabGroup:
             self.comms[r].n_gathers += 1
             for q in range(R):
                 out[q * n:(q + 1) * n].copy_(argv[q][1].reshape(-1))
+
+
+# ================================================================ depth-slab collectives over NVLink peer memory
+class PeerBuf:
+    """A region of this rank's peer-visible communication arena (quacks like a tensor for _C.ptr)."""
+
+    def __init__(self, ptr: int, nbytes: int, offset: int):
+        self.ptr, self.nbytes, self.offset = ptr, nbytes, offset
+
+    def data_ptr(self) -> int:
+        return self.ptr
+
+
+class PeerArena:
+    """This rank's peer-visible arena (cudaMalloc through the C ABI so that cudaIpc can export it) and the base addresses
+    of every peer's arena as mapped into this process.  The layout is symmetric: offset X means the same slot everywhere."""
+
+    def __init__(self, nbytes: int):
+        import ctypes as C
+        from . import _C
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        _C.check(_C.lib().gg_peer_alloc(self.nbytes, C.byref(p)), "gg_peer_alloc")
+        self.base = int(p.value)
+        self.used = 0
+        self.peer_base = None
+        self._opened = []
+
+    def export_handle(self) -> bytes:
+        import ctypes as C
+        from . import _C
+        h = C.create_string_buffer(64)
+        _C.check(_C.lib().gg_peer_export(C.c_void_p(self.base), h), "gg_peer_export")
+        return h.raw
+
+    def open_peers(self, handles, rank: int):
+        import ctypes as C
+        from . import _C
+        self.peer_base = []
+        for r, h in enumerate(handles):
+            if r == rank:
+                self.peer_base.append(self.base)
+                continue
+            p = C.c_void_p()
+            _C.check(_C.lib().gg_peer_open(C.create_string_buffer(h, 64), C.byref(p)), "gg_peer_open")
+            self.peer_base.append(int(p.value))
+            self._opened.append(int(p.value))
+
+    def alloc(self, nbytes: int, align: int = 256) -> PeerBuf:
+        off = (self.used + align - 1) // align * align
+        if off + nbytes > self.nbytes:
+            raise MemoryError(f"peer communication arena exhausted ({self.nbytes} bytes): pass a larger arena_bytes to PeerSlabComm")
+        self.used = off + nbytes
+        return PeerBuf(self.base + off, nbytes, off)
+
+    def close(self):
+        import ctypes as C
+        from . import _C
+        for p in self._opened:
+            _C.lib().gg_peer_close(C.c_void_p(p))
+        self._opened = []
+        if self.base:
+            _C.lib().gg_peer_free(C.c_void_p(self.base))
+            self.base = 0
+
+
+class PeerSlabComm:
+    """SlabComm whose collectives are gg_peer_exchange kernels over NVLink peer memory (csrc/peer_comm.cu) instead of
+    host-enqueued NCCL calls: planned as ordinary library launches, so the slab forward is CUDA-graph capturable and a
+    GroupNorm combine costs a few microseconds instead of an NCCL all-gather.  torch.distributed is used once, at
+    construction, to exchange the 64-byte cudaIpc handles of the arenas.
+
+    ``peers``: None = one process per rank (the real thing); or a list of PeerArena of the OTHER virtual ranks living in
+    this process (tests on one GPU: LocalPeerGroup)."""
+
+    transport = "nvlink-peer"
+    peer = True
+
+    def __init__(self, group=None, arena_bytes: int = 256 << 20, _virtual=None):
+        import torch
+        self.group = group
+        self.arena = PeerArena(arena_bytes)
+        if _virtual is not None:
+            self.rank, self.world = _virtual
+        else:
+            self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+            handles = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, self.arena.export_handle(), group=group)
+            else:
+                handles = [b""]
+            self.arena.open_peers(handles, self.rank)
+        assert self.world <= 8
+        self.bytes_sent = self.n_exchanges = self.n_gathers = 0
+        self.n_forwards = 0
+        self.epoch = self.arena.alloc(256)            # [0]: epoch counter, [64]: last-CTA counter
+        self._sites = 0
+        self._keep = []
+        self._torch = torch
+
+    # -- planning helpers ---------------------------------------------------------------------------------------
+    def _peer_addr(self, r: int, buf: PeerBuf, extra: int = 0) -> int:
+        return self.arena.peer_base[r] + buf.offset + extra
+
+    def _new_args(self):
+        from . import _C
+        a = _C.PeerXchgArgs()
+        a.epoch, a.done_counter, a.phase, a.ctas = self.epoch.ptr, self.epoch.ptr + 64, 3, 0
+        self._keep.append(a)
+        return a
+
+    def alloc(self, nbytes: int) -> PeerBuf:
+        """Peer-visible buffer (the destination of an all-gather must live in the arena)."""
+        return self.arena.alloc(int(nbytes))
+
+    def plan_begin(self, plan):
+        """First step of a slab plan: one epoch per forward."""
+        from . import _C
+        plan.add(_C.lib().gg_peer_epoch_inc, self.epoch.ptr)
+        self.n_forwards_planned = getattr(self, "n_forwards_planned", 0) + 1
+
+    def plan_exchange_halo(self, plan, t, lead: int, depth: int, need_lo: bool = True, need_hi: bool = True):
+        """t: [1, lead + depth + trail, H, W, C] local activation.  My last interior plane -> next rank's low-halo staging slot,
+        my first -> previous rank's high-halo slot; then wait for my neighbours' planes and copy them from the staging slots
+        into t's halo planes (zeros at the ends of the volume)."""
+        import ctypes as C
+        from . import _C
+        r, R = self.rank, self.world
+        pb = t.shape[2] * t.shape[3] * t.shape[4] * t.element_size()
+        base = t.data_ptr()
+        stage = self.arena.alloc(2 * pb)              # [0]: plane arriving from rank r - 1 (low halo), [1]: from rank r + 1
+        flags = self.arena.alloc(64)                  # [0]: raised by rank r - 1, [1]: by rank r + 1
+        a = self._new_args()
+        ns = nfo = nfi = nc = nz = 0
+        if need_lo:
+            if r < R - 1:                             # the next rank needs my last plane as ITS low halo
+                a.src[ns], a.dst[ns], a.bytes[ns] = base + (lead + depth - 1) * pb, self._peer_addr(r + 1, stage, 0), pb
+                ns += 1
+                a.flag_out[nfo] = self._peer_addr(r + 1, flags, 0)
+                nfo += 1
+                self.bytes_sent += pb
+            if r > 0:
+                a.flag_in[nfi] = flags.ptr
+                nfi += 1
+                a.csrc[nc], a.cdst[nc], a.cbytes[nc] = stage.ptr, base + (lead - 1) * pb, pb
+                nc += 1
+            else:
+                a.zdst[nz], a.zbytes[nz] = base + (lead - 1) * pb, pb
+                nz += 1
+        if need_hi:
+            if r > 0:                                 # the previous rank needs my first plane as ITS high halo
+                a.src[ns], a.dst[ns], a.bytes[ns] = base + lead * pb, self._peer_addr(r - 1, stage, pb), pb
+                ns += 1
+                a.flag_out[nfo] = self._peer_addr(r - 1, flags, 4)
+                nfo += 1
+                self.bytes_sent += pb
+            if r < R - 1:
+                a.flag_in[nfi] = flags.ptr + 4
+                nfi += 1
+                a.csrc[nc], a.cdst[nc], a.cbytes[nc] = stage.ptr + pb, base + (lead + depth) * pb, pb
+                nc += 1
+            else:
+                a.zdst[nz], a.zbytes[nz] = base + (lead + depth) * pb, pb
+                nz += 1
+        a.nsend, a.nflag_out, a.nflag_in, a.ncopy, a.nzero = ns, nfo, nfi, nc, nz
+        self.n_exchanges += 1
+        plan.add(_C.lib().gg_peer_exchange, C.byref(a))
+        plan.keep.append(a)
+
+    def plan_all_gather(self, plan, out: PeerBuf, inp_ptr: int, nbytes: int):
+        """out (in the arena, world * nbytes) = concatenation over ranks of the nbytes at inp_ptr."""
+        import ctypes as C
+        from . import _C
+        r, R = self.rank, self.world
+        assert out.nbytes >= R * nbytes and nbytes % 16 == 0
+        flags = self.arena.alloc(64)                  # [q]: raised by rank q
+        a = self._new_args()
+        ns = nfo = nfi = 0
+        for q in range(R):
+            a.src[ns], a.dst[ns], a.bytes[ns] = inp_ptr, self._peer_addr(q, out, r * nbytes), nbytes
+            ns += 1
+            if q != r:
+                a.flag_out[nfo] = self._peer_addr(q, flags, 4 * r)
+                nfo += 1
+                a.flag_in[nfi] = flags.ptr + 4 * q
+                nfi += 1
+                self.bytes_sent += nbytes
+        a.nsend, a.nflag_out, a.nflag_in, a.ncopy, a.nzero = ns, nfo, nfi, 0, 0
+        self.n_gathers += 1
+        plan.add(_C.lib().gg_peer_exchange, C.byref(a))
+        plan.keep.append(a)
+
+    def broadcast_int(self, value: int) -> int:
+        if self.world == 1 or not dist.is_initialized():
+            return int(value)
+        box = [int(value)]
+        dist.broadcast_object_list(box, src=0 if self.group is None else dist.get_global_rank(self.group, 0), group=self.group)
+        return int(box[0])
+
+    def close(self):
+        self.arena.close()
+
+
+class LocalPeerGroup:
+    """R virtual ranks of the peer-memory transport on ONE device (tests): every rank has its own arena, all "peer" base
+    addresses are plain local pointers, and the lock-step runner executes every gg_peer_exchange step as phase 1 of all
+    ranks followed by phase 2 of all ranks (a single stream cannot interleave R spinning kernels)."""
+
+    def __init__(self, world: int, arena_bytes: int = 128 << 20):
+        self.world = world
+        self.comms = [PeerSlabComm(arena_bytes=arena_bytes, _virtual=(r, world)) for r in range(world)]
+        bases = [c.arena.base for c in self.comms]
+        for c in self.comms:
+            c.arena.peer_base = list(bases)
+
+    def run(self, plans):
+        import ctypes as C
+        from . import _C
+        lib = _C.lib()
+        s = _C.stream()
+        n = len(plans[0].steps)
+        assert all(len(p.steps) == n for p in plans), "virtual ranks must hold identical plans"
+        for i in range(n):
+            fn0 = plans[0].steps[i][0]
+            if getattr(fn0, "__name__", "") == "gg_peer_exchange":
+                for phase in (1, 2):
+                    for p in plans:
+                        fn, args = p.steps[i]
+                        a = args[0]._obj
+                        a.phase = phase
+                        _C.check(fn(*args, s), "gg_peer_exchange")
+                        a.phase = 3
+                continue
+            for p in plans:
+                fn, args = p.steps[i]
+                _C.check(fn(*args, s), getattr(fn, "__name__", "step"))
+
+    def close(self):
+        for c in self.comms:
+            c.close()

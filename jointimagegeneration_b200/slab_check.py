@@ -26,7 +26,11 @@ from .sharding import LocalSlabGroup, slab_ranges
 class SlabSession:
     """The slab plan(s) this process executes: one real rank (comm given) or all `world` virtual ranks."""
 
-    def __init__(self, unet, spatial_full, world: int, comm=None):
+    def __init__(self, unet, spatial_full, world: int, comm=None, transport: str = "copy"):
+        """comm: this process' SlabComm / PeerSlabComm (one real rank), or None = all `world` ranks emulated here with
+        transport "copy" (LocalSlabGroup: collectives as device copies) or "peer" (LocalPeerGroup: the gg_peer_exchange
+        kernels with every arena in this process)."""
+        from .sharding import LocalPeerGroup
         from .unet_engine import UNetEngine
         self.unet, self.world, self.spatial = unet, world, tuple(spatial_full)
         self.ranges = slab_ranges(spatial_full[0], world)
@@ -40,7 +44,7 @@ class SlabSession:
             self.group = None
             self.plans = [unet.plan_for(1, self.local_sp)]
         else:
-            self.group = LocalSlabGroup(world)
+            self.group = LocalPeerGroup(world) if transport == "peer" else LocalSlabGroup(world)
             self.ranks = list(range(world))
             self.engines = []
             for r in self.ranks:
@@ -53,6 +57,11 @@ class SlabSession:
         if self.comm is not None:
             self.unet.enable_slab(None)
         self.plans = []
+        if self.group is not None and hasattr(self.group, "close"):
+            import torch
+            torch.cuda.synchronize()
+            self.engines = []
+            self.group.close()
 
     def load_input(self, xin_full: torch.Tensor, t: float):
         """xin_full: the unsplit plan's input, CL bf16 [1, D, H, W, Cpad]."""
@@ -118,11 +127,11 @@ def unsplit_chain(model, x: torch.Tensor, cond: torch.Tensor, t_values, seed: in
 
 
 @torch.no_grad()
-def slab_vs_unsplit(model, rec: dict, world: int, comm=None) -> dict:
+def slab_vs_unsplit(model, rec: dict, world: int, comm=None, transport: str = "copy") -> dict:
     """Runs the recorded chain through the slab plans (teacher-forced) and compares.  Returns, for the ranks this process
     holds: parity_max_abs (probabilities of step 0), bit_equal, the per-plane max-abs profile, per-step label agreement."""
     C, spatial = rec["C"], rec["spatial"]
-    ses = SlabSession(model.unet, spatial, world, comm)
+    ses = SlabSession(model.unet, spatial, world, comm, transport)
     try:
         Dl = ses.local_sp[0]
         res = dict(world=world, ranks=list(ses.ranks), parity_max_abs=0.0, bit_equal=True, plane_max_abs=[], agree=[])

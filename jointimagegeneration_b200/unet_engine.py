@@ -260,7 +260,10 @@ class UNetEngine:
     def _exchange(self, plan, x: Act, need_lo=True, need_hi=True):
         if self.slab is None or x.lead == 0 or x.halo_valid:
             return
-        plan.add_py(self.slab.exchange_halo, x.t, x.lead, x.sp[0], need_lo, need_hi)
+        if getattr(self.slab, "peer", False):       # one kernel over NVLink peer memory (csrc/peer_comm.cu), graph-capturable
+            self.slab.plan_exchange_halo(plan, x.t, x.lead, x.sp[0], need_lo, need_hi)
+        else:
+            plan.add_py(self.slab.exchange_halo, x.t, x.lead, x.sp[0], need_lo, need_hi)
         x.halo_valid = need_lo and need_hi
 
     # --------------------------------------------------------------------------- primitives
@@ -282,6 +285,11 @@ class UNetEngine:
                 plan.add(lib.gg_gn_partial, x.ip, N, S, Cx, _C.ptr(p))
                 x.stats = (p, n)               # skip tensors are normalised twice: keep the sums with the activation
             if R > 1:       # every rank needs the statistics of the whole volume: gather the partials
+                if getattr(self.slab, "peer", False):
+                    nb = N * n * Cx * 2 * 4
+                    g = self.slab.alloc(R * nb)                  # peer-visible; every rank writes its rows into every arena
+                    self.slab.plan_all_gather(plan, g, p.data_ptr(), nb)
+                    return g, R * n
                 g = ar.alloc((N, R * n, Cx, 2), torch.float32)
                 plan.add_py(self.slab.all_gather, g, p)
                 temps.append(g)
@@ -550,8 +558,12 @@ class UNetEngine:
         if R > 1:
             # queries stay local, keys/values of the whole volume are gathered (slabs are contiguous in depth,
             # tokens are ordered (d, h, w), so rank order == global token order)
-            gathered = ar.alloc((R * S, W3), torch.bfloat16)
-            plan.add_py(self.slab.all_gather, gathered, qkv.interior)
+            if getattr(self.slab, "peer", False):
+                gathered = self.slab.alloc(R * S * W3 * 2)
+                self.slab.plan_all_gather(plan, gathered, qkv.ip, S * W3 * 2)
+            else:
+                gathered = ar.alloc((R * S, W3), torch.bfloat16)
+                plan.add_py(self.slab.all_gather, gathered, qkv.interior)
             kbase, Tk = gathered.data_ptr(), R * S
         aa = _C.AttnArgs(qbase, kbase + d * 2, kbase + 2 * d * 2, o.ip, S * W3, Tk * W3, Tk * W3, S * Cc, W3, W3, W3, Cc,
                          3 * d, 3 * d, 3 * d, d, N, H, S, Tk, d, 1.0 / math.sqrt(d), None, 0)
@@ -726,6 +738,8 @@ class UNetEngine:
         t_in = torch.zeros((N,), dtype=torch.float32, device=dev)
         plan.inputs["x"], plan.inputs["t"] = x_in, t_in
         plan.keep.append(x_full)
+        if self.slab is not None and getattr(self.slab, "peer", False):
+            self.slab.plan_begin(plan)              # one communication epoch per forward
         ctx = None
         if ctx_shape is not None:
             L, cd = ctx_shape

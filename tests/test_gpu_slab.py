@@ -73,3 +73,24 @@ def test_virtual_slab_world8_planes_per_rank_16():
     res = slab_check.slab_vs_unsplit(m, rec, 8)
     print(f"world 8: slab vs unsplit max-abs {res['parity_max_abs']:.3e}; label agreement {res['agree']}")
     assert res["parity_max_abs"] <= 1e-2 and min(res["agree"]) >= 0.995
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_virtual_slab_ranks_over_peer_memory_kernels(world):
+    """The NVLink peer-memory transport (csrc/peer_comm.cu: one gg_peer_exchange kernel per halo exchange / GroupNorm
+    combine / key-value gather, flags + epochs instead of NCCL) with every rank's arena in this process: the R plans run
+    in lock step, phase 1 (push + raise flags) of all ranks before phase 2 (wait + unpack) of any.  Same parity bar as the
+    copy transport; two forwards in a row exercise the epoch / flag reuse."""
+    from jointimagegeneration_b200 import slab_check
+    from oracle import weights
+    spatial = (16 * world, 32, 32)
+    m, _ = _model(spatial)
+    x = weights.uniform_one_hot(4, 1, C, spatial).cuda()
+    cond = torch.zeros(1, 1, *spatial).cuda()
+    rec = slab_check.unsplit_chain(m, x, cond, [13, 12, 11], seed=5)
+    copy = slab_check.slab_vs_unsplit(m, rec, world, transport="copy")
+    peer = slab_check.slab_vs_unsplit(m, rec, world, transport="peer")
+    print(f"world {world} peer transport: slab vs unsplit max-abs {peer['parity_max_abs']:.3e}; label agreement {peer['agree']}")
+    assert peer["parity_max_abs"] == copy["parity_max_abs"]          # the transport moves bytes: identical results
+    assert peer["agree"] == copy["agree"]
+    assert peer["parity_max_abs"] <= 1e-2 and min(peer["agree"]) >= 0.995
