@@ -394,6 +394,10 @@ def bench_config(workload, B, world):
 def describe_launch(name, fargs, ms):
     import ctypes
     from jointimagegeneration_b200 import _C
+    if name == "gg_peer_exchange":
+        xa = fargs[0]._obj
+        return "gg_peer_exchange sends %d (%s B) waits %d copies %d : %.3f ms" % (
+            xa.nsend, "+".join(str(int(xa.bytes[i])) for i in range(xa.nsend)), xa.nflag_in, xa.ncopy, ms)
     if name != "gg_conv_fwd":
         return "%s : %.3f ms" % (name, ms)
     ca = fargs[0]._obj
@@ -760,7 +764,9 @@ def slab_section(args):
                nvlink_bytes_sent_per_forward=(comm.bytes_sent - b0) / nfp, transport=getattr(comm, "transport", "nccl"),
                cuda_graph=bool(model.use_cuda_graph))
     # communication share: CUDA-event time around the collective steps of one forward (eager; includes waiting for the peers)
-    kinds, _ = instrument_plan(st["plan"], reps=2)
+    kinds, _ = instrument_plan(st["plan"], reps=2, detail_path=os.path.join(ROOT, "gpurun_out", "bench_detail_slab_n%d_r%d.txt" % (world, rank))
+                               if args.detail else None)
+    out["kernel_ms_rank0"] = {k: round(v[0], 3) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
     cm = {k: round(_max_over_ranks(v[0], dev, world), 3) for k, v in kinds.items()
           if k in ("all_gather", "exchange_halo", "gg_peer_exchange", "gg_peer_epoch_inc")}
     out["comm_ms"] = cm

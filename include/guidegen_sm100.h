@@ -224,6 +224,17 @@ typedef struct {
     const float* gamma; const float* beta;                 /* [C1+C2] */
     float* scale_shift;                                    /* out fp32 [N, C1+C2, 2]       */
     int32_t N; int32_t groups; int64_t S; float eps;
+    /* Depth-slab mode over NVLink peer memory (slab_world > 1; see gg_peer_exchange): the partial rows are this RANK's,
+     * S is the whole volume's position count.  Phase 1 stores this rank's (sum, sum sq) per (sample, group) -- fp64,
+     * 16 bytes each -- into entry [slab_rank] of every rank's table slab_tables[q] ([world][N][groups][2] fp64, inside
+     * the peer arenas) and raises *slab_epoch in slab_flag_out[q]; phase 2 waits for slab_flag_in[q] and combines the
+     * entries in rank order.  slab_phase = 3: both (two launches). */
+    int32_t slab_world, slab_rank, slab_phase;
+    void* slab_tables[8];
+    uint32_t* slab_flag_out[8];
+    const uint32_t* slab_flag_in[8];
+    const uint32_t* slab_epoch;
+    unsigned int* slab_done_counter;
 } gg_gn_finalize_args;
 int gg_gn_finalize(const gg_gn_finalize_args* a, gg_stream_t stream);
 int gg_gn_apply(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* scale_shift,

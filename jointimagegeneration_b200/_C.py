@@ -63,7 +63,10 @@ class GnFinalizeArgs(C.Structure):
     _fields_ = [("partial1", C.c_void_p), ("C1", C.c_int32), ("nchunks1", C.c_int32),
                 ("partial2", C.c_void_p), ("C2", C.c_int32), ("nchunks2", C.c_int32),
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("scale_shift", C.c_void_p),
-                ("N", C.c_int32), ("groups", C.c_int32), ("S", C.c_int64), ("eps", C.c_float)]
+                ("N", C.c_int32), ("groups", C.c_int32), ("S", C.c_int64), ("eps", C.c_float),
+                ("slab_world", C.c_int32), ("slab_rank", C.c_int32), ("slab_phase", C.c_int32),
+                ("slab_tables", C.c_void_p * 8), ("slab_flag_out", C.c_void_p * 8), ("slab_flag_in", C.c_void_p * 8),
+                ("slab_epoch", C.c_void_p), ("slab_done_counter", C.c_void_p)]
 
 
 class PlmsArgs(C.Structure):

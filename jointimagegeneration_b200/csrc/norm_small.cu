@@ -61,10 +61,10 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
 }
 
 // step 2: group statistics in fp64 from the fp32 partials -> per-(n, channel) scale / shift
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const gg_gn_finalize_args a) {
+// (sum, sum of squares) of group g of sample n over the partial rows, in fp64, identical in every thread of the block
+__device__ __forceinline__ void gn_group_sums(const gg_gn_finalize_args& a, int g, int n, double& s_out, double& ss_out) {
     const int C = a.C1 + a.C2;
     const int cpg = C / a.groups;
-    const int g = blockIdx.x, n = blockIdx.y;
     double s = 0.0, ss = 0.0;
     // One flat index space over (partial row, channel of the group): 128 threads stride over it with four independent
     // loads in flight, instead of walking the group's channels one after the other (a launch used to cost cpg
@@ -111,8 +111,14 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const gg_gn_finalize_a
     }
     if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
     __syncthreads();
-    s = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
-    ss = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+    s_out = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+    ss_out = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void gn_write_scale_shift(const gg_gn_finalize_args& a, int g, int n, double s, double ss) {
+    const int C = a.C1 + a.C2;
+    const int cpg = C / a.groups;
     const double cnt = (double)a.S * cpg;
     const double mean = s / cnt;
     double var = ss / cnt - mean * mean;
@@ -125,6 +131,67 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const gg_gn_finalize_a
         a.scale_shift[((int64_t)n * C + c) * 2] = sc;
         a.scale_shift[((int64_t)n * C + c) * 2 + 1] = be - (float)mean * sc;
     }
+}
+
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const gg_gn_finalize_args a) {
+    double s, ss;
+    gn_group_sums(a, blockIdx.x, blockIdx.y, s, ss);
+    gn_write_scale_shift(a, blockIdx.x, blockIdx.y, s, ss);
+}
+
+// Depth-slab mode over NVLink peer memory: the statistics of the WHOLE volume from the ranks' group sums.  push: this
+// rank's (sum, sum sq) per (sample, group) -- 16 bytes each, not the partial-row tables -- stored straight into every
+// rank's table, then the epoch into the peers' flags (last block); combine: wait for the peers' flags, add the R entries
+// in rank order (identical statistics on every rank) and write scale / shift.
+__global__ void __launch_bounds__(128) gn_slab_push_kernel(const gg_gn_finalize_args a) {
+    const int g = blockIdx.x, n = blockIdx.y;
+    double s, ss;
+    gn_group_sums(a, g, n, s, ss);
+    if (threadIdx.x < a.slab_world) {
+        double* t = reinterpret_cast<double*>(a.slab_tables[threadIdx.x]) + (((int64_t)a.slab_rank * a.N + n) * a.groups + g) * 2;
+        t[0] = s; t[1] = ss;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int is_last;
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y;
+        is_last = atomicInc(a.slab_done_counter, total - 1u) == total - 1u;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < a.slab_world && threadIdx.x != a.slab_rank) {
+        __threadfence_system();
+        const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(a.slab_epoch);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.slab_flag_out[threadIdx.x]), "r"(epoch) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(128) gn_slab_combine_kernel(const gg_gn_finalize_args a) {
+    const int g = blockIdx.x, n = blockIdx.y;
+    const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(a.slab_epoch);
+    if (threadIdx.x < a.slab_world && threadIdx.x != a.slab_rank) {
+        const uint32_t* f = a.slab_flag_in[threadIdx.x];
+        uint64_t t0 = 0;
+        uint32_t spins = 0, v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int32_t)(v - epoch) < 0 && (++spins & 0x3FFu) == 0) {
+                uint64_t now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 10000000000ull) __trap();
+            }
+        } while ((int32_t)(v - epoch) < 0);
+    }
+    __syncthreads();
+    __threadfence_system();
+    double s = 0.0, ss = 0.0;
+    const double* mine = reinterpret_cast<const double*>(a.slab_tables[a.slab_rank]);
+    for (int r = 0; r < a.slab_world; ++r) {
+        const double* t = mine + (((int64_t)r * a.N + n) * a.groups + g) * 2;
+        s += __ldcg(t); ss += __ldcg(t + 1);
+    }
+    gn_write_scale_shift(a, g, n, s, ss);
 }
 
 // step 3: y = act(x * scale + shift), concat of two sources written as one CL tensor.
@@ -479,6 +546,23 @@ extern "C" int gg_gn_finalize(const gg_gn_finalize_args* a, gg_stream_t stream) 
     GG_REQUIRE(a && a->partial1 && a->scale_shift && a->N > 0 && a->groups > 0 && a->S > 0, GG_ERR_BAD_ARG);
     GG_REQUIRE(a->C2 == 0 || a->partial2, GG_ERR_BAD_ARG);
     GG_REQUIRE((a->C1 + a->C2) % a->groups == 0, GG_ERR_UNSUPPORTED);
+    if (a->slab_world > 1) {
+        GG_REQUIRE(a->slab_world <= 8 && a->slab_rank >= 0 && a->slab_rank < a->slab_world && a->slab_epoch && a->slab_done_counter &&
+                   (a->slab_phase & 3) != 0, GG_ERR_BAD_ARG);
+        for (int r = 0; r < a->slab_world; ++r)
+            GG_REQUIRE(a->slab_tables[r] != nullptr && (r == a->slab_rank || (a->slab_flag_out[r] && a->slab_flag_in[r])), GG_ERR_BAD_ARG);
+        dim3 sgrid(a->groups, a->N);
+        if (a->slab_phase & 1) {
+            gn_slab_push_kernel<<<sgrid, 128, 0, as_stream(stream)>>>(*a);
+            const int st = launch_result();
+            if (st != GG_OK) return st;
+        }
+        if (a->slab_phase & 2) {
+            gn_slab_combine_kernel<<<sgrid, 128, 0, as_stream(stream)>>>(*a);
+            return launch_result();
+        }
+        return GG_OK;
+    }
     dim3 grid(a->groups, a->N);
     gn_finalize_kernel<<<grid, 128, 0, as_stream(stream)>>>(*a);
     return launch_result();

@@ -337,7 +337,7 @@ class PeerSlabComm:
         plan.add(_C.lib().gg_peer_epoch_inc, self.epoch.ptr)
         self.n_forwards_planned = getattr(self, "n_forwards_planned", 0) + 1
 
-    def plan_exchange_halo(self, plan, t, lead: int, depth: int, need_lo: bool = True, need_hi: bool = True):
+    def plan_exchange_halo(self, plan, t, lead: int, depth: int, need_lo: bool = True, need_hi: bool = True, split: bool = False):
         """t: [1, lead + depth + trail, H, W, C] local activation.  My last interior plane -> next rank's low-halo staging slot,
         my first -> previous rank's high-halo slot; then wait for my neighbours' planes and copy them from the staging slots
         into t's halo planes (zeros at the ends of the volume)."""
@@ -382,6 +382,34 @@ class PeerSlabComm:
                 nz += 1
         a.nsend, a.nflag_out, a.nflag_in, a.ncopy, a.nzero = ns, nfo, nfi, nc, nz
         self.n_exchanges += 1
+        if not split:
+            plan.add(_C.lib().gg_peer_exchange, C.byref(a))
+            plan.keep.append(a)
+            return None
+        # split: the push now, the wait + unpack later (returned closure) -- lets a GroupNorm combine of the same tensor share
+        # the round trip (both pushes in flight before either wait)
+        a1, a2 = _C.PeerXchgArgs.from_buffer_copy(a), _C.PeerXchgArgs.from_buffer_copy(a)
+        a1.phase, a2.phase = 1, 2
+        plan.add(_C.lib().gg_peer_exchange, C.byref(a1))
+        plan.keep.extend([a1, a2])
+
+        def finish():
+            plan.add(_C.lib().gg_peer_exchange, C.byref(a2))
+        return finish
+
+    def plan_zero(self, plan, regions):
+        """Local zero fills [(ptr, nbytes), ...] (halo planes beyond the ends of the volume) as one gg_peer_exchange launch
+        without sends or waits; nothing is planned when there is nothing to clear."""
+        import ctypes as C
+        from . import _C
+        regions = [(p, n) for p, n in regions if n > 0]
+        if not regions:
+            return
+        a = self._new_args()
+        a.phase = 2
+        for i, (ptr, nbytes) in enumerate(regions):
+            a.zdst[i], a.zbytes[i] = ptr, nbytes
+        a.nzero = len(regions)
         plan.add(_C.lib().gg_peer_exchange, C.byref(a))
         plan.keep.append(a)
 
@@ -408,6 +436,23 @@ class PeerSlabComm:
         plan.add(_C.lib().gg_peer_exchange, C.byref(a))
         plan.keep.append(a)
 
+    def attach_group_norm(self, fa, N: int, groups: int):
+        """Turns a gg_gn_finalize call over this rank's partial rows into the whole-volume statistics: its push kernel stores
+        16 bytes per (sample, group) into every rank's table, its combine kernel waits for the peers and adds the R entries
+        in rank order (gg_gn_finalize_args.slab_*)."""
+        r, R = self.rank, self.world
+        tab = self.arena.alloc(R * N * groups * 16)
+        flags = self.arena.alloc(64)
+        fa.slab_world, fa.slab_rank, fa.slab_phase = R, r, 3
+        for q in range(R):
+            fa.slab_tables[q] = self._peer_addr(q, tab)
+            if q != r:
+                fa.slab_flag_out[q] = self._peer_addr(q, flags, 4 * r)
+                fa.slab_flag_in[q] = flags.ptr + 4 * q
+        fa.slab_epoch, fa.slab_done_counter = self.epoch.ptr, self.epoch.ptr + 64
+        self.n_gathers += 1
+        self.bytes_sent += (R - 1) * N * groups * 16
+
     def broadcast_int(self, value: int) -> int:
         if self.world == 1 or not dist.is_initialized():
             return int(value)
@@ -431,27 +476,50 @@ class LocalPeerGroup:
         for c in self.comms:
             c.arena.peer_base = list(bases)
 
+    @staticmethod
+    def _collective_field(step):
+        """None for a local step; else the name of the phase field of a step that talks to the other ranks."""
+        fn, args = step
+        name = getattr(fn, "__name__", "")
+        if name == "gg_peer_exchange":
+            a = args[0]._obj
+            return "phase" if (a.nsend or a.nflag_out or a.nflag_in) else None
+        if name == "gg_gn_finalize" and args[0]._obj.slab_world > 1:
+            return "slab_phase"
+        return None
+
     def run(self, plans):
-        import ctypes as C
+        """Every rank runs its local steps up to its next collective step; the collective then runs as phase 1 of all ranks
+        followed by phase 2 of all ranks (split steps -- a pure push or a pure wait -- run as they are).  Ranks may hold
+        different numbers of LOCAL steps (edge ranks clear the halo planes beyond the volume); the collective steps match."""
         from . import _C
-        lib = _C.lib()
         s = _C.stream()
-        n = len(plans[0].steps)
-        assert all(len(p.steps) == n for p in plans), "virtual ranks must hold identical plans"
-        for i in range(n):
-            fn0 = plans[0].steps[i][0]
-            if getattr(fn0, "__name__", "") == "gg_peer_exchange":
-                for phase in (1, 2):
-                    for p in plans:
-                        fn, args = p.steps[i]
-                        a = args[0]._obj
-                        a.phase = phase
-                        _C.check(fn(*args, s), "gg_peer_exchange")
-                        a.phase = 3
-                continue
-            for p in plans:
-                fn, args = p.steps[i]
-                _C.check(fn(*args, s), getattr(fn, "__name__", "step"))
+        cur = [0] * len(plans)
+        while True:
+            for r, p in enumerate(plans):               # local steps
+                while cur[r] < len(p.steps) and self._collective_field(p.steps[cur[r]]) is None:
+                    fn, args = p.steps[cur[r]]
+                    _C.check(fn(*args, s), getattr(fn, "__name__", "step"))
+                    cur[r] += 1
+            done = [cur[r] >= len(p.steps) for r, p in enumerate(plans)]
+            if all(done):
+                return
+            assert not any(done), "virtual ranks disagree on the number of collective steps"
+            steps = [p.steps[cur[r]] for r, p in enumerate(plans)]
+            fields = [self._collective_field(st) for st in steps]
+            assert len(set(fields)) == 1 and len({getattr(st[0], "__name__", "") for st in steps}) == 1
+            field = fields[0]
+            phases = {getattr(st[1][0]._obj, field) for st in steps}
+            assert len(phases) == 1, "virtual ranks disagree on the phase of a collective step"
+            for phase in ((1, 2) if phases == {3} else tuple(phases)):
+                for fn, args in steps:
+                    a = args[0]._obj
+                    old = getattr(a, field)
+                    setattr(a, field, phase)
+                    _C.check(fn(*args, s), getattr(fn, "__name__", "step"))
+                    setattr(a, field, old)
+            for r in range(len(plans)):
+                cur[r] += 1
 
     def close(self):
         for c in self.comms:

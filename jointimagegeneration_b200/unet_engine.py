@@ -266,9 +266,30 @@ class UNetEngine:
             plan.add_py(self.slab.exchange_halo, x.t, x.lead, x.sp[0], need_lo, need_hi)
         x.halo_valid = need_lo and need_hi
 
+    def _halo_overlap(self, plan, xs, need_lo=True, need_hi=True):
+        """For _gn_scale_shift(overlap=...): plans the halo pushes of the activations `xs` now and returns the planner of the
+        matching waits; marks the halos valid.  None when there is nothing to overlap (no peer-memory slab mode)."""
+        if self.slab is None or not getattr(self.slab, "peer", False) or self.slab.world == 1:
+            return None
+        todo = [x for x in xs if x.lead and not x.halo_valid]
+
+        def push():
+            fins = [self.slab.plan_exchange_halo(plan, x.t, x.lead, x.sp[0], need_lo, need_hi, split=True) for x in todo]
+            for x in todo:
+                x.halo_valid = need_lo and need_hi
+
+            def finish():
+                for f in fins:
+                    f()
+            return finish
+        return push
+
     # --------------------------------------------------------------------------- primitives
-    def _gn_scale_shift(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm) -> torch.Tensor:
-        """Per-(sample, channel) (scale, shift) of GroupNorm over cat([x1, x2], channel): fp32 [N, C1 + C2, 2]."""
+    def _gn_scale_shift(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm, overlap=None) -> torch.Tensor:
+        """Per-(sample, channel) (scale, shift) of GroupNorm over cat([x1, x2], channel): fp32 [N, C1 + C2, 2].
+        overlap (peer-memory slab mode): a callable that plans further pushes (the halo planes of the same tensors) and returns
+        the callable planning their waits -- they are placed between this GroupNorm's push and its combine, so that both
+        exchanges share one NVLink round trip."""
         lib = self.lib
         N, S = x1.N, x1.S
         C1, C2 = x1.C, (x2.C if x2 is not None else 0)
@@ -284,12 +305,9 @@ class UNetEngine:
                 p = ar.alloc((N, n, Cx, 2), torch.float32)
                 plan.add(lib.gg_gn_partial, x.ip, N, S, Cx, _C.ptr(p))
                 x.stats = (p, n)               # skip tensors are normalised twice: keep the sums with the activation
-            if R > 1:       # every rank needs the statistics of the whole volume: gather the partials
-                if getattr(self.slab, "peer", False):
-                    nb = N * n * Cx * 2 * 4
-                    g = self.slab.alloc(R * nb)                  # peer-visible; every rank writes its rows into every arena
-                    self.slab.plan_all_gather(plan, g, p.data_ptr(), nb)
-                    return g, R * n
+            if R > 1 and not getattr(self.slab, "peer", False):
+                # every rank needs the statistics of the whole volume: gather the partial rows (NCCL transport; the peer-memory
+                # transport exchanges 16 bytes per group inside gg_gn_finalize instead, see below)
                 g = ar.alloc((N, R * n, Cx, 2), torch.float32)
                 plan.add_py(self.slab.all_gather, g, p)
                 temps.append(g)
@@ -301,14 +319,30 @@ class UNetEngine:
         ss = ar.alloc((N, C1 + C2, 2), torch.float32)
         fa = _C.GnFinalizeArgs(_C.ptr(p1), C1, n1, _C.ptr(p2), C2, n2, _C.ptr(self._f32(norm.weight)),
                                _C.ptr(self._f32(norm.bias)), _C.ptr(ss), N, norm.groups, S * R, float(norm.eps))
+        if R > 1 and getattr(self.slab, "peer", False):
+            self.slab.attach_group_norm(fa, N, norm.groups)
+            if overlap is not None:
+                f1, f2 = _C.GnFinalizeArgs.from_buffer_copy(fa), _C.GnFinalizeArgs.from_buffer_copy(fa)
+                f1.slab_phase, f2.slab_phase = 1, 2
+                plan.keep.extend([f1, f2])
+                plan.add(lib.gg_gn_finalize, C.byref(f1))      # push my group sums
+                finish = overlap()                                # push my boundary planes
+                plan.add(lib.gg_gn_finalize, C.byref(f2))      # wait for the peers' sums, combine
+                finish()                                          # wait for the peers' planes, unpack
+                for tbuf in temps:
+                    ar.release(tbuf)
+                return ss
+        elif overlap is not None:
+            overlap()()
         plan.keep.append(fa)
         plan.add(lib.gg_gn_finalize, C.byref(fa))
         for tbuf in temps:
             ar.release(tbuf)
         return ss
 
-    def _gn(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm, silu: bool) -> Act:
-        """GroupNorm (+SiLU) over cat([x1, x2], channel) as a materialised tensor."""
+    def _gn(self, plan: Plan, ar: _Arena, x1: Act, x2: Optional[Act], norm: M.ParamNorm, silu: bool, with_halo: bool = False) -> Act:
+        """GroupNorm (+SiLU) over cat([x1, x2], channel) as a materialised tensor.  with_halo: the consumer is a conv with three
+        depth taps (depth-slab mode: the result must carry valid halo planes)."""
         C1, C2 = x1.C, (x2.C if x2 is not None else 0)
         if (self.fused_small_gn and self.slab is None and x1.S * (C1 + C2) * 2 <= self.fused_gn_max_bytes and C1 + C2 <= 2048
                 and (256 // ((C1 + C2) // 8)) * (C1 + C2) * 8 + 16 * (C1 + C2) <= 64 * 1024 and (C1 + C2) // 8 <= 256):
@@ -316,6 +350,23 @@ class UNetEngine:
             y = self._new_act(ar, x1.N, x1.sp, C1 + C2)
             plan.add(self.lib.gg_gn_fused, x1.ip, C1, x2.ip if x2 is not None else 0, C2, _C.ptr(self._f32(norm.weight)),
                      _C.ptr(self._f32(norm.bias)), y.ip, x1.N, x1.S, norm.groups, float(norm.eps), int(silu))
+            return y
+        xs = [x1] + ([x2] if x2 is not None else [])
+        if with_halo and self.slab is not None and getattr(self.slab, "peer", False) and self.slab.world > 1 and x1.lead:
+            # depth slabs over peer memory: exchange the RAW boundary planes while the group sums travel (one round trip for
+            # both), then normalise the interior together with the halo planes that hold a neighbour's data; the planes beyond
+            # the ends of the volume stay zero (the reference pads the NORMALISED tensor)
+            ss = self._gn_scale_shift(plan, ar, x1, x2, norm, overlap=self._halo_overlap(plan, xs))
+            y = self._new_act(ar, x1.N, x1.sp, C1 + C2)
+            lo = 1 if self.slab.rank > 0 else 0
+            hi = 1 if self.slab.rank < self.slab.world - 1 else 0
+            pp = x1.sp[1] * x1.sp[2]                       # positions per plane
+            plan.add(self.lib.gg_gn_apply, x1.ip - lo * x1.plane_bytes, C1, (x2.ip - lo * x2.plane_bytes) if x2 is not None else 0, C2,
+                     _C.ptr(ss), y.ip - lo * y.plane_bytes, x1.N, x1.S + (lo + hi) * pp, int(silu))
+            self.slab.plan_zero(plan, [(y.ip - y.plane_bytes, 0 if lo else y.plane_bytes),
+                                       (y.ip + x1.sp[0] * y.plane_bytes, 0 if hi else y.plane_bytes)])
+            y.halo_valid = True
+            ar.release(ss)
             return y
         ss = self._gn_scale_shift(plan, ar, x1, x2, norm)
         y = self._new_act(ar, x1.N, x1.sp, C1 + C2)
@@ -332,13 +383,14 @@ class UNetEngine:
         C1, C2 = x1.C, (x2.C if x2 is not None else 0)
         fuse = (self.fused_gn_apply and self._roll_ok(dims, 1, None, None, cout, x1.sp, None)
                 and (C1 + C2) * 8 <= 4096 and C1 % 64 == 0 and C2 % 64 == 0)
+        taps3 = dims >= 3 and kw.get("ksize", 3) == 3 and kw.get("stride", 1) == 1 and kw.get("taps") is None
         if not fuse:
-            a = self._gn(plan, ar, x1, x2, norm, silu)
+            a = self._gn(plan, ar, x1, x2, norm, silu, with_halo=taps3)
             out = self._conv(plan, ar, [(a, False)] + list(extra_srcs), packer([a.C]), cout, dims=dims, **kw)
             self._free(ar, a)
             return out
-        ss = self._gn_scale_shift(plan, ar, x1, x2, norm)
         xs = [x1] + ([x2] if x2 is not None else [])
+        ss = self._gn_scale_shift(plan, ar, x1, x2, norm, overlap=self._halo_overlap(plan, xs) if taps3 else None)
         ptrs, off = [], 0
         for x in xs:
             ptrs.append(_C.ptr(ss) + 8 * off)
