@@ -351,6 +351,10 @@ typedef struct {
     int32_t ss_stride, xf_silu, xf_z_lo, xf_z_hi;
     /* NULL, or (algo 4, Cout <= 16): replace the output store by the sampler epilogue above; y is not written. */
     const gg_cat_epilogue* cat;
+    /* split_k > 1: NULL = the partial tiles are summed by a second (reduce) launch; else gg_conv_num_tiles() device words,
+     * ZERO before the first launch and owned by this conv (not reused by other launches): the split of a tile that finishes
+     * last sums the partials in split order and writes the output itself -- one launch, same result. */
+    uint32_t* split_counters;
 } gg_conv_args;
 
 /* N tile (accumulator columns) the kernel uses for a given Cout */

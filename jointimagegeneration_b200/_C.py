@@ -97,7 +97,7 @@ class ConvArgs(C.Structure):
                 ("gn_partial", C.c_void_p), ("gn_chunk_base", C.c_int32), ("gn_nchunks_total", C.c_int32),
                 ("stats_d_min", C.c_int32), ("algo", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p),
                 ("src_ss", C.c_void_p * 4), ("ss_stride", C.c_int32), ("xf_silu", C.c_int32),
-                ("xf_z_lo", C.c_int32), ("xf_z_hi", C.c_int32), ("cat", C.POINTER(CatEpilogue))]
+                ("xf_z_lo", C.c_int32), ("xf_z_hi", C.c_int32), ("cat", C.POINTER(CatEpilogue)), ("split_counters", C.c_void_p)]
 
 
 class AttnArgs(C.Structure):

@@ -60,6 +60,7 @@ struct alignas(64) ConvParams {
     int split_k;
     float* workspace;      // [split_k, No*Do*Ho*Wo, Cout8]
     long long ws_split_stride;
+    unsigned int* split_counters;   // [total_tiles], zero between launches: the LAST split of a tile to finish reduces it in-kernel
 };
 
 // ------------------------------------------------------------------------------------ kernel
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
     uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    volatile uint32_t* split_last = tmem_slot + 2;      // split-K fix-up: "this CTA finished the tile last" (epilogue warps)
     float* bvec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);     // [BN] bias (+ emb[n] when a tile = one sample)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -225,6 +227,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 acc ^= 1u;
                 if (acc == 0) acc_phase ^= 1u;
+                if (p.split_counters != nullptr) {
+                    // In-kernel fix-up (no separate reduce launch): whichever split of this tile finishes LAST sums the partial
+                    // tiles in split order 0, 1, ... -- the same order whoever is last, so the result is reproducible -- and runs
+                    // the real epilogue (bias, embedding, residual, rounding, store).  atomicInc wraps the counter back to 0.
+                    __threadfence();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (threadIdx.x == 64) *split_last = atomicInc(p.split_counters + tile, (unsigned int)p.split_k - 1u) == (unsigned int)p.split_k - 1u;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (*split_last && valid) {
+                        __threadfence();
+                        const float* wbase = p.workspace + lin * p.Cout8 + nt * BN;
+                        for (int c = 0; c < ncols; c += 8) {
+                            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            for (int s2 = 0; s2 < p.split_k; ++s2) {
+                                const float* wp = wbase + (long long)s2 * p.ws_split_stride + c;
+                                const float4 a4 = __ldcg(reinterpret_cast<const float4*>(wp)), b4 = __ldcg(reinterpret_cast<const float4*>(wp + 4));
+                                v[0] += a4.x; v[1] += a4.y; v[2] += a4.z; v[3] += a4.w; v[4] += b4.x; v[5] += b4.y; v[6] += b4.z; v[7] += b4.w;
+                            }
+                            const int cg = nt * BN + c;
+                            if (p.bias) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] += __ldg(p.bias + cg + e);
+                            }
+                            if (embp) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] += __ldg(embp + cg + e);
+                            }
+                            if (p.residual) {
+                                const uint4 rr = ldg_nc_u4(p.residual + lin * p.res_stride + cg);
+                                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                            }
+                            if (p.y_is_f32) {
+                                float* yp = reinterpret_cast<float*>(p.y) + yoff + cg;
+                                *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+                                *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                            } else {
+                                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + cg) =
+                                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            }
+                        }
+                    }
+                }
                 continue;
             }
             if (p.gn_partial == nullptr) {
@@ -652,11 +697,12 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
         p.split_k = a->split_k;
         p.workspace = a->workspace;
         p.ws_split_stride = (long long)a->N * a->Do * a->Ho * a->Wo * p.Cout8;
+        p.split_counters = a->split_counters;
     }
     const int grid = (int)std::min<int64_t>((int64_t)p.total_tiles * p.split_k, num_sms());
     conv_tcgen05_kernel<<<grid, NUM_THREADS, smem, as_stream(stream)>>>(p);
     int st = launch_result();
-    if (st != GG_OK || p.split_k == 1) return st;
+    if (st != GG_OK || p.split_k == 1 || p.split_counters != nullptr) return st;
     const long long npos = (long long)a->N * a->Do * a->Ho * a->Wo;
     const long long nthr = npos * (p.Cout8 / 8);
     splitk_reduce_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, as_stream(stream)>>>(p, npos);

@@ -212,6 +212,10 @@ class UNetEngine:
         # GroupNorm + SiLU applied inside the depth-rolling conv (no separate pass); GG_FUSED_GN=0 is a tuning knob
         self.fused_gn_apply = os.environ.get("GG_FUSED_GN", "1") != "0"
         self.use_split_k = True
+        # in-kernel split-K reduction (the last split of a tile sums the partials itself, gg_conv_args.split_counters) instead of
+        # the second launch: bit-identical, but only that CTA's 128 epilogue threads do the summing -- measured SLOWER
+        # (config 3: 8.5 vs 4.8 ms per step), so off; kept as a tested knob
+        self.splitk_fixup = os.environ.get("GG_SPLITK_FIXUP", "0") != "0"
         self.num_sms = torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count \
             if next(model.parameters()).is_cuda else 148
         self.halo_gn_stats = os.environ.get("GG_HALO_STATS", "1") != "0"    # ... except in the halo / roll kernels (shuffle-reduced per tile)
@@ -512,6 +516,12 @@ class UNetEngine:
             if tiles * 2 <= self.num_sms and S >= 2:
                 ws = ar.alloc((S, N * int(math.prod(kernel_out_sp)), cout8), torch.float32)
                 a.split_k, a.workspace = S, _C.ptr(ws)
+                if self.splitk_fixup:
+                    # the last split of a tile to finish reduces it in the same launch: a few dedicated zeroed words per tile
+                    # (not arena memory: nothing else may ever write them)
+                    cnt = torch.zeros((int(self.lib.gg_conv_num_tiles(C.byref(a))),), dtype=torch.int32, device=ws.device)
+                    a.split_counters = cnt.data_ptr()
+                    plan.keep.append(cnt)
                 plan.keep.append(ws)
                 ar.release(ws)          # stream order: the reduce launch of this conv is done before any later kernel
         plan.keep.append(a)

@@ -272,6 +272,23 @@ def _conv_case(ops, N, sp, Cs, Cout, dims, k=3, stride=1, bias=True, emb=False, 
         a.gn_partial, a.gn_chunk_base, a.gn_nchunks_total = _C.ptr(part), 2, per + 3
     ops.conv_fwd(a)
     torch.cuda.synchronize()
+    if split_k > 1:
+        # the in-kernel fix-up (gg_conv_args.split_counters: the last split of a tile to finish sums the partials in split order
+        # and writes the output in the same launch) must give exactly the two-launch result, launch after launch
+        import ctypes as C
+        from jointimagegeneration_b200 import _C
+        cnt = torch.zeros((int(_C.lib().gg_conv_num_tiles(C.byref(a))),), dtype=torch.int32, device="cuda")
+        y2 = torch.full_like(y, float("nan"))
+        a.y, a.split_counters = y2.data_ptr(), cnt.data_ptr()
+        n0 = _C.launch_count()
+        for _ in range(3):
+            y2.fill_(float("nan"))
+            ops.conv_fwd(a)
+            torch.cuda.synchronize()
+            assert torch.equal(y2.view(torch.uint8), y.view(torch.uint8)), "split-K fix-up differs from the reduce launch"
+            assert int(cnt.abs().sum()) == 0, "tile counters must wrap back to zero"
+        assert _C.launch_count() - n0 == 3, "one launch per convolution"
+        a.y, a.split_counters = y.data_ptr(), None
     if stats:
         assert torch.isnan(part[:, :2]).all() and torch.isnan(part[:, -1:]).all()      # stays inside its chunk range
         got_s = part[:, 2:-1].double().sum(1)
