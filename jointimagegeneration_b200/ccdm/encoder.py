@@ -6,10 +6,16 @@ Input: cached BERT features [b, embed_dim, length] (the reference's 'b c l' layo
 and a GEGLU feed-forward, unet_openai/attention.py:127-146) over the token axis.  ``state_dict`` keys match the
 reference module (``transformer_blocks.N.attn1.to_q.weight`` ...).  Runs once per volume, before the denoising
 loop; the blocks execute on the same sm_100a kernels as the UNet's SpatialTransformer (layernorm, tcgen05 GEMMs,
-attention, GEGLU) through a planned, CUDA-graph-capturable launch list.  The frozen BERT model itself
-(``FrozenBERTEmbedder``, a HuggingFace checkpoint) stays outside: its output is this module's input.
+attention, GEGLU) through a planned, CUDA-graph-capturable launch list.
+
+``FrozenBERTEmbedder`` (:21-100) is provided with the reference's interface as well.  In the reference it IS a
+third-party model -- ``transformers.AutoModel.from_pretrained(ckpt)`` behind ``AutoTokenizer`` -- evaluated once per
+volume on the report text, outside the denoising loop; the drop-in keeps exactly that (a frozen HuggingFace checkpoint is
+data + library code, not part of this repo's hot path) and re-implements the host logic around it: the text splitter for
+reports longer than BERT's 512 tokens, the batch assembly and the ``(b x) n l -> b (n x) l`` regrouping.
 """
-from typing import Dict, Optional
+import re
+from typing import Dict, List, Optional
 
 import torch
 from torch import nn
@@ -55,3 +61,97 @@ class PreloadedBERTEncoder(nn.Module):
         plan.run()
         out = plan.outputs["tokens"].reshape(B, L, Cc).transpose(1, 2).to(inputs.dtype)    # 'b l c -> b c l'
         return inputs + out                                                                  # encoder.py:123
+
+
+class AbstractEncoder(nn.Module):
+    def encode(self, *args, **kwargs):
+        raise NotImplementedError
+
+
+class FrozenBERTEmbedder(AbstractEncoder):
+    """encoder.py:21-100.  text (str | list of str) -> BERT last_hidden_state regrouped to [b, max_length, hidden]."""
+    use_text_split = False
+    bert_max_length = 512
+
+    def __init__(self, ckpt_path="/mnt/data/oss_beijing/dailinrui/data/pretrained/bert_chinese/", device="cuda", freeze=True,
+                 max_length=512, tokenizer=None, transformer=None):
+        """tokenizer / transformer: already constructed objects (tests, or a caller that loads the checkpoint itself);
+        default = AutoTokenizer / AutoModel .from_pretrained(ckpt_path, local_files_only=True) as in the reference."""
+        super().__init__()
+        self.device = device
+        self.max_length = max_length
+        self.bert_max_length = 512
+        assert self.max_length % self.bert_max_length == 0 or self.max_length < self.bert_max_length
+        self.bert_encode_batch = self.max_length // self.bert_max_length
+        if tokenizer is None or transformer is None:
+            from transformers import AutoModel, AutoTokenizer
+            tokenizer = AutoTokenizer.from_pretrained(ckpt_path, local_files_only=True)
+            transformer = AutoModel.from_pretrained(ckpt_path, local_files_only=True)
+        self.tokenizer = tokenizer
+        self.transformer = transformer.to(self.device)
+        if freeze:
+            self.freeze()
+
+    def freeze(self):
+        self.transformer = self.transformer.eval()
+        for param in self.parameters():
+            param.requires_grad = False
+
+    @staticmethod
+    def _merge_shortest_pairs(parts: List[str], max_length: int) -> List[str]:
+        """Repeatedly joins the adjacent pair with the smallest combined length until no pair fits in max_length
+        (the reference's recursive grouping, :50-62, as a loop)."""
+        parts = list(parts)
+        while len(parts) > 1:
+            lens = [len(parts[i]) + len(parts[i + 1]) for i in range(len(parts) - 1)]
+            i = min(range(len(lens)), key=lens.__getitem__)           # first minimum, as numpy.argmin
+            if lens[i] > max_length:
+                break
+            parts[i:i + 2] = [parts[i] + parts[i + 1]]
+        return parts
+
+    @staticmethod
+    def token_split(string, max_length=512):
+        """:43-70: a report shorter than max_length stays whole; otherwise it is cut before every '{' / escaped backslash
+        pair, the pieces are regrouped greedily, and if a group is still too long the cut points become the full stops."""
+        if len(string) < max_length:
+            return [string]
+
+        def cut(pattern):
+            pos = [0] + [m.start() for m in re.finditer(pattern, string)] + [len(string)]
+            return [string[pos[i]:pos[i + 1]] for i in range(len(pos) - 1)]
+        groups = FrozenBERTEmbedder._merge_shortest_pairs(cut(r"\\\\|{"), max_length)
+        if max(len(g) for g in groups) > max_length:
+            groups = FrozenBERTEmbedder._merge_shortest_pairs(cut("\u3002"), max_length)
+        return groups
+
+    def _merge_text_list(self, *items):
+        out = []
+        for item in items:
+            parts = item if isinstance(item, list) else self.token_split(str(item))
+            parts = list(parts)
+            if len(parts) < self.bert_encode_batch:
+                parts.append("")
+            if len(parts) > self.bert_encode_batch:
+                parts = parts[:self.bert_encode_batch]
+            out.extend(parts)
+        return out
+
+    @torch.no_grad()
+    def forward(self, text):
+        if isinstance(text, str):
+            text = [text]
+        b = len(text)
+        if self.use_text_split:
+            text = self._merge_text_list(*text)
+        enc = self.tokenizer(text, truncation=True, max_length=self.bert_max_length, return_length=True,
+                             return_overflowing_tokens=False, padding="max_length", return_tensors="pt")
+        tokens = enc["input_ids"].to(self.device)
+        mask = enc["attention_mask"].to(self.device)
+        z = self.transformer(input_ids=tokens, attention_mask=mask, return_dict=True).last_hidden_state
+        x, n = self.bert_encode_batch, self.bert_max_length
+        # '(b x) n l -> b (n x) l': token-major, split-minor interleave of the x sub-texts of a report (:96)
+        return z.reshape(b, x, n, z.shape[-1]).permute(0, 2, 1, 3).reshape(b, n * x, z.shape[-1])
+
+    def encode(self, text):
+        return self(text)
