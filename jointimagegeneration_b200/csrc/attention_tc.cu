@@ -38,6 +38,7 @@ struct alignas(64) AttnTcParams {
     long long o_bs;
     int o_rs, o_hs;
     int H, Tq, Tk, n_kt;
+    int two;                // 1: two 128-row query tiles per CTA (ping-pong); 0: one (more CTAs when the grid would not fill the GPU)
     float scale_log2;
 };
 
@@ -127,7 +128,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (2 * AT_BM);
+    const bool two = p.two != 0;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (two ? 2 * AT_BM : AT_BM);
     const int n_kt = p.n_kt;
     if (warp == 0 && lane == 0) { prefetch_tmap(&p.qmap); prefetch_tmap(&p.kmap); prefetch_tmap(&p.vtmap); }
     if (warp == 1) {
@@ -151,9 +153,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     if (warp == 0) {
         // ================================================================ TMA producer
         if (elect_one()) {
-            mbar_expect_tx(q_full, 2 * AT_TILE);
+            mbar_expect_tx(q_full, two ? 2 * AT_TILE : AT_TILE);
             tma_load_4d(smem_q, &p.qmap, q_full, 0, h, q0, b);
-            tma_load_4d(smem_q + AT_TILE, &p.qmap, q_full, 0, h, q0 + AT_BM, b);
+            if (two) tma_load_4d(smem_q + AT_TILE, &p.qmap, q_full, 0, h, q0 + AT_BM, b);
         }
         __syncwarp();
         for (int j = 0; j < n_kt; ++j) {
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         mbar_wait(q_full, 0);
         mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        if (elect_one()) { issue_s(0, 0); issue_s(1, 0); }
+        if (elect_one()) { issue_s(0, 0); if (two) issue_s(1, 0); }
         __syncwarp();
         for (int j = 0; j < n_kt; ++j) {
             const int st = j % AT_ST, stn = (j + 1) % AT_ST;
@@ -206,21 +208,28 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             mbar_wait(&s_free[0], ph);
             tc_fence_after();
             if (more) { if (elect_one()) issue_s(0, stn); __syncwarp(); }
-            mbar_wait(&s_free[1], ph);
-            tc_fence_after();
-            if (more) { if (elect_one()) issue_s(1, stn); __syncwarp(); }
+            if (two) {
+                mbar_wait(&s_free[1], ph);
+                tc_fence_after();
+                if (more) { if (elect_one()) issue_s(1, stn); __syncwarp(); }
+            }
             // ---- O_g += P_g(j) V_j once P_g(j) is in shared memory
             mbar_wait(&p_full[0], ph);
             tc_fence_after();
-            if (elect_one()) issue_pv(0, st, j);
-            __syncwarp();
-            mbar_wait(&p_full[1], ph);
-            tc_fence_after();
             if (elect_one()) {
-                issue_pv(1, st, j);
-                umma_commit(&kv_empty[st]);          // every MMA that reads this K / V^T stage has been issued before this commit
+                issue_pv(0, st, j);
+                if (!two) umma_commit(&kv_empty[st]);
             }
             __syncwarp();
+            if (two) {
+                mbar_wait(&p_full[1], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_pv(1, st, j);
+                    umma_commit(&kv_empty[st]);      // every MMA that reads this K / V^T stage has been issued before this commit
+                }
+                __syncwarp();
+            }
         }
     } else {
         // ================================================================ softmax + output: warps 2..5 tile A, 6..9 tile B
@@ -233,7 +242,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         const int swz = row & 7;
         const float sl2 = p.scale_log2;
         float m_used = -INFINITY, l = 0.f;
-        for (int j = 0; j < n_kt; ++j) {
+        const int n_mine = (g == 1 && !two) ? 0 : n_kt;          // one-tile CTAs: the warps of tile B have nothing to do
+        for (int j = 0; j < n_mine; ++j) {
             const uint32_t ph = (uint32_t)j & 1u;
             mbar_wait(&s_full[g], ph);
             tc_fence_after();
@@ -318,6 +328,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             if (lane == 0) mbar_arrive(&p_full[g]);
         }
         // ---- output: O / l
+        if (n_mine > 0) {
         mbar_wait(&pv_done[g], ((uint32_t)(n_kt - 1)) & 1u);
         tc_fence_after();
         const int t = q0 + g * AT_BM + row;
@@ -335,6 +346,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 *reinterpret_cast<uint4*>(orow + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
                 *reinterpret_cast<uint4*>(orow + 16 * c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
             }
+        }
         }
     }
     tc_fence_before();
@@ -408,7 +420,12 @@ static int launch_attention_tc(const gg_attn_args* a, cudaStream_t stream) {
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    const dim3 grid((unsigned)((a->Tq + 2 * AT_BM - 1) / (2 * AT_BM)), (unsigned)a->H, (unsigned)a->B);
+    // two query tiles per CTA share every K / V^T tile and hide each other's tensor-core latency; when that grid would leave
+    // SMs idle (a depth slab's share of the queries), one tile per CTA doubles the CTA count instead
+    const int64_t ctas2 = (int64_t)((a->Tq + 2 * AT_BM - 1) / (2 * AT_BM)) * a->H * a->B;
+    p.two = 2 * ctas2 > num_sms() ? 1 : 0;          // one tile per CTA only while the doubled grid still is a single wave
+    const int rows = p.two ? 2 * AT_BM : AT_BM;
+    const dim3 grid((unsigned)((a->Tq + rows - 1) / rows), (unsigned)a->H, (unsigned)a->B);
     fn<<<grid, AT_THREADS, smem, stream>>>(p);
     return launch_result();
 }

@@ -462,7 +462,7 @@ def test_conv_roll_sampler_epilogue_equals_logits_plus_per_voxel_kernel(ops, N, 
 
 # -------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,H,T,d", [(2, 4, 64, 32), (1, 8, 2048, 32), (2, 10, 256, 32), (3, 2, 16, 32), (1, 5, 100, 32),
-                                     (1, 2, 130, 64)])
+                                     (1, 2, 130, 64), (4, 10, 1024, 32)])
 def test_attention_legacy(ops, B, H, T, d):
     no_tf32()
     rs = np.random.RandomState(2)
@@ -492,11 +492,12 @@ def test_attention_cross(ops):
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,d", [(2, 5, 300, 77, 64), (1, 8, 1024, 512, 64), (2, 3, 200, 333, 32), (1, 8, 4096, 4096, 32),
-                                         (1, 2, 64, 2000, 32)])
+                                         (1, 2, 64, 2000, 32), (2, 16, 2500, 1100, 64), (8, 8, 2048, 2048, 32)])
 def test_attention_tensor_core_kernel(ops, B, H, Tq, Tk, d):
     """attention_tc.cu (tcgen05 Q K^T and P V, TMEM accumulators, TMA operands, lazy online-softmax rescaling) through
     gg_attention_fwd with a workspace: cross-attention shapes (separate q / kv tensors, ragged Tq / Tk, key-tail masking,
-    d = 32 and 64) and a long self-attention, against fp32 softmax attention.  Large score ranges exercise the rescaling."""
+    d = 32 and 64) and a long self-attention, against fp32 softmax attention.  Large score ranges exercise the rescaling; the
+    last two shapes fill the GPU and run two query tiles per CTA, the others one."""
     from jointimagegeneration_b200 import _C
     import ctypes as C_
     no_tf32()
