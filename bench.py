@@ -243,26 +243,36 @@ def run_ours(args, workload=None, K=None, W=None, sub=False):
     value = (1 if slab else world) * K / (ms / 1e3)
     launches_per_step = model.launches_per_step(plan)                           # kernels of libguidegen_sm100 per resident step
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
-    x_host = x_T.cpu().pin_memory()
+    # ---- end to end through the public API, as the reference's own caller drives it (Trainer.test_step, ccdm/ddpm/trainer.py:
+    # 412-421; evaluator.py:135-148): the batch's condition volume comes from HOST memory, x_T is drawn ON THE DEVICE with
+    # OneHotCategoricalBCHW(logits=zeros).sample() (trainer.py:418), DenoisingModel.forward runs the chain, and the result
+    # the caller keeps -- the arg-max label volume it writes to NIfTI -- goes back to the host.  Copies are inside the timed region.
+    from jointimagegeneration_b200.ccdm import OneHotCategoricalBCHW
     c_host = cond.cpu().pin_memory()
-    out_host = torch.empty((B, Cc) + sp, dtype=torch.int64).pin_memory()
+    lab_host = torch.empty((B,) + sp, dtype=torch.uint8).pin_memory()
     Ke = max(2, min(K, 10))
+
+    def test_step(k):
+        image = c_host.to(dev, non_blocking=True)
+        x = OneHotCategoricalBCHW(logits=torch.zeros((B, Cc) + sp, device=dev)).sample()
+        pred = model(x, image, t=torch.tensor(10000 + k), context=context)["diffusion_out"]     # the reference's own K-step knob (:190-197)
+        lab_host.copy_(pred.argmax(dim=1).to(torch.uint8), non_blocking=False)
+
     # one untimed short call first: the public path's own one-time work (its plan / graph for this call signature,
     # pinned staging buffers) is not part of a steady-state step
-    model(x_host, c_host, t=torch.tensor(10000 + 2), context=context)
+    test_step(2)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    res = model(x_host, c_host, t=torch.tensor(10000 + Ke), context=context)["diffusion_out"]   # reference's own K-step knob (:190-197)
-    out_host.copy_(res, non_blocking=False)
+    test_step(Ke)
     torch.cuda.synchronize()
     e2e_s = _max_over_ranks(time.perf_counter() - t0, dev, world)
     e2e = {"value": (1 if slab else world) * Ke / e2e_s, "unit": "steps/s", "steps": Ke,
-           "h2d_bytes_per_step": (x_host.numel() * 4 + c_host.numel() * 4) // Ke,
-           "d2h_bytes_per_step": out_host.numel() * 8 // Ke,
-           "call": "DenoisingModel.forward(x_host, condition_host, t=10000+K) -> int64 one-hot on host (loop='resident', CUDA graph)"}
+           "h2d_bytes_per_step": c_host.numel() * 4 // Ke, "d2h_bytes_per_step": lab_host.numel() // Ke,
+           "call": "Trainer.test_step flow (trainer.py:418-421): condition from pinned host memory -> x_T = OneHotCategoricalBCHW(logits=0).sample() on "
+                   "the device -> DenoisingModel.forward(x_T, condition, t=10000+K) -> arg-max label volume (uint8) to the host "
+                   "(loop='resident', CUDA graph)"}
 
     line = {"metric": "denoising steps/sec", "value": value, "unit": "steps/s (1 step = UNet forward + categorical posterior/draw for a batch of %d volumes)" % B,
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if slab else "weak",

@@ -339,7 +339,7 @@ typedef struct {
      * and applies bias / emb / residual.  split_k <= 1: off. */
     int32_t split_k;
     float* workspace;
-    /* Fused GroupNorm + SiLU on the INPUT (algo 4 only): when src_ss[i] is not NULL, source i is the raw,
+    /* Fused GroupNorm + SiLU on the INPUT (algo 1..4): when src_ss[i] is not NULL, source i is the raw,
      * un-normalised activation and the kernel applies  silu?(x * scale + shift)  to each halo plane in shared
      * memory before the MMAs read it (the separate gg_gn_apply pass and its tensor disappear).  src_ss[i] points
      * at the (scale, shift) pair of the source's first channel for sample 0 -- gg_gn_finalize's output, offset by

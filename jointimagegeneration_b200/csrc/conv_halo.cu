@@ -26,6 +26,8 @@
 namespace gg {
 
 constexpr int H_ACC_COLS = 256;
+constexpr int H_XW = 8;                            // transform warps (four cannot keep up with the nine taps of a plane: measured)
+constexpr int H_THREADS_XF = H_THREADS + 32 * H_XW;  // + warps 7..: GroupNorm / SiLU transform of the landed halo planes
 constexpr int H_MAX_SB = 8;
 constexpr int H_MAX_SA = 4;
 
@@ -38,6 +40,9 @@ struct HaloSeg {
     int plane;             // (bh + kh - 1) * pitch rows between depth planes
     uint32_t a_bytes;      // bytes of ONE depth plane of the halo window (= one A stage load)
     int g;                 // taps (along kw) whose weights share one B stage: kw or 1
+    int C;                 // channels
+    int inv_pitch;         // ceil(2^16 / pitch)
+    const float* ss;       // XFORM: (scale, shift) of channel 0, sample 0 of this source; nullptr = the source is used as it is
 };
 
 struct alignas(64) HaloParams {
@@ -60,10 +65,12 @@ struct alignas(64) HaloParams {
     int y_is_f32;
     float* gn_partial;             // fused GroupNorm statistics (BN == Cout8 == 64): [N, gn_nchunks_total, 64, 2]
     int gn_chunk_base, gn_nchunks_total;
+    int ss_stride, xf_silu, z_lo, z_hi;      // XFORM (fused GroupNorm + SiLU on the input planes, as conv_roll.cu)
+    int Hi, Wi;                    // input extents (= output extents: stride 1)
 };
 
-template <int G, bool STATS, bool PAIR>
-__global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+template <int G, bool STATS, bool PAIR, bool XFORM>
+__global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -75,7 +82,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     uint64_t* b_empty = b_full + H_MAX_SB;
     uint64_t* tfull = b_empty + H_MAX_SB;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* a_ready = tempty + 2;                // XFORM (PAIR: the leader's): plane landed AND transformed in every CTA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + H_MAX_SA);
     float* bvec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512);      // [BN] bias + emb[n]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], PAIR ? 2 * H_XW : H_XW); }
             for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 8 : 4); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -127,7 +135,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
                     for (int a = 0; a < sg.kd; ++a) {
                         mbar_wait(&a_empty[sa], pha ^ 1u);
                         if (elect_one()) {
-                            if constexpr (PAIR) {
+                            if constexpr (XFORM) {       // each CTA's transform warps watch their own plane land
+                                mbar_expect_tx(&a_full[sa], sg.a_bytes);
+                                tma_load_5d(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], &a_full[sa], j * BK, w0 + sg.ow, h0 + sg.oh,
+                                            d0 + sg.od + sg.dshift + a, n0);
+                            } else if constexpr (PAIR) {
                                 if (rank == 0) mbar_expect_tx(&a_full[sa], 2u * sg.a_bytes);
                                 tma_load_5d_pair(smem + (size_t)sa * p.a_stage_bytes, &p.amap[s], leader_addr(&a_full[sa]), j * BK,
                                                  w0 + sg.ow, h0 + sg.oh, d0 + sg.od + sg.dshift + a, n0);
@@ -195,7 +207,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
                 for (int j = 0; j < sg.nchunks; ++j) {
                     const bool last_chunk = (s == p.nseg - 1) && (j == sg.nchunks - 1);
                     for (int a = 0; a < sg.kd; ++a) {
-                        mbar_wait(&a_full[sa], pha);
+                        mbar_wait(XFORM ? &a_ready[sa] : &a_full[sa], pha);
+                        if constexpr (XFORM) tc_fence_after();
                         const uint32_t a_stage16 = (a_base + (uint32_t)sa * p.a_stage_bytes) >> 4;
                         for (int b = 0; b < sg.kh; ++b) {
                             const uint32_t row16 = a_stage16 + (uint32_t)(b * sg.pitch) * 8u;      // 128 B rows -> 8 x 16 B
@@ -250,6 +263,82 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
             }
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;
+        }
+    } else if (XFORM && warp >= 7) {
+        // ================================================================ transform (warps 7..10): GroupNorm (+ SiLU) in place on
+        // every landed halo plane of a normalised source (same arithmetic and rounding points as gg_gn_apply: xf_pair).  Rows
+        // are 128 B = 64 channels, SWIZZLE_128B: the 16-byte chunk at physical slot jp of stage row r holds channels
+        // 8 (jp ^ (r & 7)) .. + 7.  Rows outside the tensor stay zero (the reference pads the NORMALISED tensor); the
+        // (scale, shift) pairs of a thread's eight channels come straight from gg_gn_finalize's table (L1 / L2 hits).
+        const int xt = (int)threadIdx.x - H_THREADS;        // 0..32 H_XW - 1
+        constexpr int XR = 4 * H_XW, XB = 3;                // rows per pass of all transform threads, rows per thread and batch
+        const int jl = xt & 7;
+        int sa = 0;
+        uint32_t pha = 0;
+        const bool silu = p.xf_silu != 0;
+        const float kk = silu ? 0.5f : 1.f;
+        const uint32_t ready_r = PAIR ? leader_addr(&a_ready[0]) : 0u;
+        for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
+            int mt = tile / p.n_tiles_n;
+            const int iw = (PAIR ? 2 : 1) * (mt % p.tw) + rank; mt /= p.tw;
+            const int ih = mt % p.th; mt /= p.th;
+            const int d0 = mt % p.Do, n0 = mt / p.Do;
+            const int h0 = ih * H_BH, w0 = iw * H_BW;
+            for (int s = 0; s < p.nseg; ++s) {
+                const HaloSeg sg = p.seg[s];
+                for (int j = 0; j < sg.nchunks; ++j) {
+                    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+                    if (sg.ss != nullptr) {      // (s0, b0, s1, b1) per channel pair -> (s0, s1, b0, b1), halved when SiLU follows
+                        const int c0 = j * BK + 8 * jl;
+                        const float4* src = reinterpret_cast<const float4*>(sg.ss + (long long)n0 * p.ss_stride + 2 * c0);
+                        float4 v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = (c0 + 2 * e < sg.C) ? __ldg(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        q0 = make_float4(kk * v[0].x, kk * v[0].z, kk * v[0].y, kk * v[0].w);
+                        q1 = make_float4(kk * v[1].x, kk * v[1].z, kk * v[1].y, kk * v[1].w);
+                        q2 = make_float4(kk * v[2].x, kk * v[2].z, kk * v[2].y, kk * v[2].w);
+                        q3 = make_float4(kk * v[3].x, kk * v[3].z, kk * v[3].y, kk * v[3].w);
+                    }
+                    for (int a = 0; a < sg.kd; ++a) {
+                        mbar_wait(&a_full[sa], pha);
+                        const int z = d0 + sg.od + a;              // local depth plane (without the slab shift)
+                        if (sg.ss != nullptr && z >= p.z_lo && z < p.z_hi) {
+                            uint8_t* stg = smem + (size_t)sa * p.a_stage_bytes;
+                            const int nrow = sg.plane;
+#pragma unroll 1
+                            for (int r0 = xt >> 3; r0 < nrow; r0 += XR * XB) {
+                                uint4 v[XB];
+                                uint4* ptr[XB];
+                                bool ok[XB];
+#pragma unroll
+                                for (int u = 0; u < XB; ++u) {
+                                    const int r = r0 + XR * u, rc = min(r, nrow - 1);
+                                    const int hh = (int)(((uint32_t)rc * (uint32_t)sg.inv_pitch) >> 16), ww = rc - hh * sg.pitch;
+                                    const int gh = h0 + sg.oh + hh, gw = w0 + sg.ow + ww;
+                                    ok[u] = r < nrow && gh >= 0 && gh < p.Hi && gw >= 0 && gw < p.Wi;
+                                    ptr[u] = reinterpret_cast<uint4*>(stg + rc * 128 + ((jl ^ (rc & 7)) << 4));
+                                    v[u] = *ptr[u];
+                                }
+#pragma unroll
+                                for (int u = 0; u < XB; ++u) {
+                                    v[u].x = xf_pair(v[u].x, q0, silu); v[u].y = xf_pair(v[u].y, q1, silu);
+                                    v[u].z = xf_pair(v[u].z, q2, silu); v[u].w = xf_pair(v[u].w, q3, silu);
+                                }
+#pragma unroll
+                                for (int u = 0; u < XB; ++u)
+                                    if (ok[u]) *ptr[u] = v[u];
+                            }
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> tensor-core reads
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            if constexpr (PAIR) mbar_arrive_remote(ready_r + (uint32_t)sa * 8u);
+                            else mbar_arrive(&a_ready[sa]);
+                        }
+                        if (++sa == SA) { sa = 0; pha ^= 1u; }
+                    }
+                }
+            }
         }
     } else {
         // ================================================================ epilogue (warps 2..5)
@@ -319,9 +408,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     }
 }
 
-template <int G, bool STATS, bool PAIR>
+template <int G, bool STATS, bool PAIR, bool XFORM>
 static int launch_halo(const HaloParams& p, int grid, size_t smem, cudaStream_t stream) {
-    auto* fn = conv_halo_kernel<G, STATS, PAIR>;
+    auto* fn = conv_halo_kernel<G, STATS, PAIR, XFORM>;
     static bool attr_set = false;      // one flag per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
@@ -330,7 +419,7 @@ static int launch_halo(const HaloParams& p, int grid, size_t smem, cudaStream_t 
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(H_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(XFORM ? H_THREADS_XF : H_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -340,10 +429,15 @@ static int launch_halo(const HaloParams& p, int grid, size_t smem, cudaStream_t 
     return launch_result();
 }
 template <bool STATS, bool PAIR>
-static int launch_halo_g(int G, const HaloParams& p, int grid, size_t smem, cudaStream_t stream) {
-    if (G == 3) return launch_halo<3, STATS, PAIR>(p, grid, smem, stream);
-    if (G == 2) return launch_halo<2, STATS, PAIR>(p, grid, smem, stream);
-    return launch_halo<1, STATS, PAIR>(p, grid, smem, stream);
+static int launch_halo_g(int G, bool xform, const HaloParams& p, int grid, size_t smem, cudaStream_t stream) {
+    if (xform) {
+        if (G == 3) return launch_halo<3, STATS, PAIR, true>(p, grid, smem, stream);
+        if (G == 2) return launch_halo<2, STATS, PAIR, true>(p, grid, smem, stream);
+        return launch_halo<1, STATS, PAIR, true>(p, grid, smem, stream);
+    }
+    if (G == 3) return launch_halo<3, STATS, PAIR, false>(p, grid, smem, stream);
+    if (G == 2) return launch_halo<2, STATS, PAIR, false>(p, grid, smem, stream);
+    return launch_halo<1, STATS, PAIR, false>(p, grid, smem, stream);
 }
 
 // ---------------------------------------------------------------------------------------- host
@@ -382,6 +476,7 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     const int64_t W = a->W, H = a->H, D = a->D, N = a->N;
     uint32_t max_a = 0;
     int num_kb = 0;
+    bool xform = false;
     for (int s = 0; s < a->nsrc; ++s) {
         const gg_conv_src& src = a->src[s];
         GG_REQUIRE(src.x != nullptr && src.C > 0 && src.C % 8 == 0, GG_ERR_BAD_ARG);
@@ -392,6 +487,13 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
         if (src.centre_only) { sg.kd = sg.kh = sg.kw = 1; sg.od = sg.oh = sg.ow = 0; }
         else { sg.kd = a->kd; sg.kh = a->kh; sg.kw = a->kw; sg.od = a->od; sg.oh = a->oh; sg.ow = a->ow; }
         sg.pitch = H_BW + sg.kw - 1;
+        sg.inv_pitch = (65536 + sg.pitch - 1) / sg.pitch;
+        sg.C = src.C;
+        sg.ss = a->src_ss[s];
+        if (sg.ss != nullptr) {
+            GG_REQUIRE(aligned(sg.ss, 16) && a->ss_stride % 4 == 0 && !src.centre_only, GG_ERR_ALIGNMENT);
+            xform = true;
+        }
         sg.plane = (H_BH + sg.kh - 1) * sg.pitch;
         sg.a_bytes = (uint32_t)sg.plane * 128u;
         max_a = std::max(max_a, sg.a_bytes);
@@ -403,6 +505,7 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
         num_kb += sg.nchunks * sg.kd * sg.kh * sg.kw;
     }
     p.nseg = a->nsrc;
+    p.ss_stride = a->ss_stride; p.xf_silu = a->xf_silu; p.z_lo = a->xf_z_lo; p.z_hi = a->xf_z_hi; p.Hi = a->H; p.Wi = a->W;
     const int b_rows = pair ? BN / 2 : BN;          // weight rows per CTA and tap
     if (!encode_w_map(&p.wmap, a->w_packed, (int64_t)num_kb * BK, a->Cout, b_rows)) return GG_ERR_DRIVER;
     p.a_stage_bytes = (max_a + 1023u) & ~1023u;
@@ -447,9 +550,9 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
                                               (size_t)(grid * 4) * row_bytes, (size_t)a->N, stream);
             if (e != cudaSuccess) return (int)e;
         }
-        return pair ? launch_halo_g<true, true>(G, p, grid, smem, stream) : launch_halo_g<true, false>(G, p, grid, smem, stream);
+        return pair ? launch_halo_g<true, true>(G, xform, p, grid, smem, stream) : launch_halo_g<true, false>(G, xform, p, grid, smem, stream);
     }
-    return pair ? launch_halo_g<false, true>(G, p, grid, smem, stream) : launch_halo_g<false, false>(G, p, grid, smem, stream);
+    return pair ? launch_halo_g<false, true>(G, xform, p, grid, smem, stream) : launch_halo_g<false, false>(G, xform, p, grid, smem, stream);
 }
 
 }  // namespace gg

@@ -69,6 +69,29 @@ __device__ __forceinline__ void epilogue_row_stats(uint32_t t_addr, int BN, int 
     }
 }
 
+// Transform of one bf16 pair (packed f32x2 arithmetic, two FMAs per instruction).  q = (s0, s1, b0, b1) of the two
+// channels.  SiLU: q is pre-halved so that h = x s/2 + b/2 = v/2 exactly, and silu(v) = v sigmoid(v) = h + h tanh(h)
+// (one MUFU per element; the same formulation and rounding points as gg_gn_apply).
+__device__ __forceinline__ uint32_t xf_pair(uint32_t w, float4 q, bool silu) {
+    uint64_t x, sc, sh, h;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(w << 16), "r"(w & 0xffff0000u));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sc) : "f"(q.x), "f"(q.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sh) : "f"(q.z), "f"(q.w));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(h) : "l"(x), "l"(sc), "l"(sh));
+    float h0, h1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(h));
+    if (silu) {
+        float t0, t1;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+        uint64_t t, y;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+        asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(y) : "l"(h), "l"(t));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(y));
+    }
+    return pack_bf16(h0, h1);
+}
+
 __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);

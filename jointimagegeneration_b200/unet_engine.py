@@ -211,6 +211,11 @@ class UNetEngine:
         self.separate_skip = os.environ.get("GG_SEPARATE_SKIP", "0") != "0"     # see _resblock (measured: no gain, off)
         # GroupNorm + SiLU applied inside the depth-rolling conv (no separate pass); GG_FUSED_GN=0 is a tuning knob
         self.fused_gn_apply = os.environ.get("GG_FUSED_GN", "1") != "0"
+        # ... and inside the halo-brick conv (every other stride-1 3^d conv on grids >= 16 x 8: the LDM networks, the deeper
+        # CCDM levels): the same transform (eight warps) on its landed input windows.  Tested bit-exact, but measured NO gain:
+        # that kernel loads a window once per depth tap and per N tile, so it re-normalises what gg_gn_apply normalises once
+        # (config 2: conv +3.2 ms vs gn_apply -1.6 ms; config 4: -1 %; config 3: -1 %), so off by default
+        self.fused_gn_halo = os.environ.get("GG_FUSED_GN_HALO", "0") != "0"
         self.use_split_k = True
         # in-kernel split-K reduction (the last split of a tile sums the partials itself, gg_conv_args.split_counters) instead of
         # the second launch: bit-identical, but only that CTA's 128 epilogue threads do the summing -- measured SLOWER
@@ -387,6 +392,9 @@ class UNetEngine:
         C1, C2 = x1.C, (x2.C if x2 is not None else 0)
         fuse = (self.fused_gn_apply and self._roll_ok(dims, 1, None, None, cout, x1.sp, None)
                 and (C1 + C2) * 8 <= 4096 and C1 % 64 == 0 and C2 % 64 == 0)
+        if not fuse and self.fused_gn_halo and kw.get("ksize", 3) == 3 and kw.get("stride", 1) == 1 and kw.get("taps") is None:
+            # the halo-brick kernel normalises its landed windows itself (any channel count: the table is read per chunk)
+            fuse = self._halo_ok((3 if dims >= 3 else 1, 3 if dims >= 2 else 1, 3), 1, x1.sp)
         taps3 = dims >= 3 and kw.get("ksize", 3) == 3 and kw.get("stride", 1) == 1 and kw.get("taps") is None
         if not fuse:
             a = self._gn(plan, ar, x1, x2, norm, silu, with_halo=taps3)
@@ -461,7 +469,7 @@ class UNetEngine:
         algo = 1 if halo and (halo_stats or not (stats and self.fused_gn_stats)) else 0
         if algo == 1 and self._roll_ok(dims, stride, taps, offsets, cout, out_spatial, y_strides):
             algo = 4        # narrow outputs: depth-rolling kernel (three depth taps stacked along N)
-        assert src_ss is None or (algo == 4 and callable(w_packed)), "fused input GroupNorm needs the depth-rolling kernel"
+        assert src_ss is None or (algo in (1, 4) and callable(w_packed)), "fused input GroupNorm needs the halo-brick or depth-rolling kernel"
         if callable(w_packed):          # packed-weight K order depends on the kernel
             w_packed = w_packed(algo >= 1)
         else:
