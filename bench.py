@@ -532,7 +532,23 @@ def run_ours_ldm(args, workload, K=None, W=None):
             "slices_per_sec": value * B / S}
     if rank == 0:
         peaks = load_peaks()
-        kinds, _ = instrument_plan(plan, detail_path=os.path.join(ROOT, "gpurun_out", "bench_detail_%s.txt" % workload) if args.detail else None)
+        line["detail"]["lanes"] = len(plan.lanes)
+        iso = plan
+        if len(plan.lanes) > 1:
+            # the timed step runs the batch as concurrent sample lanes (Plan.lanes); per-launch times are taken from the
+            # SINGLE-lane plan of the same batch, every kernel alone on the GPU
+            line["detail"]["lanes_note"] = ("the step runs %d sample lanes concurrently (parallel branches of one CUDA graph); roofline / kernel_ms "
+                                            "time every launch of the single-lane plan alone on the GPU" % len(plan.lanes))
+            prev = os.environ.get("GG_LANES")
+            os.environ["GG_LANES"] = "1"
+            iso = unet.plan_for(B, hw)
+            iso.run()
+            if prev is None:
+                del os.environ["GG_LANES"]
+            else:
+                os.environ["GG_LANES"] = prev
+        kinds, _ = instrument_plan(iso, detail_path=os.path.join(ROOT, "gpurun_out", "bench_detail_%s.txt" % workload) if args.detail else None)
+        del iso
         conv_ms, n_conv = kinds["gg_conv_fwd"]
         ach = wl["flop_per_sample"] * B / (conv_ms / 1e3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "conv_roll_kernel + conv_halo_kernel + conv_tcgen05_kernel (all %d conv launches of one step)" % n_conv, "achieved": ach,

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libguidegen_sm100.so")
+LIB_PATH = os.environ.get("GG_LIB") or os.path.join(_HERE, "lib", "libguidegen_sm100.so")     # GG_LIB: a tuning build (build.py)
 
 _lib = None
 

@@ -14,13 +14,15 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
-OBJ_DIR = os.path.join(OUT_DIR, "obj")
-LIB = os.path.join(OUT_DIR, "libguidegen_sm100.so")
+# tuning builds: GG_BUILD_TAG=<tag> GG_BUILD_DEFS="-DFOO=1 ..." -> lib/libguidegen_sm100_<tag>.so (loaded with GG_LIB=<path>)
+TAG = os.environ.get("GG_BUILD_TAG", "")
+OBJ_DIR = os.path.join(OUT_DIR, "obj" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(OUT_DIR, "libguidegen_sm100%s.so" % ("_" + TAG if TAG else ""))
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-I", INCLUDE, "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "-I", INCLUDE, "--expt-relaxed-constexpr"] + os.environ.get("GG_BUILD_DEFS", "").split()
 
 
 def _sources():

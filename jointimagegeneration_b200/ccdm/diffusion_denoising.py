@@ -301,19 +301,24 @@ class DenoisingModel(nn.Module):
         st["lab_a"], st["lab_b"] = st["lab_b"], st["lab_a"]
 
     def _launch_fused_head(self, st: dict, coef: Tensor, offset: int):
-        """The head conv with softmax + posterior + clamp + draw + next-input write in its epilogue (gg_conv_args.cat)."""
+        """The head conv with softmax + posterior + clamp + draw + next-input write in its epilogue (gg_conv_args.cat); one
+        launch per lane of the plan, each over its own sample range."""
         import ctypes as C
         from .. import _C
-        fa, cat = st["plan"].fused_head
-        cat.labels_in, cat.labels_out = st["lab_a"].data_ptr(), st["lab_b"].data_ptr()
-        cat.next_x = st["xin"].data_ptr()
-        cat.cond = st["cond_cl"].data_ptr() if st["cond_cl"] is not None else None
-        cat.coef = coef.data_ptr()
-        cat.C, cat.n_cond, cat.Cin_pad, cat.mode = st["C"], st["n_cond"], st["xin"].shape[-1], ops.CAT_SAMPLE
-        cat.clamp_min, cat.seed, cat.offset, cat.vox_base = 1e-12, int(st["seed"]), int(offset), int(st["vox_base"])
-        ref = C.byref(fa)
-        _C.check(_C.lib().gg_conv_fwd(ref, _C.stream()), "gg_conv_fwd (sampler epilogue)")
-        return (ref,)
+        plan = st["plan"]
+        V, xin = st["V"], st["xin"]
+        refs = []
+        for fa, cat, n0 in plan.fused_heads:
+            cat.labels_in, cat.labels_out = st["lab_a"].data_ptr() + n0 * V, st["lab_b"].data_ptr() + n0 * V
+            cat.next_x = xin.data_ptr() + n0 * V * xin.shape[-1] * xin.element_size()
+            cat.cond = (st["cond_cl"].data_ptr() + n0 * V * st["n_cond"] * st["cond_cl"].element_size()) if st["cond_cl"] is not None else None
+            cat.coef = coef.data_ptr() + n0 * 2 * coef.element_size()
+            cat.C, cat.n_cond, cat.Cin_pad, cat.mode = st["C"], st["n_cond"], xin.shape[-1], ops.CAT_SAMPLE
+            cat.clamp_min, cat.seed, cat.offset, cat.vox_base = 1e-12, int(st["seed"]), int(offset), int(st["vox_base"]) + n0 * V
+            ref = C.byref(fa)
+            _C.check(_C.lib().gg_conv_fwd(ref, _C.stream()), "gg_conv_fwd (sampler epilogue)")
+            refs.append(ref)
+        return tuple(refs)
 
     def launches_per_step(self, plan) -> int:
         """libguidegen_sm100 launches of one resident step."""
@@ -323,7 +328,7 @@ class DenoisingModel(nn.Module):
         """For per-launch timing (bench.py): (plan steps to run, [(name, launch)]) that together make one resident step."""
         plan = st["plan"]
         if st.get("fused_head"):
-            return plan.steps[:-1], [("gg_conv_fwd", lambda: self._launch_fused_head(st, coef, offset))]
+            return plan.body_steps, [("gg_conv_fwd", lambda: self._launch_fused_head(st, coef, offset))]
 
         def cat_step():
             ops.cat_step_cl(plan.outputs["head"], st["lab_a"], coef, st["lab_b"], st["B"], st["V"], st["C"], mode=ops.CAT_SAMPLE,

@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const gg_attn_ar
     __nv_bfloat16* sKb = sQ + 2 * ATT_BM * LD;
     __nv_bfloat16* sVb = sKb + 2 * ATT_BN * LD;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     const int q0 = blockIdx.x * (2 * ATT_BM), h = blockIdx.y, b = blockIdx.z;
     const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + (int64_t)b * a.q_bs + (int64_t)h * a.q_hs;
     const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)b * a.k_bs + (int64_t)h * a.k_hs;
@@ -213,7 +215,8 @@ extern "C" int gg_attention_fwd(const gg_attn_args* a, gg_stream_t stream) {
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    if (a->d == 32) attention_kernel<32><<<grid, ATT_THREADS, smem_for(32), as_stream(stream)>>>(*a);
-    else attention_kernel<64><<<grid, ATT_THREADS, smem_for(64), as_stream(stream)>>>(*a);
+    const cudaError_t le = a->d == 32 ? launch_k(attention_kernel<32>, grid, dim3(ATT_THREADS), smem_for(32), as_stream(stream), *a)
+                                      : launch_k(attention_kernel<64>, grid, dim3(ATT_THREADS), smem_for(64), as_stream(stream), *a);
+    if (le != cudaSuccess) return (int)le;
     return launch_result();
 }

@@ -86,6 +86,8 @@ template <int D>
 __global__ void __launch_bounds__(256) attn_vt_kernel(const __nv_bfloat16* __restrict__ v, long long v_bs, int v_rs, int v_hs,
                                                       __nv_bfloat16* __restrict__ vt, int H, int Tk, int Tkp) {
     __shared__ __nv_bfloat16 tile[64][D + 2];
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 64;
     const __nv_bfloat16* src = v + (long long)b * v_bs + (long long)h * v_hs;
     for (int i = threadIdx.x; i < 64 * (D / 2); i += 256) {
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     const bool two = p.two != 0;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (two ? 2 * AT_BM : AT_BM);
     const int n_kt = p.n_kt;
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) { prefetch_tmap(&p.qmap); prefetch_tmap(&p.kmap); prefetch_tmap(&p.vtmap); }
     if (warp == 1) {
         if (lane == 0) {
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                     // prologue above: shared memory / TMEM / kernel parameters only (common.cuh)
     // TMEM columns: S_A [0, 128), S_B [128, 256), O_A [256, 256 + D), O_B [320, 320 + D)
     constexpr uint32_t COL_S = 0, COL_O = 256, O_STRIDE = 64;
 
@@ -407,8 +411,10 @@ static int launch_attention_tc(const gg_attn_args* a, cudaStream_t stream) {
     p.scale_log2 = a->scale * 1.4426950408889634f;
     {
         const dim3 grid((unsigned)((a->Tk + 63) / 64), (unsigned)a->H, (unsigned)a->B);
-        attn_vt_kernel<D><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->v), a->v_bs, a->v_rs, a->v_hs,
-                                                    reinterpret_cast<__nv_bfloat16*>(a->workspace), a->H, a->Tk, (int)Tkp);
+        const cudaError_t e = launch_k(attn_vt_kernel<D>, grid, dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(a->v),
+                                       (long long)a->v_bs, (int)a->v_rs, (int)a->v_hs, reinterpret_cast<__nv_bfloat16*>(a->workspace), (int)a->H,
+                                       (int)a->Tk, (int)Tkp);
+        if (e != cudaSuccess) return (int)e;
         const int st = launch_result();
         if (st != GG_OK) return st;
     }
@@ -426,7 +432,8 @@ static int launch_attention_tc(const gg_attn_args* a, cudaStream_t stream) {
     p.two = 2 * ctas2 > num_sms() ? 1 : 0;          // one tile per CTA only while the doubled grid still is a single wave
     const int rows = p.two ? 2 * AT_BM : AT_BM;
     const dim3 grid((unsigned)((a->Tq + rows - 1) / rows), (unsigned)a->H, (unsigned)a->B);
-    fn<<<grid, AT_THREADS, smem, stream>>>(p);
+    const cudaError_t le = launch_k(fn, grid, dim3(AT_THREADS), smem, stream, p);
+    if (le != cudaSuccess) return (int)le;
     return launch_result();
 }
 

@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include "../../include/guidegen_sm100.h"
 
 namespace gg {
@@ -33,7 +35,41 @@ inline int num_sms() {
 
 #define GG_REQUIRE(cond, code) do { if (!(cond)) return (code); } while (0)
 
+// Programmatic dependent launch (GG_PDL=1; OFF by default).  With the stream-serialization attribute a kernel is scheduled while
+// its predecessor still runs: its CTAs become resident as SM resources free up, run their prologue (barrier init, TMEM allocation,
+// tensor-map prefetch) and block in pdl_wait() until the predecessor has COMPLETED and its memory is visible.  Rule for every
+// kernel launched through launch_k: nothing before pdl_wait() reads or writes global memory another kernel touches; ordering
+// stays transitive (kernel N cannot complete before its own wait has seen N-1 complete).  Captured into CUDA graphs as
+// programmatic dependency edges.  MEASURED on B200 (profiles/r2_lanes_and_pdl.md): inside a CUDA graph the kernel-to-kernel
+// gap is already ~1 us, and nothing was gained -- config 3: 4.81 ms (off) / 4.80 (completion trigger) / 4.99 (early trigger:
+// dependents placed greedily on the SMs that free up first); config 4: 11.4 / 11.3 / 11.4; two lanes + early trigger 12.2.
+// All GPU tests pass with it on.  Kept as a tested knob.
+inline bool pdl_enabled() {
+    static const int on = [] { const char* e = getenv("GG_PDL"); return e ? atoi(e) : 0; }();
+    return on != 0;
+}
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 // ---------------------------------------------------------------------------- device helpers
+#ifndef GG_PDL_TRIGGER
+#define GG_PDL_TRIGGER 1        // 0: dependents are released only by this grid's completion (tuning builds)
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if GG_PDL_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

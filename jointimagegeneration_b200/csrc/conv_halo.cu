@@ -17,8 +17,17 @@
 // The A ring holds depth planes of the halo window (18 x 10 rows = 23 KB each, used by the kh*kw taps of one
 // depth tap), three planes deep, so the next chunk's planes stream in while the current ones are consumed.
 //
-// Roles (224 threads): warp 0 = A (halo) producer, warp 1 = MMA issuer, warps 2..5 = epilogue,
-// warp 6 = B (weight) producer.  K order of the packed weights: source -> 64-channel chunk -> tap.
+// Roles: warp 0 = A (halo) producer, warp 1 = MMA issuer, warps 2..5 = epilogue, warp 6 = B (weight) producer, warps 7..10 = a
+// second epilogue group (352 threads; with the fused input transform these are transform warps instead, 480 threads).
+// K order of the packed weights: source -> 64-channel chunk -> tap.
+//
+// Two epilogue groups (round 2): a tile with a short reduction (the 2 x 2 x 2 taps of the folded upsample: 4096 tensor-core
+// clocks) used to wait for its four epilogue warps (~9000 clocks per 128 x 128 tile with statistics, ncu: tensor pipe 47 %);
+// warps w and w + 5 share a TMEM lane quadrant (w % 4) and take half of the tile's columns each.
+//
+// Stationary weights (round 2): when the weight ring holds exactly the B stages of ONE tile (SB == stages per tile, one
+// N tile), stage i carries the same weights for every tile of the CTA: they are loaded for the first tile only.  The
+// upsample phases streamed 128 KB of weights per CTA and tile from L2 next to 80 KB of input windows.
 #include <cstdlib>
 
 #include "halo_common.cuh"
@@ -28,6 +37,7 @@ namespace gg {
 constexpr int H_ACC_COLS = 256;
 constexpr int H_XW = 8;                            // transform warps (four cannot keep up with the nine taps of a plane: measured)
 constexpr int H_THREADS_XF = H_THREADS + 32 * H_XW;  // + warps 7..: GroupNorm / SiLU transform of the landed halo planes
+constexpr int H_THREADS_E2 = H_THREADS + 128;        // + warps 7..10: second epilogue group (kernels without the transform)
 constexpr int H_MAX_SB = 8;
 constexpr int H_MAX_SA = 4;
 
@@ -54,6 +64,7 @@ struct alignas(64) HaloParams {
     int No, Do, Ho, Wo;
     int th, tw;                    // tiles along h, w (d and n are 1 per tile)
     int n_tiles_n, total_tiles;
+    int w_stat;                    // stationary weights: SB == B stages per tile, loaded once per CTA
     int Cout8;
     const float* bias;
     const float* emb;
@@ -70,7 +81,7 @@ struct alignas(64) HaloParams {
 };
 
 template <int G, bool STATS, bool PAIR, bool XFORM>
-__global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS_E2, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -91,6 +102,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
     // persistent schedule: in PAIR mode a "tile" is a pair of w-adjacent bricks and the two CTAs of a cluster walk
     // the same tile sequence (p.tw = pairs along w); CTA `rank` owns brick 2 iw + rank
     const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < p.nseg; ++i) prefetch_tmap(&p.amap[i]);
         prefetch_tmap(&p.wmap);
@@ -99,7 +111,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
         if (lane == 0) {
             for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], PAIR ? 2 * H_XW : H_XW); }
             for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 8 : 4); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (PAIR ? 8 : 4) * (XFORM ? 1 : 2)); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -118,6 +130,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
     if constexpr (PAIR) cluster_sync_all();       // the peer's barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                     // the prologue above touched only shared memory / TMEM / kernel parameters (common.cuh)
 
     if (warp == 0) {
         // ================================================================ A (halo brick) producer
@@ -159,6 +172,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
         int sb = 0;
         uint32_t phb = 0;
         for (int tile = tile0; tile < p.total_tiles; tile += tstep) {
+            if (p.w_stat && tile != tile0) break;       // stationary weights: every stage already holds what this tile needs
             const int nt = tile % p.n_tiles_n;
             int kb = 0;
             for (int s = 0; s < p.nseg; ++s) {
@@ -193,7 +207,9 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
         const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem_b);
         int sa = 0, sb = 0;
         uint32_t pha = 0, phb = 0, acc = 0, acc_phase = 0;
+        const bool w_stat = p.w_stat != 0;
         for (int tile = tile0; tile < (rank == 0 ? p.total_tiles : 0); tile += tstep) {
+            const bool b_wait = !w_stat || tile == tile0;       // stationary weights: landed during the first tile, never released
             mbar_wait(&tempty[acc], acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * H_ACC_COLS;
@@ -213,7 +229,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
                         for (int b = 0; b < sg.kh; ++b) {
                             const uint32_t row16 = a_stage16 + (uint32_t)(b * sg.pitch) * 8u;      // 128 B rows -> 8 x 16 B
                             if (G > 1 && sg.g == G) {
-                                mbar_wait(&b_full[sb], phb);
+                                if (b_wait) mbar_wait(&b_full[sb], phb);
                                 tc_fence_after();
                                 if (elect_one()) {
                                     const uint32_t b16 = (b_base + (uint32_t)sb * p.b_stage_bytes) >> 4;
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
                                         umma_bf16_t<PAIR>(d_tmem, ad + 4, bd + 4, idesc, 1u);
                                         umma_bf16_t<PAIR>(d_tmem, ad + 6, bd + 6, idesc, 1u);
                                     }
-                                    umma_commit_t<PAIR>(&b_empty[sb]);
+                                    if (!w_stat) umma_commit_t<PAIR>(&b_empty[sb]);
                                     if (b == sg.kh - 1) {
                                         umma_commit_t<PAIR>(&a_empty[sa]);
                                         if (last_chunk && a == sg.kd - 1) umma_commit_t<PAIR>(&tfull[acc]);
@@ -236,7 +252,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
                                 if (++sb == SB) { sb = 0; phb ^= 1u; }
                             } else {
                                 for (int c = 0; c < sg.kw; ++c) {
-                                    mbar_wait(&b_full[sb], phb);
+                                    if (b_wait) mbar_wait(&b_full[sb], phb);
                                     tc_fence_after();
                                     if (elect_one()) {
                                         const uint64_t ad = a_tmpl | (uint64_t)(row16 + 8u * c);
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
                                         umma_bf16_t<PAIR>(d_tmem, ad + 2, bd + 2, idesc, 1u);
                                         umma_bf16_t<PAIR>(d_tmem, ad + 4, bd + 4, idesc, 1u);
                                         umma_bf16_t<PAIR>(d_tmem, ad + 6, bd + 6, idesc, 1u);
-                                        umma_commit_t<PAIR>(&b_empty[sb]);
+                                        if (!w_stat) umma_commit_t<PAIR>(&b_empty[sb]);
                                         if (b == sg.kh - 1 && c == sg.kw - 1) {
                                             umma_commit_t<PAIR>(&a_empty[sa]);
                                             if (last_chunk && a == sg.kd - 1) umma_commit_t<PAIR>(&tfull[acc]);
@@ -341,11 +357,16 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
             }
         }
     } else {
-        // ================================================================ epilogue (warps 2..5)
+        // ================================================================ epilogue (warps 2..5; without XFORM also warps 7..10:
+        // warps w and w + 5 serve the same TMEM lane quadrant and split the tile's columns at a multiple of 32)
+        constexpr int ET = XFORM ? 128 : 256;          // epilogue threads
+        const int eg = warp >= 7 ? 1 : 0;              // column group
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int rh = row >> 3, rw = row & 7;
-        const int etid = threadIdx.x - 64;             // 0..127 among the epilogue warps
+        const int etid = eg ? (int)threadIdx.x - H_THREADS + 128 : (int)threadIdx.x - 64;       // 0..ET-1 among the epilogue warps
+        const int c_split = XFORM ? BN : min(BN, (BN / 2 + 31) / 32 * 32);
+        const int c_lo = eg ? c_split : 0, c_n = eg ? BN - c_split : c_split;      // this warp's columns [c_lo, c_lo + c_n) of the tile
         uint32_t acc = 0, acc_phase = 0;
         int cur_n = -1, cur_nt = -1;
         const uint32_t tempty_r0 = PAIR ? leader_addr(&tempty[0]) : 0u, tempty_r1 = PAIR ? leader_addr(&tempty[1]) : 0u;
@@ -358,8 +379,8 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
             const int h = ih * H_BH + rh, w = iw * H_BW + rw;
             const bool valid = h < p.Ho && w < p.Wo;
             if (n != cur_n || nt != cur_nt) {          // uniform over the four epilogue warps (same tile sequence)
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone is done with the previous vector
-                for (int c = etid; c < BN; c += 128) {
+                asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");      // everyone is done with the previous vector
+                for (int c = etid; c < BN; c += ET) {
                     const int ch = nt * BN + c;
                     float v = 0.f;
                     if (ch < p.Cout8) {
@@ -368,24 +389,27 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS, 1) conv_halo
                     }
                     bvec[c] = v;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
                 cur_n = n; cur_nt = nt;
             }
             const long long yoff = (long long)n * p.y_sn + (long long)d * p.y_sd + (long long)h * p.y_sh + (long long)w * p.y_sw;
             const long long lin = (((long long)n * p.Do + d) * p.Ho + h) * p.Wo + w;
-            const int ncols = min(BN, p.Cout8 - nt * BN);
-            const __nv_bfloat16* res_row = p.residual ? p.residual + lin * p.res_stride + nt * BN : nullptr;
-            void* y_row = p.y_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.y) + yoff + nt * BN)
-                                     : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + nt * BN);
+            const int ncols = max(0, min(c_n, p.Cout8 - nt * BN - c_lo));       // real output columns among this warp's c_n
+            const int ch0 = nt * BN + c_lo;
+            const __nv_bfloat16* res_row = p.residual ? p.residual + lin * p.res_stride + ch0 : nullptr;
+            void* y_row = p.y_is_f32 ? static_cast<void*>(reinterpret_cast<float*>(p.y) + yoff + ch0)
+                                     : static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + ch0);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + acc * H_ACC_COLS + ((uint32_t)(q * 32) << 16);
-            if constexpr (STATS) {
-                float* stat_row = p.gn_partial + (((long long)n * p.gn_nchunks_total + p.gn_chunk_base + (long long)blockIdx.x * 4 + q) *
-                                                      p.Cout8 + nt * BN) * 2;
-                epilogue_row_stats(t_addr, BN, ncols, bvec, res_row, reinterpret_cast<__nv_bfloat16*>(y_row), valid, stat_row, lane);
-            } else {
-                epilogue_row(t_addr, BN, ncols, bvec, res_row, y_row, p.y_is_f32, valid);
+            const uint32_t t_addr = tmem_base + acc * H_ACC_COLS + (uint32_t)c_lo + ((uint32_t)(q * 32) << 16);
+            if (c_n > 0) {
+                if constexpr (STATS) {
+                    float* stat_row = p.gn_partial + (((long long)n * p.gn_nchunks_total + p.gn_chunk_base + (long long)blockIdx.x * 4 + q) *
+                                                          p.Cout8 + ch0) * 2;
+                    epilogue_row_stats(t_addr, c_n, ncols, bvec + c_lo, res_row, reinterpret_cast<__nv_bfloat16*>(y_row), valid, stat_row, lane);
+                } else {
+                    epilogue_row(t_addr, c_n, ncols, bvec + c_lo, res_row, y_row, p.y_is_f32, valid);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -419,11 +443,13 @@ static int launch_halo(const HaloParams& p, int grid, size_t smem, cudaStream_t 
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(XFORM ? H_THREADS_XF : H_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(XFORM ? H_THREADS_XF : H_THREADS_E2); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
     if (e != cudaSuccess) return (int)e;
     return launch_result();
@@ -447,7 +473,8 @@ int conv_halo_grid(const gg_conv_args* a, bool* pair_out) {
     const int BN = a->block_n > 0 ? a->block_n : gg_conv_pick_block_n(a->Cout);
     const int th = (a->Ho + H_BH - 1) / H_BH, tw = (a->Wo + H_BW - 1) / H_BW;
     bool pair = a->algo == 3 || (a->algo == 1 && tw % 2 == 0);
-    if (const char* e = getenv("GG_HALO_PAIR")) { if (a->algo == 1) pair = pair && atoi(e) != 0; }     // tuning knob
+    static const int knob_pair = [] { const char* e = getenv("GG_HALO_PAIR"); return e ? atoi(e) : 1; }();      // tuning knob, read once
+    if (a->algo == 1) pair = pair && knob_pair != 0;
     const int64_t tiles = (int64_t)a->N * a->Do * th * (pair ? (tw + 1) / 2 : tw) * ((a->Cout + BN - 1) / BN);
     if (pair_out) *pair_out = pair;
     return pair ? 2 * (int)std::min<int64_t>(tiles, num_sms() / 2) : (int)std::min<int64_t>(tiles, num_sms());
@@ -516,7 +543,8 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     for (int s = 0; s < a->nsrc; ++s) kwmax = std::max(kwmax, p.seg[s].kw);
     // a B stage holds a whole kw row of taps when three A planes and >= 3 such B stages still fit
     int G = kwmax;
-    if (const char* e = getenv("GG_HALO_MAXG")) G = std::min(G, std::max(1, atoi(e)));     // tuning knob
+    static const int knob_maxg = [] { const char* e = getenv("GG_HALO_MAXG"); return e ? std::max(1, atoi(e)) : 3; }();     // tuning knob, read once
+    G = std::min(G, knob_maxg);
     int SA = 3;
     int SB = (avail - SA * (int)p.a_stage_bytes) / (G * (int)p.b_tap_bytes);
     if (SB < 3) {
@@ -530,6 +558,17 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     }
     p.b_stage_bytes = (uint32_t)G * p.b_tap_bytes;
     for (int s = 0; s < a->nsrc; ++s) p.seg[s].g = (G > 1 && p.seg[s].kw == G) ? G : 1;
+    {   // stationary weights: the ring holds exactly one tile's B stages (and the CTA keeps them for all its tiles)
+        int nst = 0;
+        for (int s = 0; s < a->nsrc; ++s) nst += p.seg[s].nchunks * p.seg[s].kd * p.seg[s].kh * (p.seg[s].kw / p.seg[s].g);
+        static const bool allow = [] { const char* e = getenv("GG_HALO_WSTAT"); return e == nullptr || atoi(e) != 0; }();
+        if (allow && p.n_tiles_n == 1 && nst <= H_MAX_SB && p.total_tiles > grid / (pair ? 2 : 1) &&
+            nst * (int)p.b_stage_bytes + 3 * (int)p.a_stage_bytes <= avail) {
+            SB = nst;
+            SA = std::min(H_MAX_SA, (avail - nst * (int)p.b_stage_bytes) / (int)p.a_stage_bytes);
+            p.w_stat = 1;
+        }
+    }
     p.SA = SA; p.SB = SB;
     const size_t smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * p.b_stage_bytes + bar_bytes + 1024;
 

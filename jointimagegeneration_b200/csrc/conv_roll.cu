@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
     const int item0 = (int)(blockIdx.x >> 1), istep = (int)(gridDim.x >> 1);
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < p.nseg; ++i) prefetch_tmap(&p.amap[i]);
         prefetch_tmap(&p.wmap);
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                     // the prologue above touched only shared memory / TMEM / kernel parameters (common.cuh)
 
     if (warp == 0) {
         // ================================================================ A (halo plane) producer
@@ -734,10 +736,12 @@ static int launch_roll(const RollParams& p, int grid, size_t smem, cudaStream_t 
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(RollThreads<XW>::value); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
     if (e != cudaSuccess) return (int)e;
     return launch_result();

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    pdl_launch_dependents();        // the next kernel's CTAs may become resident (and run their prologue) as this one's exit
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < MAX_MAPS; ++i) prefetch_tmap(&p.amap[i]);
         prefetch_tmap(&p.wmap);
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                     // everything above touched only this CTA's shared memory / TMEM and the kernel parameters
 
     if (warp == 0) {
         // ================================================================ TMA producer
@@ -403,6 +405,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tcgen05_kernel(const __gr
 
 // sum of the split-K partials + bias + emb + residual -> output (8 channels per thread)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ConvParams p, long long npos) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int P8 = p.Cout8 >> 3;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npos * P8) return;
@@ -700,11 +704,13 @@ extern "C" int gg_conv_fwd(const gg_conv_args* a, gg_stream_t stream) {
         p.split_counters = a->split_counters;
     }
     const int grid = (int)std::min<int64_t>((int64_t)p.total_tiles * p.split_k, num_sms());
-    conv_tcgen05_kernel<<<grid, NUM_THREADS, smem, as_stream(stream)>>>(p);
+    cudaError_t le = launch_k(conv_tcgen05_kernel, dim3(grid), dim3(NUM_THREADS), smem, as_stream(stream), p);
+    if (le != cudaSuccess) return (int)le;
     int st = launch_result();
     if (st != GG_OK || p.split_k == 1 || p.split_counters != nullptr) return st;
     const long long npos = (long long)a->N * a->Do * a->Ho * a->Wo;
     const long long nthr = npos * (p.Cout8 / 8);
-    splitk_reduce_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, as_stream(stream)>>>(p, npos);
+    le = launch_k(splitk_reduce_kernel, dim3((unsigned)((nthr + 255) / 256)), dim3(256), 0, as_stream(stream), p, npos);
+    if (le != cudaSuccess) return (int)le;
     return launch_result();
 }

@@ -18,6 +18,8 @@ static inline int64_t gn_chunk_positions(int64_t S, int32_t C) {
 __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t S, int C, int64_t cs,
                                                          int nchunks, float* __restrict__ partial) {
     extern __shared__ float sm[];  // [R][2*C]
+    pdl_launch_dependents();
+    pdl_wait();
     const int P8 = C >> 3;
     const int R = 256 / P8;
     const int oct = threadIdx.x % P8, row = threadIdx.x / P8;
@@ -134,6 +136,8 @@ __device__ __forceinline__ void gn_write_scale_shift(const gg_gn_finalize_args& 
 }
 
 __global__ void __launch_bounds__(128) gn_finalize_kernel(const gg_gn_finalize_args a) {
+    pdl_launch_dependents();
+    pdl_wait();
     double s, ss;
     gn_group_sums(a, blockIdx.x, blockIdx.y, s, ss);
     gn_write_scale_shift(a, blockIdx.x, blockIdx.y, s, ss);
@@ -210,6 +214,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
                                                        const __nv_bfloat16* __restrict__ x2, int C2,
                                                        const float* __restrict__ ss, __nv_bfloat16* __restrict__ y,
                                                        int64_t S, int64_t cs) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int C = C1 + C2, P8 = C >> 3;
     const int R = 256 / P8;
     const int oct = threadIdx.x % P8, row = threadIdx.x / P8;
@@ -379,6 +385,8 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                         int64_t rows, int C, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -426,6 +434,8 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 
 __global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                     int64_t rows, int inner) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int P8 = inner >> 3;
     const int64_t total = rows * P8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -443,6 +453,8 @@ __global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* __restr
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                          int N, int D, int H, int W, int C, int fd, int fh, int fw) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int P8 = C >> 3;
     const int Do = D * fd, Ho = H * fh, Wo = W * fw;
     const int64_t total = (int64_t)N * Do * Ho * Wo * P8;
@@ -461,6 +473,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
 // timestep embedding + small-M linear (fp32; accurate sinf/cosf/expf -- no fast-math here)
 // ------------------------------------------------------------------------------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ emb, int B, int dim, float max_period) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
@@ -477,6 +491,8 @@ template <int MT, bool VEC>
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ y, int M, int N,
                                                            int K, int act_in, int act_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -537,8 +553,9 @@ extern "C" int gg_gn_partial(const void* x_cl, int32_t N, int64_t S, int32_t C, 
     const int R = 256 / (C / 8);
     const size_t smem = (size_t)R * 2 * C * sizeof(float);
     dim3 grid(nchunks, N);
-    gn_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x_cl), S, C, cs, nchunks,
-                                                            partial);
+    const cudaError_t e = launch_k(gn_partial_kernel, grid, dim3(256), smem, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x_cl), S,
+                                   (int)C, cs, nchunks, partial);
+    if (e != cudaSuccess) return (int)e;
     return launch_result();
 }
 
@@ -564,7 +581,8 @@ extern "C" int gg_gn_finalize(const gg_gn_finalize_args* a, gg_stream_t stream) 
         return GG_OK;
     }
     dim3 grid(a->groups, a->N);
-    gn_finalize_kernel<<<grid, 128, 0, as_stream(stream)>>>(*a);
+    const cudaError_t e = launch_k(gn_finalize_kernel, grid, dim3(128), 0, as_stream(stream), *a);
+    if (e != cudaSuccess) return (int)e;
     return launch_result();
 }
 
@@ -583,14 +601,10 @@ extern "C" int gg_gn_apply(const void* x1_cl, int32_t C1, const void* x2_cl, int
     int64_t nblk = (S + cs - 1) / cs;
     if (nblk > 65535 * 16) return GG_ERR_UNSUPPORTED;
     dim3 grid((unsigned)nblk, (unsigned)N);
-    if (silu)
-        gn_apply_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x1_cl), C1,
-                                                                 reinterpret_cast<const __nv_bfloat16*>(x2_cl), C2, scale_shift,
-                                                                 reinterpret_cast<__nv_bfloat16*>(y_cl), S, cs);
-    else
-        gn_apply_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x1_cl), C1,
-                                                                  reinterpret_cast<const __nv_bfloat16*>(x2_cl), C2, scale_shift,
-                                                                  reinterpret_cast<__nv_bfloat16*>(y_cl), S, cs);
+    const cudaError_t e = launch_k(silu ? gn_apply_kernel<true> : gn_apply_kernel<false>, grid, dim3(256), 0, as_stream(stream),
+                                   reinterpret_cast<const __nv_bfloat16*>(x1_cl), (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2_cl), (int)C2,
+                                   scale_shift, reinterpret_cast<__nv_bfloat16*>(y_cl), S, cs);
+    if (e != cudaSuccess) return (int)e;
     return launch_result();
 }
 
@@ -632,8 +646,9 @@ extern "C" int gg_layernorm(const void* x, const float* gamma, const float* beta
     GG_REQUIRE(C % 8 == 0, GG_ERR_UNSUPPORTED);
     GG_REQUIRE(aligned(x, 16) && aligned(y, 16), GG_ERR_ALIGNMENT);
     const unsigned blocks = (unsigned)((rows + 7) / 8);
-    layernorm_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
-                                                          reinterpret_cast<__nv_bfloat16*>(y), rows, C, eps);
+    const cudaError_t e = launch_k(layernorm_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), gamma,
+                                   beta, reinterpret_cast<__nv_bfloat16*>(y), rows, (int)C, eps);
+    if (e != cudaSuccess) return (int)e;
     return launch_result();
 }
 
@@ -725,8 +740,9 @@ extern "C" int gg_geglu(const void* x, void* y, int64_t rows, int32_t inner, gg_
     GG_REQUIRE(aligned(x, 16) && aligned(y, 16), GG_ERR_ALIGNMENT);
     const int64_t total = rows * (inner / 8);
     const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
-    geglu_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                      reinterpret_cast<__nv_bfloat16*>(y), rows, inner);
+    const cudaError_t e = launch_k(geglu_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x),
+                                   reinterpret_cast<__nv_bfloat16*>(y), rows, (int)inner);
+    if (e != cudaSuccess) return (int)e;
     return launch_result();
 }
 
@@ -738,15 +754,18 @@ extern "C" int gg_upsample2x(const void* x_cl, void* y_cl, int32_t N, int32_t D,
     const int fd = dims >= 3 ? 2 : 1, fh = dims >= 2 ? 2 : 1, fw = 2;
     const int64_t total = (int64_t)N * D * fd * H * fh * W * fw * (C / 8);
     const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
-    upsample2x_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x_cl),
-                                                           reinterpret_cast<__nv_bfloat16*>(y_cl), N, D, H, W, C, fd, fh, fw);
+    const cudaError_t e = launch_k(upsample2x_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x_cl),
+                                   reinterpret_cast<__nv_bfloat16*>(y_cl), (int)N, (int)D, (int)H, (int)W, (int)C, fd, fh, fw);
+    if (e != cudaSuccess) return (int)e;
     return launch_result();
 }
 
 extern "C" int gg_timestep_embedding(const float* t, float* emb, int32_t B, int32_t dim, float max_period, gg_stream_t stream) {
     GG_REQUIRE(t && emb && B > 0 && dim >= 2, GG_ERR_BAD_ARG);
     const int total = B * (dim / 2);
-    timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(t, emb, B, dim, max_period);
+    const cudaError_t e = launch_k(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, as_stream(stream), t, emb, (int)B, (int)dim,
+                                   max_period);
+    if (e != cudaSuccess) return (int)e;
     return launch_result();
 }
 
@@ -756,12 +775,9 @@ extern "C" int gg_small_linear(const float* x, const float* w, const float* b, f
     const unsigned blocks = (unsigned)((N + 7) / 8);
     const bool vec = (K % 4 == 0) && aligned(x, 16) && aligned(w, 16);
     cudaStream_t s = as_stream(stream);
-    if (M <= 4) {
-        if (vec) small_linear_kernel<4, true><<<blocks, 256, 0, s>>>(x, w, b, y, M, N, K, act_in, act_out);
-        else small_linear_kernel<4, false><<<blocks, 256, 0, s>>>(x, w, b, y, M, N, K, act_in, act_out);
-    } else {
-        if (vec) small_linear_kernel<16, true><<<blocks, 256, 0, s>>>(x, w, b, y, M, N, K, act_in, act_out);
-        else small_linear_kernel<16, false><<<blocks, 256, 0, s>>>(x, w, b, y, M, N, K, act_in, act_out);
-    }
+    auto fn = M <= 4 ? (vec ? small_linear_kernel<4, true> : small_linear_kernel<4, false>)
+                     : (vec ? small_linear_kernel<16, true> : small_linear_kernel<16, false>);
+    const cudaError_t e = launch_k(fn, dim3(blocks), dim3(256), 0, s, x, w, b, y, (int)M, (int)N, (int)K, (int)act_in, (int)act_out);
+    if (e != cudaSuccess) return (int)e;
     return launch_result();
 }

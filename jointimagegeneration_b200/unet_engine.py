@@ -106,10 +106,15 @@ class _PyStep:
 
 
 class Plan:
+    """A static launch list.  ``lanes``: independent step lists over disjoint sample ranges of the batch (one by default).
+    With several lanes ``run()`` forks the current stream: lane 0 stays on it, every other lane is enqueued on its own side
+    stream and joined at the end, so the many small launches of a low-resolution network (a few dozen CTAs, ~10 us each)
+    overlap instead of queueing behind each other; under capture the lanes become parallel branches of ONE CUDA graph."""
     has_py = False
 
     def __init__(self):
-        self.steps = []       # (cfunc, args tuple without the stream)
+        self.lanes = [[]]     # per lane: (cfunc, args tuple without the stream)
+        self._cur = 0
         self.keep = []        # ctypes structs / tensors that must outlive the plan
         self.inputs: Dict[str, torch.Tensor] = {}
         self.outputs: Dict[str, torch.Tensor] = {}
@@ -119,42 +124,83 @@ class Plan:
         self.flops = 0        # 2 * MACs actually issued by conv / attention launches
         # (gg_conv_args copy, gg_cat_epilogue) of the head conv with the sampler in its epilogue (CCDM resident loop), or None
         self.fused_head = None
+        # the same per lane: [(gg_conv_args copy, gg_cat_epilogue, first sample of the lane)]
+        self.fused_heads = []
+        self._side = None     # side streams + fork / join events of a multi-lane plan (made on first use)
+
+    # ---- construction
+    def begin_lane(self, j: int):
+        while len(self.lanes) <= j:
+            self.lanes.append([])
+        self._cur = j
 
     def add(self, fn, *args):
-        self.steps.append((fn, args))
+        self.lanes[self._cur].append((fn, args))
 
     def add_py(self, fn, *args):
         """A host-side step (collective / halo exchange): called as fn(*args), enqueues on the current stream."""
-        self.steps.append((_PyStep(fn), args))
+        self.lanes[self._cur].append((_PyStep(fn), args))
         self.has_py = True
+
+    @property
+    def steps(self):
+        """All launches in lane order (per-launch timing, launch counts); THE list for a single-lane plan."""
+        return self.lanes[0] if len(self.lanes) == 1 else [st for lane in self.lanes for st in lane]
+
+    @property
+    def body_steps(self):
+        """Everything but each lane's last step (the head conv)."""
+        return [st for lane in self.lanes for st in lane[:-1]]
+
+    # ---- execution
+    @staticmethod
+    def _launch(fn, args, s):
+        if isinstance(fn, _PyStep):
+            fn.fn(*args)
+            return
+        st = fn(*args, s)
+        if st != 0:
+            _C.check(st, fn.__name__)
+
+    def _enqueue(self, lanes):
+        if len(lanes) == 1:
+            s = _C.stream()
+            for fn, args in lanes[0]:
+                self._launch(fn, args, s)
+            return
+        assert not self.has_py, "host-side steps (NCCL slab transport) run on the current stream: single-lane plans only"
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            dev = main.device
+            self._side = ([torch.cuda.Stream(device=dev) for _ in lanes[1:]], torch.cuda.Event(),
+                          [torch.cuda.Event() for _ in lanes[1:]])
+        side, fork, joins = self._side
+        fork.record(main)
+        handles = [main.cuda_stream]
+        for s in side:
+            s.wait_event(fork)
+            handles.append(s.cuda_stream)
+        for i in range(max(len(lane) for lane in lanes)):       # round robin: every stream is fed from the first launch on
+            for j, lane in enumerate(lanes):
+                if i < len(lane):
+                    self._launch(lane[i][0], lane[i][1], handles[j])
+        for s, ev in zip(side, joins):
+            ev.record(s)
+            main.wait_event(ev)
 
     def run(self):
         if self.graph is not None:
             self.graph.replay()
             return
-        s = _C.stream()
-        for fn, args in self.steps:
-            if isinstance(fn, _PyStep):
-                fn.fn(*args)
-                continue
-            st = fn(*args, s)
-            if st != 0:
-                _C.check(st, fn.__name__)
+        self._enqueue(self.lanes)
 
     def run_body(self):
-        """Everything but the last step (the head conv): the caller launches the head itself -- with the sampler epilogue
-        whose per-step arguments (coefficients, Philox offset, label buffers) change from step to step."""
+        """Everything but the last step of each lane (the head conv): the caller launches the head itself -- with the sampler
+        epilogue whose per-step arguments (coefficients, Philox offset, label buffers) change from step to step."""
         if self.graph_body is not None:
             self.graph_body.replay()
             return
-        s = _C.stream()
-        for fn, args in self.steps[:-1]:
-            if isinstance(fn, _PyStep):
-                fn.fn(*args)
-                continue
-            st = fn(*args, s)
-            if st != 0:
-                _C.check(st, fn.__name__)
+        self._enqueue([lane[:-1] for lane in self.lanes])
 
     def capture_body(self):
         if self.has_py or self.graph_body is not None:
@@ -163,14 +209,12 @@ class Plan:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            s = _C.stream()
-            for fn, args in self.steps[:-1]:
-                _C.check(fn(*args, s), fn.__name__)
+            self._enqueue([lane[:-1] for lane in self.lanes])
         self.graph_body = g
 
     def capture(self):
-        """Capture the forward into a CUDA graph (after one eager warm-up run).  Plans with collectives
-        (depth-slab mode) stay eager: capturing the NCCL ops works, but measured no gain at 2 GPUs and mixing
+        """Capture the forward into a CUDA graph (after one eager warm-up run).  Plans with host-side collectives
+        (depth-slab mode over NCCL) stay eager: capturing the NCCL ops works, but measured no gain at 2 GPUs and mixing
         captured and eager collectives on one communicator dead-locked at teardown (round-1 experiment)."""
         if self.has_py:
             return
@@ -178,17 +222,12 @@ class Plan:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            s = _C.stream()
-            for fn, args in self.steps:
-                if isinstance(fn, _PyStep):
-                    fn.fn(*args)
-                else:
-                    _C.check(fn(*args, s), fn.__name__)
+            self._enqueue(self.lanes)
         self.graph = g
 
     @property
     def num_launches(self):
-        return len(self.steps)
+        return sum(len(lane) for lane in self.lanes)
 
 
 class UNetEngine:
@@ -795,27 +834,86 @@ class UNetEngine:
         return out
 
     # -------------------------------------------------------------------------------- plan
-    def build_plan(self, N: int, spatial: Tuple[int, ...], in_ch_pad: int, ctx_shape=None, f32_head: bool = True) -> Plan:
+    def pick_lanes(self, N: int, spatial) -> int:
+        """Independent sample lanes of a plan (Plan.lanes).  GG_LANES pins the count.  Measured on B200 (round 2,
+        profiles/r2_lanes_and_pdl.md): no gain where every launch already fills the GPU (config 2: 45.0 -> 45.9 ms) and none on
+        the 64 x 64 latents of config 3 either (4.80 -> 5.05 ms: there a launch is a persistent 1-CTA-per-SM kernel whose
+        fixed cost, not its CTA count, is the time -- lanes only multiply the launches); two samples of a 512 x 512 slice
+        (config 4) gain 5 % from overlapping each other's tails.  So: two lanes for mid-sized 2-D batches, one otherwise."""
+        env = os.environ.get("GG_LANES")
+        if self.slab is not None:
+            return 1
+        if env is not None:
+            k = max(1, int(env))
+        else:
+            positions = N * int(math.prod(spatial))
+            k = 2 if (self.dims == 2 and (1 << 18) < positions <= (1 << 20)) else 1
+        while k > 1 and N % k != 0:
+            k -= 1
+        return k
+
+    def build_plan(self, N: int, spatial: Tuple[int, ...], in_ch_pad: int, ctx_shape=None, f32_head: bool = True,
+                   lanes: Optional[int] = None) -> Plan:
         self.lib = _C.lib()
         m = self.model
         dev = self._dev()
-        plan, ar = Plan(), _Arena(dev)
+        plan = Plan()
+        lanes = self.pick_lanes(N, spatial) if lanes is None else lanes
+        assert N % lanes == 0
         sp3 = (1,) * (3 - len(spatial)) + tuple(spatial)
         lead, trail = self._lead, self._trail
         x_full = torch.zeros((N, sp3[0] + lead + trail) + sp3[1:] + (in_ch_pad,), dtype=torch.bfloat16, device=dev)
-        x_act = Act(x_full, lead, trail)
-        x_in = x_act.interior                       # contiguous: lead > 0 only with N == 1
         t_in = torch.zeros((N,), dtype=torch.float32, device=dev)
-        plan.inputs["x"], plan.inputs["t"] = x_in, t_in
+        plan.inputs["x"], plan.inputs["t"] = Act(x_full, lead, trail).interior, t_in     # contiguous: lead > 0 only with N == 1
         plan.keep.append(x_full)
-        if self.slab is not None and getattr(self.slab, "peer", False):
-            self.slab.plan_begin(plan)              # one communication epoch per forward
-        ctx = None
+        c_in = None
         if ctx_shape is not None:
             L, cd = ctx_shape
             c_in = torch.zeros((N, 1, 1, L, cd), dtype=torch.bfloat16, device=dev)
             plan.inputs["context"] = c_in
-            ctx = Act(c_in)
+        oc = m.out[2]
+        head_full = None
+        if lanes > 1:
+            # the lanes write disjoint sample ranges of ONE head tensor
+            head_full = torch.zeros((N, sp3[0] + lead + trail) + sp3[1:] + ((oc.out_channels + 7) // 8 * 8,),
+                                    dtype=torch.float32 if f32_head else torch.bfloat16, device=dev)
+            plan.keep.append(head_full)
+            plan.outputs["head"] = Act(head_full, lead, trail).interior
+        per = N // lanes
+        for j in range(lanes):
+            plan.begin_lane(j)
+            n0, n1 = j * per, (j + 1) * per
+            ar = _Arena(dev)
+            head = self._build_lane(plan, ar, Act(x_full[n0:n1], lead, trail), t_in[n0:n1],
+                                    Act(c_in[n0:n1]) if c_in is not None else None, sp3, f32_head,
+                                    Act(head_full[n0:n1], lead, trail) if head_full is not None else None)
+            if lanes == 1:
+                plan.outputs["head"] = head.interior
+            ha = plan.lanes[j][-1][1][0]._obj
+            if (kind_ccdm_head(m) and int(ha.algo) == 4 and oc.out_channels <= 16 and f32_head
+                    and per * int(math.prod(sp3)) % 4 == 0):
+                # the same launch with the categorical sampler in its epilogue (gg_conv_args.cat): used by the resident loop
+                cat = _C.CatEpilogue()
+                fa = _C.ConvArgs.from_buffer_copy(ha)
+                fa.cat = C.pointer(cat)
+                plan.fused_heads.append((fa, cat, n0))
+                plan.keep.append((fa, cat))
+            plan.keep.append(ar.stores)      # kernels hold raw pointers into these: they must outlive the plan
+            plan.arena_bytes += ar.total
+        if len(plan.fused_heads) == lanes:
+            plan.fused_head = plan.fused_heads[0][:2]
+        else:
+            plan.fused_heads = []
+        return plan
+
+    def _build_lane(self, plan: Plan, ar: _Arena, x_act: Act, t_in: torch.Tensor, ctx: Optional[Act], sp3, f32_head: bool,
+                    head_out: Optional[Act]) -> Act:
+        """The launches of one forward over the samples of `x_act` (all of the batch, or one lane's share)."""
+        m = self.model
+        dev = self._dev()
+        N = x_act.N
+        if self.slab is not None and getattr(self.slab, "peer", False):
+            self.slab.plan_begin(plan)              # one communication epoch per forward
         # ---- timestep path (unet.py:772 / :511-515) + every ResBlock's emb projection in one launch
         mc = m.model_channels
         E = 4 * mc
@@ -892,25 +990,15 @@ class UNetEngine:
         # ---- head: GN -> SiLU -> conv (-> softmax fused downstream)   unet.py:715-721
         oc = m.out[2]
         b = self._vec8((id(oc.bias), "b"), lambda: oc.bias, oc.out_channels)
+        kw = dict(out=head_out) if head_out is not None else {}
         head = self._gn_conv(plan, ar, h, None, m.out[0], True, lambda splits: self._packer(oc, splits), oc.out_channels,
-                             dims=oc.dims, bias=_C.ptr(b), f32_out=f32_head)
+                             dims=oc.dims, bias=_C.ptr(b), f32_out=f32_head, **kw)
         self._free(ar, h)
-        plan.outputs["head"] = head.interior
-        ha = plan.steps[-1][1][0]._obj
-        if kind_ccdm_head(m) and int(ha.algo) == 4 and oc.out_channels <= 16 and f32_head and N * int(math.prod(sp3)) % 4 == 0:
-            # the same launch with the categorical sampler in its epilogue (gg_conv_args.cat): used by the resident loop
-            cat = _C.CatEpilogue()
-            fa = _C.ConvArgs.from_buffer_copy(ha)
-            fa.cat = C.pointer(cat)
-            plan.fused_head = (fa, cat)
-            plan.keep.append((fa, cat))
         plan.keep.extend([emb_all, emb, e1, temb])
-        plan.keep.append(ar.stores)      # kernels hold raw pointers into these: they must outlive the plan
-        plan.arena_bytes = ar.total
-        return plan
+        return head
 
     def get_plan(self, N, spatial, in_ch_pad, ctx_shape=None) -> Plan:
-        key = (N, tuple(spatial), in_ch_pad, ctx_shape)
+        key = (N, tuple(spatial), in_ch_pad, ctx_shape, os.environ.get("GG_LANES"))
         if key not in self.plans:
             self.plans[key] = self.build_plan(N, tuple(spatial), in_ch_pad, ctx_shape)
         return self.plans[key]
