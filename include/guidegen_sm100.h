@@ -244,6 +244,12 @@ int gg_gn_apply(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, co
  * above where their launch latency dominates (LDM latents, deep CCDM levels).  C1 + C2 <= 2048. */
 int gg_gn_fused(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* gamma, const float* beta, void* y_cl,
                 int32_t N, int64_t S, int32_t groups, float eps, int32_t silu, gg_stream_t stream);
+/* Cluster size (1..8) gg_gn_fused uses for a sample of S positions x C channels when the sample fits the shared memory of one
+ * cluster (the slice of every CTA is loaded once by bulk async copies; statistics and normalisation read shared memory), or 0
+ * when it does not fit and gg_gn_fused streams the slice from L2 twice instead (slower than the three launches: callers
+ * check this before choosing the one-launch form). */
+int32_t gg_gn_fused_resident(int64_t S, int32_t C);
+
 
 /* ------------------------------------------------------------------------------------------
  * K1-K5,K15  implicit-GEMM convolution on tcgen05 tensor cores (bf16 x bf16 -> fp32 in TMEM)

@@ -156,6 +156,7 @@ SYMBOLS = {
     "gg_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
     "gg_small_linear": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "gg_gn_fused": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _i32, _vp]),
+    "gg_gn_fused_resident": (_i32, [_i64, _i32]),
     "gg_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
     "gg_geglu": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "gg_softmax_rows": (C.c_int, [_vp, _vp, _i64, _i32, _f32, _vp]),

@@ -31,6 +31,15 @@
 
 namespace gg {
 
+// GG_ROLL_TIMING (build define, with GG_ROLL_DBG=1 at run time): GG_CLK() around the waits of the MMA issuer and the transform
+// warps.  Off in release builds: the issuer is a single thread whose instruction stream IS the critical path of the kernel
+// (ncu, skip-source layer: 65 % of its time goes to issuing, 30 % to waiting for weights), six clock reads per step do not belong there.
+#ifdef GG_ROLL_TIMING
+#define GG_CLK() clock64()
+#else
+#define GG_CLK() 0ll
+#endif
+
 constexpr int R_MAX_SA = 6, R_MAX_SB = 8;
 constexpr int R_THREADS = 352;      // warps 0, 1, 6 = producers / MMA; warps 2..5 drain brick 0, warps 7..10 drain brick 1
 // XFORM adds warps 11..: GroupNorm/SiLU transform of the landed halo planes (RollThreads below)
@@ -340,14 +349,14 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
             const uint32_t tap16 = (3u * p.b_unit_bytes) >> 4;
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0, phf[2] = {0, 0};
-            long long w_slot = 0, w_a = 0, w_b = 0, t_begin = clock64(), tq;
+            long long w_slot = 0, w_a = 0, w_b = 0, t_begin = GG_CLK(), tq;
             for (int item = item0; item < p.total_items; item += istep) {
                 const RollItem it = roll_item(p, item);
                 for (int t = 0; t < it.L + 2; ++t)
                     for (int wi = 0; wi < 2; ++wi) {
-                        tq = clock64();
+                        tq = GG_CLK();
                         mbar_wait(&slot_free[wi], phf[wi]);
-                        w_slot += clock64() - tq;
+                        w_slot += GG_CLK() - tq;
                         phf[wi] ^= 1u;
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)(wi * 3 * BNs);
@@ -357,9 +366,9 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
                             if (sg.centre && (t == 0 || t == it.L + 1)) continue;
                             const uint64_t a_tmpl = make_sw128_desc_sbo(0, (uint32_t)sg.pitch * 128u);
                             for (int j = 0; j < sg.nchunks; ++j) {
-                                tq = clock64();
+                                tq = GG_CLK();
                                 mbar_wait(XFORM ? &a_ready[sa] : &a_full[sa], pha);
-                                w_a += clock64() - tq;
+                                w_a += GG_CLK() - tq;
                                 if constexpr (XFORM) tc_fence_after();
                                 const uint32_t a_stage16 = (a_base + (uint32_t)sa * p.a_stage_bytes) >> 4;
                                 if (sg.centre) {
@@ -380,9 +389,9 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
                                     for (int b = 0; b < sg.kh; ++b) {
                                         const uint32_t row16 = a_stage16 + (uint32_t)(b * sg.pitch) * 8u;
                                         for (int cg = 0; cg < sg.kw / sg.g; ++cg) {
-                                            tq = clock64();
+                                            tq = GG_CLK();
                                             mbar_wait(&b_full[sb], phb);
-                                            w_b += clock64() - tq;
+                                            w_b += GG_CLK() - tq;
                                             tc_fence_after();
                                             if (elect_one()) {
                                                 const uint32_t b16 = (b_base + (uint32_t)sb * p.b_stage_bytes) >> 4;
@@ -415,7 +424,7 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
             }
             if (p.dbg != nullptr && elect_one()) {
                 unsigned long long* o = p.dbg + (size_t)(blockIdx.x >> 1) * 4;
-                o[0] = (unsigned long long)(clock64() - t_begin); o[1] = (unsigned long long)w_slot;
+                o[0] = (unsigned long long)(GG_CLK() - t_begin); o[1] = (unsigned long long)w_slot;
                 o[2] = (unsigned long long)w_a; o[3] = (unsigned long long)w_b;
             }
         }
@@ -427,7 +436,7 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
         int sa = 0, cur_n = -1;
         uint32_t pha = 0;
         const bool silu = p.xf_silu != 0;
-        long long x_wait = 0, x_begin = clock64(), xq;
+        long long x_wait = 0, x_begin = GG_CLK(), xq;
         for (int item = item0; item < p.total_items; item += istep) {
             const RollItem it = roll_item(p, item);
             if (it.n != cur_n) {        // (scale, shift) of this sample; uniform over the four warps
@@ -455,9 +464,9 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
                         const RollSeg sg = p.seg[s];
                         if (sg.centre && (t == 0 || t == it.L + 1)) continue;
                         for (int j = 0; j < sg.nchunks; ++j) {
-                            xq = clock64();
+                            xq = GG_CLK();
                             mbar_wait(&a_full[sa], pha);
-                            x_wait += clock64() - xq;
+                            x_wait += GG_CLK() - xq;
                             if (sg.ss_off >= 0 && z >= p.z_lo && z < p.z_hi) {
                                 uint8_t* stg = smem + (size_t)sa * p.a_stage_bytes;
                                 const int nrow = (H_BH + sg.kh - 1) * sg.pitch;
@@ -502,7 +511,7 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
         }
         if (p.dbg != nullptr && rank == 0 && xt == 0) {
             unsigned long long* o = p.dbg + 2048 + (size_t)(blockIdx.x >> 1) * 2;
-            o[0] = (unsigned long long)(clock64() - x_begin); o[1] = (unsigned long long)x_wait;
+            o[0] = (unsigned long long)(GG_CLK() - x_begin); o[1] = (unsigned long long)x_wait;
         }
     } else {
         // ================================================================ epilogue: warps 2..5 drain brick 0, warps 7..10 brick 1

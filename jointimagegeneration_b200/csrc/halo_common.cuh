@@ -117,8 +117,20 @@ __device__ __forceinline__ uint32_t leader_addr(const void* smem_ptr) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(smem_ptr)), "r"(0u));
     return r;
 }
+// Arrive on a barrier of the cluster (the leader's).  NOT `.release.cluster`: that form compiles to MEMBAR.ALL.GPU + ERRBAR +
+// CGAERRBAR in front of every arrive -- the epilogue warps of a pair kernel then wait for all their global stores to be
+// acknowledged before the accumulator goes back to the tensor core (ncu source page of the folded-upsample conv: 25 % of all
+// warp samples sat on that fence), and every transformed plane pays a GPU-scope fence on its way to the MMA issuer.  What these
+// arrives order is shared memory of the arriving CTA written through the generic proxy (made visible to the tensor core by the
+// fence.proxy.async in front) and TMEM reads (tcgen05.wait::ld + tcgen05.fence::before_thread_sync in front): the default
+// release at CTA scope is what that needs (the form CUTLASS's ClusterBarrier::arrive uses for the same hand-overs).
+// GG_ARRIVE_CLUSTER_RELEASE=1 (build define) restores the old form.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+#ifdef GG_ARRIVE_CLUSTER_RELEASE
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,
                                                  int c3, int c4) {

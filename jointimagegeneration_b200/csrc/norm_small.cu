@@ -380,6 +380,207 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------------------------------
+// GroupNorm (+SiLU) of SMALL tensors, shared-memory resident (round 2, second design).  The cluster form above re-reads its
+// slice from L2 and keeps only 256 threads x 4 loads in flight per CTA -- measured slower than the three launches it
+// replaces.  Here a sample's slice per CTA (<= ~190 KB) is brought into shared memory ONCE by bulk async copies (cp.async.bulk:
+// the bytes in flight do not depend on the thread count; eight chunks, one mbarrier each, so the statistics start on the first
+// chunk while the rest streams in), the statistics and the normalisation both read shared memory, and the tensor crosses
+// L2 exactly once in each direction.  Cluster of 1..8 CTAs per sample (the host picks the smallest that fits, at least one CTA
+// per ~48 KB); statistics combined over the cluster in fp64 through distributed shared memory as above.
+// Same apply formula and rounding points as gn_apply_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int GNR_THREADS = 512;
+constexpr int GNR_CHUNKS = 8;
+__device__ __forceinline__ void gnr_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gnr_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gnr_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void gnr_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok, spins = 0;
+    uint64_t t0 = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && (++spins & 0xFFFu) == 0) {       // watchdog: a protocol bug must surface as a launch error, not a hang
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    } while (!ok);
+}
+__device__ __forceinline__ void gnr_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GNR_THREADS, 1) gn_resident_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
+                                                                    int C2, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    __nv_bfloat16* __restrict__ y, int64_t S, int groups, float eps, int rows_per_cta) {
+    extern __shared__ __align__(128) uint8_t rsm[];
+    const int C = C1 + C2, P8 = C >> 3, R = GNR_THREADS / P8;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rsm);                   // [GNR_CHUNKS]
+    float2* part = reinterpret_cast<float2*>(rsm + 128);                 // [R][C]  per-thread-row channel sums of this CTA
+    float2* csum = part + R * C;                                         // [C]     this CTA's channel sums (read by the whole cluster)
+    float2* ssm = csum + C;                                              // [C]     (scale, shift)
+    uint8_t* buf1 = reinterpret_cast<uint8_t*>(ssm + C);                 // [rows_per_cta][C1] bf16
+    uint8_t* buf2 = buf1 + (size_t)rows_per_cta * C1 * 2;                // [rows_per_cta][C2] bf16
+    uint32_t rank, cl;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cl));
+    pdl_launch_dependents();
+    const int n = blockIdx.x / cl;
+    const int64_t p0 = (int64_t)rank * rows_per_cta;
+    const int rows = (int)max((int64_t)0, min(S, p0 + rows_per_cta) - p0);
+    const int rpc = max(1, (rows + GNR_CHUNKS - 1) / GNR_CHUNKS);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < GNR_CHUNKS; ++k) gnr_mbar_init(&bars[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < GNR_CHUNKS; ++k) {
+            const int r0 = k * rpc, r1 = min(rows, r0 + rpc);
+            if (r1 <= r0) { gnr_mbar_arrive(&bars[k]); continue; }
+            const uint32_t b1 = (uint32_t)(r1 - r0) * (uint32_t)C1 * 2u, b2 = (uint32_t)(r1 - r0) * (uint32_t)C2 * 2u;
+            gnr_mbar_expect_tx(&bars[k], b1 + b2);
+            gnr_bulk_load(buf1 + (size_t)r0 * C1 * 2, x1 + ((int64_t)n * S + p0 + r0) * C1, b1, &bars[k]);
+            if (C2 > 0) gnr_bulk_load(buf2 + (size_t)r0 * C2 * 2, x2 + ((int64_t)n * S + p0 + r0) * C2, b2, &bars[k]);
+        }
+    }
+    const int oct = threadIdx.x % P8, row = threadIdx.x / P8;
+    const bool active = row < R;
+    const int c0 = oct * 8;
+    const uint8_t* base = c0 < C1 ? buf1 + c0 * 2 : buf2 + (c0 - C1) * 2;
+    const int pitch = (c0 < C1 ? C1 : C2) * 2;
+    // ---- pass 1: per-channel (sum, sum of squares) over this CTA's rows, chunk by chunk as they land
+    {
+        float s1[8], s2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
+        auto acc = [&](uint4 v) {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+                s1[2 * e] += lo; s2[2 * e] = fmaf(lo, lo, s2[2 * e]);
+                s1[2 * e + 1] += hi; s2[2 * e + 1] = fmaf(hi, hi, s2[2 * e + 1]);
+            }
+        };
+        int p = row;
+        for (int k = 0; k < GNR_CHUNKS; ++k) {
+            gnr_mbar_wait(&bars[k], 0);
+            if (!active) continue;
+            const int r1 = min(rows, (k + 1) * rpc);
+            for (; p + 3 * R < r1; p += 4 * R) {
+                const uint4 a = *reinterpret_cast<const uint4*>(base + (size_t)p * pitch), b = *reinterpret_cast<const uint4*>(base + (size_t)(p + R) * pitch);
+                const uint4 c = *reinterpret_cast<const uint4*>(base + (size_t)(p + 2 * R) * pitch), d = *reinterpret_cast<const uint4*>(base + (size_t)(p + 3 * R) * pitch);
+                acc(a); acc(b); acc(c); acc(d);
+            }
+            for (; p < r1; p += R) acc(*reinterpret_cast<const uint4*>(base + (size_t)p * pitch));
+        }
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) part[row * C + c0 + e] = make_float2(s1[e], s2[e]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += GNR_THREADS) {
+        float a = 0.f, b = 0.f;
+        for (int r = 0; r < R; ++r) { const float2 v = part[r * C + c]; a += v.x; b += v.y; }
+        csum[c] = make_float2(a, b);
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // ---- group statistics: a warp per group, lanes stride over the (rank, channel) pairs of the cluster, fp64, fixed order
+    const int cpg = C / groups;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < groups; g += GNR_THREADS / 32) {
+        double s = 0.0, q = 0.0;
+        const uint32_t local = (uint32_t)__cvta_generic_to_shared(csum + g * cpg);
+        const int total = (int)cl * cpg;
+        for (int e = lane; e < total; e += 64) {            // two independent remote loads in flight per lane
+            const int e2 = e + 32;
+            const int r = e / cpg, c = e - r * cpg;
+            const int r2 = e2 < total ? e2 / cpg : r, c2 = e2 < total ? e2 - r2 * cpg : c;
+            uint32_t ra, rb;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(r));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(local), "r"(r2));
+            float2 va, vb;
+            asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(va.x), "=f"(va.y) : "r"(ra + 8u * (uint32_t)c));
+            asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(vb.x), "=f"(vb.y) : "r"(rb + 8u * (uint32_t)c2));
+            s += (double)va.x; q += (double)va.y;
+            if (e2 < total) { s += (double)vb.x; q += (double)vb.y; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        const double cnt = (double)S * cpg, mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+            const float sc = (gamma ? __ldg(gamma + c) : 1.0f) * rstd;
+            ssm[c] = make_float2(sc, (beta ? __ldg(beta + c) : 0.0f) - (float)mean * sc);
+        }
+    }
+    // nobody may leave while a peer still reads its csum; also publishes ssm within the CTA
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // ---- pass 2: normalise this CTA's rows out of shared memory
+    if (!active) return;
+    float sc[8], sh[8];
+    const float f = SILU ? 0.5f : 1.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float2 k = ssm[c0 + e]; sc[e] = k.x * f; sh[e] = k.y * f; }
+    __nv_bfloat16* dst = y + ((int64_t)n * S + p0) * C + c0;
+    auto apply = [&](uint4 v, int p) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float f0 = fmaf(bf16_lo(w[e]), sc[2 * e], sh[2 * e]), f1 = fmaf(bf16_hi(w[e]), sc[2 * e + 1], sh[2 * e + 1]);
+            if (SILU) { f0 = fmaf(f0, tanh_fast(f0), f0); f1 = fmaf(f1, tanh_fast(f1), f1); }
+            o[e] = pack_bf16(f0, f1);
+        }
+        *reinterpret_cast<uint4*>(dst + (int64_t)p * C) = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+    int p = row;
+    for (; p + 3 * R < rows; p += 4 * R) {
+        const uint4 a = *reinterpret_cast<const uint4*>(base + (size_t)p * pitch), b = *reinterpret_cast<const uint4*>(base + (size_t)(p + R) * pitch);
+        const uint4 c = *reinterpret_cast<const uint4*>(base + (size_t)(p + 2 * R) * pitch), d = *reinterpret_cast<const uint4*>(base + (size_t)(p + 3 * R) * pitch);
+        apply(a, p); apply(b, p + R); apply(c, p + 2 * R); apply(d, p + 3 * R);
+    }
+    for (; p < rows; p += R) apply(*reinterpret_cast<const uint4*>(base + (size_t)p * pitch), p);
+}
+
+// cluster size and rows per CTA of the shared-memory-resident form; 0 = the sample does not fit (cluster of 8 x ~190 KB)
+static int gn_resident_plan(int64_t S, int C, int* rows_per_cta, size_t* smem) {
+    if (C <= 0 || C % 8 != 0 || C > 2048 || S <= 0) return 0;
+    const int R = GNR_THREADS / (C / 8);
+    if (R < 1) return 0;
+    const size_t overhead = 128 + (size_t)(R * C + 2 * C) * sizeof(float2);
+    const size_t cap = 226 * 1024 - overhead;
+    const int64_t sample = S * C * 2;
+    int cl = 1;
+    while (cl < 8 && sample > (int64_t)cl * 48 * 1024) cl *= 2;
+    while (cl < 8 && (uint64_t)((S + cl - 1) / cl) * C * 2 > cap) cl *= 2;
+    const int64_t rows = (S + cl - 1) / cl;
+    if ((uint64_t)rows * C * 2 > cap) return 0;
+    *rows_per_cta = (int)rows;
+    *smem = overhead + (size_t)rows * C * 2;
+    return cl;
+}
+
+// ------------------------------------------------------------------------------------------
 // LayerNorm (one warp per row), GEGLU, nearest x2 upsample
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
@@ -608,32 +809,56 @@ extern "C" int gg_gn_apply(const void* x1_cl, int32_t C1, const void* x2_cl, int
     return launch_result();
 }
 
+extern "C" int32_t gg_gn_fused_resident(int64_t S, int32_t C) {
+    int rows = 0;
+    size_t smem = 0;
+    return gn_resident_plan(S, C, &rows, &smem);
+}
+
 extern "C" int gg_gn_fused(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* gamma, const float* beta,
                            void* y_cl, int32_t N, int64_t S, int32_t groups, float eps, int32_t silu, gg_stream_t stream) {
     GG_REQUIRE(x1_cl && y_cl && N > 0 && S > 0 && C1 > 0 && C2 >= 0 && (C2 == 0 || x2_cl) && groups > 0, GG_ERR_BAD_ARG);
     const int C = C1 + C2;
     GG_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0 && C <= 2048 && groups <= 256, GG_ERR_UNSUPPORTED);
     GG_REQUIRE(aligned(x1_cl, 16) && aligned(y_cl, 16) && (!x2_cl || aligned(x2_cl, 16)), GG_ERR_ALIGNMENT);
-    const int R = 256 / (C / 8);
-    const size_t smem = (size_t)(R * C + 2 * C) * sizeof(float2);
+    const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(x1_cl);
+    const __nv_bfloat16* a2 = reinterpret_cast<const __nv_bfloat16*>(x2_cl);
+    __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y_cl);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gn_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    GG_REQUIRE(smem <= 64 * 1024, GG_ERR_UNSUPPORTED);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(N * GNF_CL)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = GNF_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(x1_cl);
-    const __nv_bfloat16* a2 = reinterpret_cast<const __nv_bfloat16*>(x2_cl);
-    __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y_cl);
+    attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.stream = as_stream(stream);
+    int rows = 0;
+    size_t rsmem = 0;
+    const int cl = gn_resident_plan(S, C, &rows, &rsmem);
+    if (cl > 0) {       // the sample fits the shared memory of a cluster: one pass over L2 in each direction
+        cfg.gridDim = dim3((unsigned)(N * cl)); cfg.blockDim = dim3(GNR_THREADS); cfg.dynamicSmemBytes = rsmem;
+        attr[0].val.clusterDim.x = (unsigned)cl;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        cudaError_t e = silu ? cudaLaunchKernelEx(&cfg, gn_resident_kernel<true>, a1, (int)C1, a2, (int)C2, gamma, beta, yy, S, (int)groups, eps, rows)
+                             : cudaLaunchKernelEx(&cfg, gn_resident_kernel<false>, a1, (int)C1, a2, (int)C2, gamma, beta, yy, S, (int)groups, eps, rows);
+        if (e != cudaSuccess) return (int)e;
+        return launch_result();
+    }
+    const int R = 256 / (C / 8);
+    const size_t smem = (size_t)(R * C + 2 * C) * sizeof(float2);
+    GG_REQUIRE(smem <= 64 * 1024, GG_ERR_UNSUPPORTED);
+    cfg.gridDim = dim3((unsigned)(N * GNF_CL)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem;
+    attr[0].val.clusterDim.x = GNF_CL;
+    cfg.numAttrs = 1;
     cudaError_t e = silu ? cudaLaunchKernelEx(&cfg, gn_fused_kernel<true>, a1, (int)C1, a2, (int)C2, gamma, beta, yy, S, (int)groups, eps)
                          : cudaLaunchKernelEx(&cfg, gn_fused_kernel<false>, a1, (int)C1, a2, (int)C2, gamma, beta, yy, S, (int)groups, eps);
     if (e != cudaSuccess) return (int)e;

@@ -15,6 +15,7 @@ The reference has no slab mode; the semantics checked are those of its single-de
 one GPU, real ranks under torchrun) and by bench.py --gpus N (N > 1) to put slab parity into the driver's record.
 """
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -101,7 +102,16 @@ def unsplit_chain(model, x: torch.Tensor, cond: torch.Tensor, t_values, seed: in
     assert B == 1
     spatial = tuple(x.shape[2:])
     V = int(math.prod(spatial))
+    # the reference plan takes the kernel choices of a slab plan wherever those do not depend on the decomposition: the slab
+    # plans compute GroupNorm with the three-launch form (whole-volume statistics), so the unsplit plan does here, too --
+    # results then differ only through the order in which the ranks' group sums are combined
+    eng = unet.engine
+    prev = eng.fused_small_gn
+    eng.fused_small_gn = False
+    eng.plans.pop((1, tuple(spatial), unet.in_channels_padded, None, os.environ.get("GG_LANES")), None)
     plan = unet.plan_for(1, spatial)
+    eng.fused_small_gn = prev
+    eng.plans.pop((1, tuple(spatial), unet.in_channels_padded, None, os.environ.get("GG_LANES")), None)      # not a plan other callers should get
     xin = plan.inputs["x"]
     ops.nchw_to_cl(x.float().contiguous(), cond.float().contiguous(), c_pad=unet.in_channels_padded, out=xin)
     n_cond = cond.shape[1]

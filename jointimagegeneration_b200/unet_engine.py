@@ -241,12 +241,12 @@ class UNetEngine:
         self.fused_upsample = fused_upsample
         self.use_halo_conv = True
         self.use_roll_conv = True
-        # one-launch GroupNorm for L2-resident tensors (gg_gn_fused): measured SLOWER on config 3 (7.24 vs 4.85 ms per step:
-        # 8 CTAs per sample leave too few loads in flight), so off; kept as a tested kernel + knob
-        self.fused_small_gn = os.environ.get("GG_FUSED_SMALL_GN", "0") != "0"
-        # ... per SAMPLE: a cluster of 8 CTAs walks one sample, so the one-launch form wins only while a sample's slice per
-        # CTA is a few tens of KB (deep levels); larger samples keep the three-kernel form with its 64 KB chunks
-        self.fused_gn_max_bytes = int(os.environ.get("GG_FUSED_GN_MAX_KB", "384")) * 1024
+        # one-launch GroupNorm (gg_gn_fused, shared-memory-resident form: the slice of every CTA is loaded once by bulk async
+        # copies, statistics and normalisation read shared memory).  Measured inside CUDA graphs (tools/bench_gn.py,
+        # profiles/r2_lanes_and_pdl.md): the three launches cost only 9-16 us per GroupNorm there, the one launch 10-13 us with
+        # clusters of 2 / 4 CTAs per sample and 23-30 us with clusters of 8 (16 samples x 8 CTAs x ~200 KB do not become
+        # resident together).  So: 1 = where the plan is a cluster of 2 or 4 (default), 2 = wherever a sample fits, 0 = never.
+        self.fused_small_gn = int(os.environ.get("GG_FUSED_SMALL_GN", "1"))
         self.separate_skip = os.environ.get("GG_SEPARATE_SKIP", "0") != "0"     # see _resblock (measured: no gain, off)
         # GroupNorm + SiLU applied inside the depth-rolling conv (no separate pass); GG_FUSED_GN=0 is a tuning knob
         self.fused_gn_apply = os.environ.get("GG_FUSED_GN", "1") != "0"
@@ -392,9 +392,10 @@ class UNetEngine:
         """GroupNorm (+SiLU) over cat([x1, x2], channel) as a materialised tensor.  with_halo: the consumer is a conv with three
         depth taps (depth-slab mode: the result must carry valid halo planes)."""
         C1, C2 = x1.C, (x2.C if x2 is not None else 0)
-        if (self.fused_small_gn and self.slab is None and x1.S * (C1 + C2) * 2 <= self.fused_gn_max_bytes and C1 + C2 <= 2048
-                and (256 // ((C1 + C2) // 8)) * (C1 + C2) * 8 + 16 * (C1 + C2) <= 64 * 1024 and (C1 + C2) // 8 <= 256):
-            # L2-resident tensor: statistics + apply in one launch (a cluster per sample) instead of three dependent ones
+        if (self.fused_small_gn and (self.slab is None or self.slab.world == 1) and C1 + C2 <= 2048
+                and x1.stats is None and (x2 is None or x2.stats is None)
+                and int(self.lib.gg_gn_fused_resident(x1.S, C1 + C2)) in ((2, 4) if int(self.fused_small_gn) == 1 else (1, 2, 4, 8))):
+            # the sample fits the shared memory of one cluster: statistics + apply in one launch instead of three dependent ones
             y = self._new_act(ar, x1.N, x1.sp, C1 + C2)
             plan.add(self.lib.gg_gn_fused, x1.ip, C1, x2.ip if x2 is not None else 0, C2, _C.ptr(self._f32(norm.weight)),
                      _C.ptr(self._f32(norm.bias)), y.ip, x1.N, x1.S, norm.groups, float(norm.eps), int(silu))

@@ -686,9 +686,18 @@ def test_conv_stride2_asymmetric_pad(ops, sp, C, Cout):
 
 
 @pytest.mark.parametrize("N,sp,C1,C2,silu", [(16, (64, 64), 320, 0, True), (3, (5, 7, 9), 64, 128, False), (2, (8, 8), 800, 800, True),
-                                             (1, (4, 4, 4), 320, 0, True), (4, (16, 16), 640, 320, True)])
+                                             (1, (4, 4, 4), 320, 0, True), (4, (16, 16), 640, 320, True), (16, (64, 64), 160, 0, True),
+                                             (5, (32, 32), 320, 320, True), (8, (8, 16, 16), 256, 0, False), (2, (4, 4), 1600, 448, True),
+                                             (3, (3, 3), 32, 0, True), (2, (17, 32), 160, 320, True)])
 def test_group_norm_one_launch(ops, N, sp, C1, C2, silu):
-    """gg_gn_fused (cluster per sample, DSMEM reduction) vs the three-kernel GroupNorm and vs torch."""
+    """gg_gn_fused vs the three-kernel GroupNorm and vs torch: the shared-memory-resident form (cluster of 1..8 CTAs per
+    sample, bulk async loads, DSMEM reduction) where a sample fits, the L2-streaming cluster form where it does not
+    (the first case)."""
+    from jointimagegeneration_b200 import _C
+    S = int(np.prod(sp))
+    cl = int(_C.lib().gg_gn_fused_resident(S, C1 + C2))
+    assert (cl == 0) == (N == 16 and C1 == 320), cl
+    assert cl in (0, 1, 2, 4, 8)
     no_tf32()
     rs = np.random.RandomState(7)
     sp3 = (1,) * (3 - len(sp)) + tuple(sp)
