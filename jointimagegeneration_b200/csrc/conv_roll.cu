@@ -51,7 +51,7 @@ constexpr int R_SS_BYTES = 4096;    // (scale, shift) table: up to 512 channels 
 
 // Tuning knobs (environment), read ONCE at first use: the launch path itself never calls getenv.
 struct RollKnobs {
-    int no_tma_epi, g, sa, dbg, skip_first, xw;
+    int no_tma_epi, g, sa, dbg, skip_first, xw, cw;
     RollKnobs() {
         auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
         no_tma_epi = getenv("GG_ROLL_NO_TMA_EPI") != nullptr;
@@ -60,6 +60,7 @@ struct RollKnobs {
         dbg = getenv("GG_ROLL_DBG") != nullptr;
         skip_first = geti("GG_ROLL_SKIP_FIRST", 0);
         xw = geti("GG_ROLL_XW", 0);
+        cw = geti("GG_ROLL_CW", 1);
     }
 };
 static const RollKnobs& roll_knobs() { static const RollKnobs k; return k; }
@@ -73,6 +74,7 @@ struct RollSeg {
     int kb_base;     // first 64-wide K block of this source in the packed weights
     int taps;        // K blocks per chunk: 3 kh kw, or 1 (centre_only)
     int C;           // channels
+    int cw_idx0;     // centre_only sources with stationary weights: index of this source's first tile in the resident region
     int ss_off;      // XFORM: first entry of this source in the shared (scale, shift) table, -1 = used as is
     const float* ss; // XFORM: (scale, shift) of channel 0, sample 0
 };
@@ -84,6 +86,7 @@ struct alignas(64) RollParams {
     int tma_epi;                   // bf16 64-channel outputs leave (and residuals arrive) through a staging tile + TMA
     RollSeg seg[H_MAX_SEGS];
     int nseg, BNs, SA, SB;
+    int cw_tiles;                  // stationary 1x1x1 weights: tiles (one per 64-channel chunk of the centre_only sources) resident in smem, 0 = off
     int order[H_MAX_SEGS];         // sequence in which a step walks the sources (1x1x1 sources first, see conv_roll_fwd)
     uint32_t a_stage_bytes, b_stage_bytes, b_unit_bytes;
     int No, Do, Ho, Wo;
@@ -209,7 +212,8 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
     const int SA = p.SA, SB = p.SB;
     constexpr int BNs = BNS;
     uint8_t* smem_b = smem + (size_t)SA * p.a_stage_bytes;
-    uint8_t* smem_c = smem_b + (size_t)SB * p.b_stage_bytes;            // tma_epi: one 16 KB staging tile per epilogue group
+    uint8_t* smem_cw = smem_b + (size_t)SB * p.b_stage_bytes;          // stationary 1x1x1 weights: cw_tiles x b_unit_bytes
+    uint8_t* smem_c = smem_cw + (size_t)p.cw_tiles * p.b_unit_bytes;    // tma_epi: one 16 KB staging tile per epilogue group
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_c + (p.tma_epi ? 2 * R_STAGE_BYTES : 0));
     uint64_t* a_empty = a_full + R_MAX_SA;
     uint64_t* b_full = a_empty + R_MAX_SA;
@@ -218,7 +222,8 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
     uint64_t* slot_free = step_done + 2;            // [wi] (leader's): finished slot of brick wi drained and zeroed
     uint64_t* a_ready = slot_free + 2;              // XFORM (leader's): plane landed AND transformed in both CTAs
     uint64_t* res_full = a_ready + R_MAX_SA;        // [wi] tma_epi: residual brick landed in the staging tile
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+    uint64_t* cw_full = res_full + 2;               // (leader's) the stationary 1x1x1 weights of both CTAs have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cw_full + 1);
     // XFORM: per channel PAIR (2k, 2k+1) the quad (s_2k, s_2k+1, b_2k, b_2k+1), halved when SiLU follows: [ss_entries / 2]
     float4* ss_tab = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a_full) + 1024);
     float* bvec_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512);  // [2][BNs] bias + emb[n], per epilogue group
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
             for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 2 * (XW > 0 ? XW : 1)); }
             for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&step_done[i], 1); mbar_init(&slot_free[i], 8); mbar_init(&res_full[i], 1); }
+            mbar_init(cw_full, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -294,6 +300,22 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
         int sb = 0;
         uint32_t phb = 0;
         const int half_rows = BNs >> 1;
+        if (p.cw_tiles > 0 && item0 < p.total_items) {
+            // the 1x1x1 (skip) weights are the same in every step: one resident tile per 64-channel chunk, loaded once, so
+            // that they never take a slot of the weight ring (a two-stage ring next to five plane stages is all that fits)
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(cw_full, 2u * (uint32_t)p.cw_tiles * p.b_unit_bytes);
+                const uint32_t bar = leader_addr(cw_full);
+                for (int s = 0; s < p.nseg; ++s) {
+                    const RollSeg sg = p.seg[s];
+                    if (!sg.centre) continue;
+                    for (int j = 0; j < sg.nchunks; ++j)
+                        tma_load_2d_pair(smem_cw + (size_t)(sg.cw_idx0 + j) * p.b_unit_bytes, &p.wmap, bar, (sg.kb_base + j * sg.taps) * BK,
+                                         rank * half_rows);
+                }
+            }
+            __syncwarp();
+        }
         for (int item = item0; item < p.total_items; item += istep) {
             const RollItem it = roll_item(p, item);
             for (int t = 0; t < it.L + 2; ++t)
@@ -301,7 +323,7 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
                     for (int si = 0; si < p.nseg; ++si) {
                         const int s = p.order[si];
                         const RollSeg sg = p.seg[s];
-                        if (sg.centre && (t == 0 || t == it.L + 1)) continue;
+                        if (sg.centre && (p.cw_tiles > 0 || t == 0 || t == it.L + 1)) continue;
                         for (int j = 0; j < sg.nchunks; ++j) {
                             const int kb0 = sg.kb_base + j * sg.taps;
                             if (sg.centre) {
@@ -344,7 +366,9 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
         if (rank == 0) {
             const uint32_t idesc_full = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * BNs) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             const uint32_t idesc_one = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNs >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-            const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem_b);
+            const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem_b), cw_base = smem_u32(smem_cw);
+            const bool cw_on = p.cw_tiles > 0;
+            bool cw_ready = false;
             const uint64_t b_tmpl = make_sw128_desc_sbo(0, 1024u);
             const uint32_t tap16 = (3u * p.b_unit_bytes) >> 4;
             int sa = 0, sb = 0;
@@ -372,19 +396,24 @@ __global__ void __launch_bounds__(RollThreads<XW>::value, 1) conv_roll_kernel(co
                                 if constexpr (XFORM) tc_fence_after();
                                 const uint32_t a_stage16 = (a_base + (uint32_t)sa * p.a_stage_bytes) >> 4;
                                 if (sg.centre) {
-                                    mbar_wait(&b_full[sb], phb);
+                                    if (cw_on) {
+                                        if (!cw_ready) { mbar_wait(cw_full, 0u); cw_ready = true; }
+                                    } else {
+                                        mbar_wait(&b_full[sb], phb);
+                                    }
                                     tc_fence_after();
                                     if (elect_one()) {
                                         const uint64_t ad = a_tmpl | (uint64_t)a_stage16;
-                                        const uint64_t bd = b_tmpl | (uint64_t)((b_base + (uint32_t)sb * p.b_stage_bytes) >> 4);
+                                        const uint64_t bd = b_tmpl | (uint64_t)((cw_on ? cw_base + (uint32_t)(sg.cw_idx0 + j) * p.b_unit_bytes
+                                                                                       : b_base + (uint32_t)sb * p.b_stage_bytes) >> 4);
                                         const uint32_t dc = d_tmem + (uint32_t)((t % 3) * BNs);      // slot of output plane z
 #pragma unroll
                                         for (int k = 0; k < 4; ++k) umma_bf16_t<true>(dc, ad + 2 * k, bd + 2 * k, idesc_one, 1u);
-                                        umma_commit_t<true>(&b_empty[sb]);
+                                        if (!cw_on) umma_commit_t<true>(&b_empty[sb]);
                                         umma_commit_t<true>(&a_empty[sa]);
                                     }
                                     __syncwarp();
-                                    if (++sb == SB) { sb = 0; phb ^= 1u; }
+                                    if (!cw_on && ++sb == SB) { sb = 0; phb ^= 1u; }
                                 } else {
                                     for (int b = 0; b < sg.kh; ++b) {
                                         const uint32_t row16 = a_stage16 + (uint32_t)(b * sg.pitch) * 8u;
@@ -868,7 +897,14 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
         }
     }
     const int bar_bytes = 1024 + (xform ? R_SS_BYTES : 0) + (p.tma_epi ? 2 * R_STAGE_BYTES : 0);   // + barriers, additive vectors, (scale, shift) table
-    const int avail = H_SMEM_BUDGET - 1024 - bar_bytes;
+    // stationary 1x1x1 weights (GG_ROLL_CW=0 sends them through the weight ring again): one resident tile per chunk of the centre_only sources
+    p.cw_tiles = 0;
+    if (knobs.cw != 0) {
+        for (int s = 0; s < a->nsrc; ++s)
+            if (a->src[s].centre_only) { p.seg[s].cw_idx0 = p.cw_tiles; p.cw_tiles += p.seg[s].nchunks; }
+        if (p.cw_tiles > 16) p.cw_tiles = 0;
+    }
+    const int avail = H_SMEM_BUDGET - 1024 - bar_bytes - p.cw_tiles * (int)p.b_unit_bytes;
     const int tap_bytes = 3 * (int)p.b_unit_bytes;
     GG_REQUIRE(kwmax == 3, GG_ERR_UNSUPPORTED);
     // Ring shapes.  Default: a weight stage = one kw row of stacked tap tiles (G = 3, 12 MMAs per stage), three plane
@@ -900,7 +936,8 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
                 if (skip_first ? (c == (pass == 0)) : (pass == 0)) p.order[n++] = s2;
             }
     }
-    int SA = has_centre ? 5 : xform ? 4 : 3;
+    // (with stationary 1x1x1 weights the ring carries only the 3^3 taps; the resident tiles take 4 KB per chunk, i.e. half a plane stage)
+    int SA = has_centre ? (p.cw_tiles > 0 ? 4 : 5) : xform ? 4 : 3;
     int SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes);
     if (SB < 3 && SA > 3 && !has_centre) { SA = 3; SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes); }
     if (SB < 2 && SA > 3) { SA = 4; SB = (avail - SA * (int)p.a_stage_bytes) / (G * tap_bytes); }       // no transform table / staging: smaller budget
@@ -916,7 +953,8 @@ int conv_roll_fwd(const gg_conv_args* a, cudaStream_t stream) {
     p.b_stage_bytes = (uint32_t)(G * tap_bytes);
     for (int s = 0; s < a->nsrc; ++s) p.seg[s].g = (G > 1 && p.seg[s].kw == G) ? G : 1;
     p.SA = SA; p.SB = SB;
-    const size_t smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * p.b_stage_bytes + bar_bytes + 1024;
+    const size_t smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * p.b_stage_bytes + (size_t)p.cw_tiles * p.b_unit_bytes + bar_bytes + 1024;
+    GG_REQUIRE(smem <= (size_t)H_SMEM_BUDGET, GG_ERR_UNSUPPORTED);
 
     p.bias = a->bias; p.emb = a->emb; p.emb_stride = a->emb_stride;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.res_stride = a->res_stride;
