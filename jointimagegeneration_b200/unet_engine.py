@@ -251,10 +251,13 @@ class UNetEngine:
         # GroupNorm + SiLU applied inside the depth-rolling conv (no separate pass); GG_FUSED_GN=0 is a tuning knob
         self.fused_gn_apply = os.environ.get("GG_FUSED_GN", "1") != "0"
         # ... and inside the halo-brick conv (every other stride-1 3^d conv on grids >= 16 x 8: the LDM networks, the deeper
-        # CCDM levels): the same transform (eight warps) on its landed input windows.  Tested bit-exact, but measured NO gain:
-        # that kernel loads a window once per depth tap and per N tile, so it re-normalises what gg_gn_apply normalises once
-        # (config 2: conv +3.2 ms vs gn_apply -1.6 ms; config 4: -1 %; config 3: -1 %), so off by default
-        self.fused_gn_halo = os.environ.get("GG_FUSED_GN_HALO", "0") != "0"
+        # CCDM levels): the same transform (eight warps) on its landed input windows, bit-identical to gg_gn_apply + conv
+        # (tests/test_gpu_kernels.py::test_conv_halo_fused_groupnorm).  That kernel loads a window once per depth tap and per
+        # N tile, so it re-normalises what gg_gn_apply normalises once; while every "window transformed" signal of a CTA pair
+        # carried a GPU-scope fence (halo_common.cuh::mbar_arrive_remote, round 2) that cost more than the saved pass
+        # (config 2 +1.6 ms).  Without the fence it wins: config 2 43.3 -> 42.6 ms, config 3 4.69 -> 4.44, config 4 10.8 -> 10.2
+        # (tools/run_ab.sh), so ON by default; GG_FUSED_GN_HALO=0 restores the separate pass
+        self.fused_gn_halo = os.environ.get("GG_FUSED_GN_HALO", "1") != "0"
         self.use_split_k = True
         # in-kernel split-K reduction (the last split of a tile sums the partials itself, gg_conv_args.split_counters) instead of
         # the second launch: bit-identical, but only that CTA's 128 epilogue threads do the summing -- measured SLOWER
