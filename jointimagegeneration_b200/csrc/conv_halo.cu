@@ -35,9 +35,13 @@
 namespace gg {
 
 constexpr int H_ACC_COLS = 256;
-constexpr int H_XW = 8;                            // transform warps (four cannot keep up with the nine taps of a plane: measured)
-constexpr int H_THREADS_XF = H_THREADS + 32 * H_XW;  // + warps 7..: GroupNorm / SiLU transform of the landed halo planes
-constexpr int H_THREADS_E2 = H_THREADS + 128;        // + warps 7..10: second epilogue group (kernels without the transform)
+// Template parameter XW = transform warps: 0 = no fused input GroupNorm (warps 7..10 are a second epilogue group, 352 threads);
+// 8 = warps 7..14 transform, one epilogue group (3-D layers: three depth taps re-normalise every window, long reductions hide
+// the epilogue); 4 = warps 7..10 transform, warps 11..14 a second epilogue group (2-D layers: one window per chunk, short
+// reductions).  Measured: 8 vs 4 transform warps with one epilogue group (tools/run_ad.sh): config 2 41.7 / 42.1 ms, config 4
+// 10.02 / 9.84 ms; 8 vs 4 + second epilogue group (tools/run_ae.sh): config 3 4.44 / 4.48, config 4 10.41 / 10.38.  Default 8.
+constexpr int H_THREADS_XF = H_THREADS + 256;        // XW = 4 or 8
+constexpr int H_THREADS_E2 = H_THREADS + 128;        // XW = 0
 constexpr int H_MAX_SB = 8;
 constexpr int H_MAX_SA = 4;
 
@@ -80,8 +84,12 @@ struct alignas(64) HaloParams {
     int Hi, Wi;                    // input extents (= output extents: stride 1)
 };
 
-template <int G, bool STATS, bool PAIR, bool XFORM>
-__global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS_E2, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+template <int G, bool STATS, bool PAIR, int XW>
+__global__ void __launch_bounds__(XW > 0 ? H_THREADS_XF : H_THREADS_E2, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+    constexpr bool XFORM = XW > 0;
+    constexpr int H_XW = XW > 0 ? XW : 1;          // transform warps
+    constexpr int EGROUPS = XW == 8 ? 1 : 2;       // epilogue warp groups
+    constexpr int EG1_WARP = XW == 4 ? 11 : 7;     // first warp of the second group
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS_E2, 1) conv_h
         if (lane == 0) {
             for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], PAIR ? 2 * H_XW : H_XW); }
             for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (PAIR ? 8 : 4) * (XFORM ? 1 : 2)); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (PAIR ? 8 : 4) * EGROUPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS_E2, 1) conv_h
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;
         }
-    } else if (XFORM && warp >= 7) {
+    } else if (XFORM && warp >= 7 && warp < 7 + H_XW) {
         // ================================================================ transform (warps 7..10): GroupNorm (+ SiLU) in place on
         // every landed halo plane of a normalised source (same arithmetic and rounding points as gg_gn_apply: xf_pair).  Rows
         // are 128 B = 64 channels, SWIZZLE_128B: the 16-byte chunk at physical slot jp of stage row r holds channels
@@ -357,15 +365,15 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS_E2, 1) conv_h
             }
         }
     } else {
-        // ================================================================ epilogue (warps 2..5; without XFORM also warps 7..10:
-        // warps w and w + 5 serve the same TMEM lane quadrant and split the tile's columns at a multiple of 32)
-        constexpr int ET = XFORM ? 128 : 256;          // epilogue threads
-        const int eg = warp >= 7 ? 1 : 0;              // column group
+        // ================================================================ epilogue (warps 2..5; with two groups also warps 7..10
+        // (XW = 0) or 11..14 (XW = 4): warps of the same TMEM lane quadrant (warp % 4) split the tile's columns at a multiple of 32)
+        constexpr int ET = 128 * EGROUPS;              // epilogue threads
+        const int eg = (EGROUPS == 2 && warp >= EG1_WARP) ? 1 : 0;       // column group
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int rh = row >> 3, rw = row & 7;
-        const int etid = eg ? (int)threadIdx.x - H_THREADS + 128 : (int)threadIdx.x - 64;       // 0..ET-1 among the epilogue warps
-        const int c_split = XFORM ? BN : min(BN, (BN / 2 + 31) / 32 * 32);
+        const int etid = eg ? (int)threadIdx.x - 32 * EG1_WARP + 128 : (int)threadIdx.x - 64;       // 0..ET-1 among the epilogue warps
+        const int c_split = EGROUPS == 1 ? BN : min(BN, (BN / 2 + 31) / 32 * 32);
         const int c_lo = eg ? c_split : 0, c_n = eg ? BN - c_split : c_split;      // this warp's columns [c_lo, c_lo + c_n) of the tile
         uint32_t acc = 0, acc_phase = 0;
         int cur_n = -1, cur_nt = -1;
@@ -432,9 +440,10 @@ __global__ void __launch_bounds__(XFORM ? H_THREADS_XF : H_THREADS_E2, 1) conv_h
     }
 }
 
-template <int G, bool STATS, bool PAIR, bool XFORM>
+template <int G, bool STATS, bool PAIR, int XW>
 static int launch_halo(const HaloParams& p, int grid, size_t smem, cudaStream_t stream) {
-    auto* fn = conv_halo_kernel<G, STATS, PAIR, XFORM>;
+    constexpr bool XFORM = XW > 0;
+    auto* fn = conv_halo_kernel<G, STATS, PAIR, XW>;
     static bool attr_set = false;      // one flag per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_BUDGET);
@@ -455,15 +464,20 @@ static int launch_halo(const HaloParams& p, int grid, size_t smem, cudaStream_t 
     return launch_result();
 }
 template <bool STATS, bool PAIR>
-static int launch_halo_g(int G, bool xform, const HaloParams& p, int grid, size_t smem, cudaStream_t stream) {
-    if (xform) {
-        if (G == 3) return launch_halo<3, STATS, PAIR, true>(p, grid, smem, stream);
-        if (G == 2) return launch_halo<2, STATS, PAIR, true>(p, grid, smem, stream);
-        return launch_halo<1, STATS, PAIR, true>(p, grid, smem, stream);
+static int launch_halo_g(int G, int xw, const HaloParams& p, int grid, size_t smem, cudaStream_t stream) {
+    if (xw == 8) {
+        if (G == 3) return launch_halo<3, STATS, PAIR, 8>(p, grid, smem, stream);
+        if (G == 2) return launch_halo<2, STATS, PAIR, 8>(p, grid, smem, stream);
+        return launch_halo<1, STATS, PAIR, 8>(p, grid, smem, stream);
     }
-    if (G == 3) return launch_halo<3, STATS, PAIR, false>(p, grid, smem, stream);
-    if (G == 2) return launch_halo<2, STATS, PAIR, false>(p, grid, smem, stream);
-    return launch_halo<1, STATS, PAIR, false>(p, grid, smem, stream);
+    if (xw == 4) {
+        if (G == 3) return launch_halo<3, STATS, PAIR, 4>(p, grid, smem, stream);
+        if (G == 2) return launch_halo<2, STATS, PAIR, 4>(p, grid, smem, stream);
+        return launch_halo<1, STATS, PAIR, 4>(p, grid, smem, stream);
+    }
+    if (G == 3) return launch_halo<3, STATS, PAIR, 0>(p, grid, smem, stream);
+    if (G == 2) return launch_halo<2, STATS, PAIR, 0>(p, grid, smem, stream);
+    return launch_halo<1, STATS, PAIR, 0>(p, grid, smem, stream);
 }
 
 // ---------------------------------------------------------------------------------------- host
@@ -571,6 +585,11 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
     }
     p.SA = SA; p.SB = SB;
     const size_t smem = (size_t)p.SA * p.a_stage_bytes + (size_t)p.SB * p.b_stage_bytes + bar_bytes + 1024;
+    // transform warps of the fused input GroupNorm: eight (one epilogue group); GG_HALO_XW=4 selects four + a second epilogue
+    // group (see the XW template parameter) -- measured equal within the box-to-box noise on the 2-D networks
+    // (config 3: 4.44 / 4.48 ms, config 4: 10.41 / 10.38 ms, tools/run_ae.sh), so the simpler shape stays the default
+    static const int knob_xw = [] { const char* e = getenv("GG_HALO_XW"); return e ? atoi(e) : 0; }();
+    const int xw = !xform ? 0 : (knob_xw == 4 ? 4 : 8);
 
     p.bias = a->bias; p.emb = a->emb; p.emb_stride = a->emb_stride;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.res_stride = a->res_stride;
@@ -589,9 +608,9 @@ int conv_halo_fwd(const gg_conv_args* a, cudaStream_t stream) {
                                               (size_t)(grid * 4) * row_bytes, (size_t)a->N, stream);
             if (e != cudaSuccess) return (int)e;
         }
-        return pair ? launch_halo_g<true, true>(G, xform, p, grid, smem, stream) : launch_halo_g<true, false>(G, xform, p, grid, smem, stream);
+        return pair ? launch_halo_g<true, true>(G, xw, p, grid, smem, stream) : launch_halo_g<true, false>(G, xw, p, grid, smem, stream);
     }
-    return pair ? launch_halo_g<false, true>(G, xform, p, grid, smem, stream) : launch_halo_g<false, false>(G, xform, p, grid, smem, stream);
+    return pair ? launch_halo_g<false, true>(G, xw, p, grid, smem, stream) : launch_halo_g<false, false>(G, xw, p, grid, smem, stream);
 }
 
 }  // namespace gg
