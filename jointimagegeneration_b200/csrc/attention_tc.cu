@@ -53,6 +53,40 @@ __device__ __forceinline__ float ex2_fast(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// exp2 of a PAIR of scores on the FMA pipe instead of the MUFU (16 / clk / SM: the unit this kernel is bound by -- ncu: XU pipe
+// 62 % of peak while active, tensor pipe 15 %).  Round to the nearest integer with the 1.5 * 2^23 trick, degree-3 polynomial of
+// 2^f on f in [-1/2, 1/2] (relative error <= 6e-4, below the bf16 rounding of P: 2^-9), the integer part shifted straight into
+// the exponent field.  The argument is clamped to >= -125 (masked keys are -inf): such a term is 2^-125, nothing next to the
+// row maximum's 2^0 in the fp32 row sum and 0 after the bf16 rounding of P relative to it.
+// Every GG_ATTN_POLY-th pair takes this path (default 3; measured, tools/run_af.sh: T = 16384 site 1.003 ms with none, 0.884
+// with every 4th, 0.856 with every 3rd, 0.941 with every 2nd pair on the FMA pipe; T = 4096: 0.272 / 0.244 / 0.238 / 0.256).
+__device__ __forceinline__ void ex2_poly_x2(uint64_t x, float& e0, float& e1) {
+    float x0, x1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+    x0 = fmaxf(x0, -125.0f); x1 = fmaxf(x1, -125.0f);
+    const uint64_t xc = [&] { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x0), "f"(x1)); return r; }();
+    const uint64_t magic = [&] { uint64_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(12582912.0f)); return r; }();
+    const uint64_t nmagic = [&] { uint64_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(-12582912.0f)); return r; }();
+    uint64_t rr, nf, f, pp;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rr) : "l"(xc), "l"(magic));            // low mantissa bits = round(x)
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(nf) : "l"(rr), "l"(nmagic));           // round(x) as a float
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(xc), "l"(nf));                // f = x - round(x)
+    const uint64_t c3 = [&] { uint64_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(0.05550411f)); return r; }();
+    const uint64_t c2 = [&] { uint64_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(0.24022651f)); return r; }();
+    const uint64_t c1 = [&] { uint64_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(0.69314718f)); return r; }();
+    const uint64_t c0 = [&] { uint64_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(1.0f)); return r; }();
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pp) : "l"(c3), "l"(f), "l"(c2));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pp) : "l"(pp), "l"(f), "l"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pp) : "l"(pp), "l"(f), "l"(c0));
+    uint32_t p0, p1, r0, r1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(pp));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(r0), "=r"(r1) : "l"(rr));
+    e0 = __uint_as_float(p0 + (r0 << 23));         // magic's low 23 mantissa bits are 0x400000: << 23 leaves round(x) mod 2^9
+    e1 = __uint_as_float(p1 + (r1 << 23));
+}
+#ifndef GG_ATTN_POLY
+#define GG_ATTN_POLY 3          // k > 0: every k-th pair of scores takes the polynomial; 0: all exponentials on the MUFU
+#endif
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -302,7 +336,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 const uint64_t x = fma_f32x2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sl2x2, negm);
                 float x0, x1;
                 asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
-                const float e0 = ex2_fast(x0), e1 = ex2_fast(x1);
+                float e0, e1;
+                if (GG_ATTN_POLY > 0 && (i % (GG_ATTN_POLY > 0 ? GG_ATTN_POLY : 1)) == (GG_ATTN_POLY - 1)) ex2_poly_x2(x, e0, e1);
+                else { e0 = ex2_fast(x0); e1 = ex2_fast(x1); }
                 r[i] = pack_bf16(e0, e1);
                 ls2[i & 3] = add_f32x2(ls2[i & 3], pack_f32x2(e0, e1));
             }
