@@ -1,5 +1,7 @@
 // norm_small.cu -- GroupNorm32 (+SiLU), LayerNorm, GEGLU, nearest upsample, timestep embedding,
 // small-M linear.  All HBM- or latency-bound; channels-last bf16 activations, fp32 statistics.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gg {
@@ -687,51 +689,71 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
     if ((dim & 1) && j == 0) emb[(int64_t)b * dim + dim - 1] = 0.f;
 }
 
-// one warp per output feature n: the weight row is read once (128-bit when K % 4 == 0), up to MT rows of x per pass
-template <int MT, bool VEC>
+// one warp per NF consecutive output features: every weight row is read once (128-bit when K % 4 == 0); a chunk of up to MT rows
+// of x is loaded ONCE per warp and used for all NF features (NF = 4 for the wide projection of the timestep embedding onto every
+// ResBlock, [16, 640] x [~14 k, 640]^T: with one feature per warp each of the 14 k warps re-read all 40 KB of x through L1).
+// The arithmetic per output is the same expression in the same order for every NF: results do not depend on NF.
+// ACT_IN (SiLU on x) is a template parameter: as a run-time flag the compiler evaluated expf + a precise division for every
+// element of x and selected afterwards -- ~25 instructions next to each FMA.
+template <int MT, bool VEC, int NF, bool ACT_IN>
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ y, int M, int N,
-                                                           int K, int act_in, int act_out) {
+                                                           int K, int act_out) {
     pdl_launch_dependents();
     pdl_wait();
-    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int n0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * NF;
     const int lane = threadIdx.x & 31;
-    if (n >= N) return;
-    auto act = [&](float v) { return act_in ? v / (1.0f + expf(-v)) : v; };
+    if (n0 >= N) return;
+    auto act = [&](float v) { return ACT_IN ? v / (1.0f + expf(-v)) : v; };
     for (int m0 = 0; m0 < M; m0 += MT) {
-        float acc[MT];
+        float acc[MT][NF];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[m][f] = 0.f;
         if (VEC) {
             for (int k = lane * 4; k < K; k += 128) {
-                const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (int64_t)n * K + k));
+                float4 wv[NF];
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+                    wv[f] = n0 + f < N ? __ldg(reinterpret_cast<const float4*>(w + (int64_t)(n0 + f) * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int m = 0; m < MT; ++m) {
                     if (m0 + m < M) {
                         const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (int64_t)(m0 + m) * K + k));
-                        acc[m] += act(xv.x) * wv.x + act(xv.y) * wv.y + act(xv.z) * wv.z + act(xv.w) * wv.w;
+                        const float a0 = act(xv.x), a1 = act(xv.y), a2 = act(xv.z), a3 = act(xv.w);
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) acc[m][f] += a0 * wv[f].x + a1 * wv[f].y + a2 * wv[f].z + a3 * wv[f].w;
                     }
                 }
             }
         } else {
             for (int k = lane; k < K; k += 32) {
-                const float wv = __ldg(w + (int64_t)n * K + k);
+                float wv[NF];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) wv[f] = n0 + f < N ? __ldg(w + (int64_t)(n0 + f) * K + k) : 0.f;
 #pragma unroll
                 for (int m = 0; m < MT; ++m)
-                    if (m0 + m < M) acc[m] += act(__ldg(x + (int64_t)(m0 + m) * K + k)) * wv;
+                    if (m0 + m < M) {
+                        const float a = act(__ldg(x + (int64_t)(m0 + m) * K + k));
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) acc[m][f] += a * wv[f];
+                    }
             }
         }
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            float v = acc[m];
+        for (int m = 0; m < MT; ++m)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && m0 + m < M) {
-                v += bias ? bias[n] : 0.f;
-                if (act_out) v = v / (1.0f + expf(-v));
-                y[(int64_t)(m0 + m) * N + n] = v;
+            for (int f = 0; f < NF; ++f) {
+                float v = acc[m][f];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && m0 + m < M && n0 + f < N) {
+                    v += bias ? bias[n0 + f] : 0.f;
+                    if (act_out) v = v / (1.0f + expf(-v));
+                    y[(int64_t)(m0 + m) * N + n0 + f] = v;
+                }
             }
-        }
     }
 }
 
@@ -997,12 +1019,20 @@ extern "C" int gg_timestep_embedding(const float* t, float* emb, int32_t B, int3
 extern "C" int gg_small_linear(const float* x, const float* w, const float* b, float* y, int32_t M, int32_t N, int32_t K,
                                int32_t act_in, int32_t act_out, gg_stream_t stream) {
     GG_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0, GG_ERR_BAD_ARG);
-    const unsigned blocks = (unsigned)((N + 7) / 8);
     const bool vec = (K % 4 == 0) && aligned(x, 16) && aligned(w, 16);
     cudaStream_t s = as_stream(stream);
-    auto fn = M <= 4 ? (vec ? small_linear_kernel<4, true> : small_linear_kernel<4, false>)
-                     : (vec ? small_linear_kernel<16, true> : small_linear_kernel<16, false>);
-    const cudaError_t e = launch_k(fn, dim3(blocks), dim3(256), 0, s, x, w, b, y, (int)M, (int)N, (int)K, (int)act_in, (int)act_out);
+    // four features per warp once there are enough features to fill the GPU that way (>= 2 warps per SM scheduler)
+    const bool wide = N >= 4 * 8 * 2 * num_sms();
+    auto pick = [&](auto act_tag) {
+        constexpr bool A = decltype(act_tag)::value;
+        return wide ? (M <= 4 ? (vec ? small_linear_kernel<4, true, 4, A> : small_linear_kernel<4, false, 4, A>)
+                              : (vec ? small_linear_kernel<16, true, 4, A> : small_linear_kernel<16, false, 4, A>))
+                    : (M <= 4 ? (vec ? small_linear_kernel<4, true, 1, A> : small_linear_kernel<4, false, 1, A>)
+                              : (vec ? small_linear_kernel<16, true, 1, A> : small_linear_kernel<16, false, 1, A>));
+    };
+    auto fn = act_in ? pick(std::true_type{}) : pick(std::false_type{});
+    const unsigned blocks = (unsigned)((N + 8 * (wide ? 4 : 1) - 1) / (8 * (wide ? 4 : 1)));
+    const cudaError_t e = launch_k(fn, dim3(blocks), dim3(256), 0, s, x, w, b, y, (int)M, (int)N, (int)K, (int)act_out);
     if (e != cudaSuccess) return (int)e;
     return launch_result();
 }

@@ -259,6 +259,9 @@ class UNetEngine:
         # (tools/run_ab.sh), so ON by default; GG_FUSED_GN_HALO=0 restores the separate pass
         self.fused_gn_halo = os.environ.get("GG_FUSED_GN_HALO", "1") != "0"
         self.use_split_k = True
+        # split-K shape: at most splitk_max K ranges per tile, at least splitk_min_kb 64-wide K blocks per range (tuning knobs)
+        self.splitk_max = int(os.environ.get("GG_SPLITK_MAX", "16"))
+        self.splitk_min_kb = int(os.environ.get("GG_SPLITK_MIN_KB", "6"))
         # in-kernel split-K reduction (the last split of a tile sums the partials itself, gg_conv_args.split_counters) instead of
         # the second launch: bit-identical, but only that CTA's 128 epilogue threads do the summing -- measured SLOWER
         # (config 3: 8.5 vs 4.8 ms per step), so off; kept as a tested knob
@@ -563,7 +566,7 @@ class UNetEngine:
                 g = _C.ConvArgs.from_buffer_copy(a)
                 g.D, g.Do = D * self.slab.world, out_spatial[0] * self.slab.world
                 tiles = int(self.lib.gg_conv_num_tiles(C.byref(g)))
-            S = min(16, self.num_sms // max(tiles, 1), nkb // 6)
+            S = min(self.splitk_max, self.num_sms // max(tiles, 1), nkb // self.splitk_min_kb)
             if tiles * 2 <= self.num_sms and S >= 2:
                 ws = ar.alloc((S, N * int(math.prod(kernel_out_sp)), cout8), torch.float32)
                 a.split_k, a.workspace = S, _C.ptr(ws)
