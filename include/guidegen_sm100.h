@@ -239,9 +239,11 @@ typedef struct {
 int gg_gn_finalize(const gg_gn_finalize_args* a, gg_stream_t stream);
 int gg_gn_apply(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* scale_shift,
                 void* y_cl, int32_t N, int64_t S, int32_t silu, gg_stream_t stream);
-/* The same GroupNorm (+SiLU) in ONE launch for tensors that fit in L2 (a cluster of 8 CTAs per sample, channel sums
- * exchanged through distributed shared memory, fp64 combine in rank order): replaces the three dependent launches
- * above where their launch latency dominates (LDM latents, deep CCDM levels).  C1 + C2 <= 2048. */
+/* The same GroupNorm (+SiLU) in ONE launch (F.group_norm + F.silu of nn.py:17-19 / util.py:214-216 over th.cat([x1, x2], 1)): a
+ * cluster of 1..8 CTAs per sample, channel sums exchanged through distributed shared memory, fp64 combine in rank order.  When
+ * a sample fits the shared memory of the cluster (gg_gn_fused_resident() > 0) every CTA loads its slice once with bulk async
+ * copies and both passes read shared memory; otherwise the slice is streamed from L2 twice.  C1 + C2 <= 2048.  Same apply
+ * formula and rounding points as gg_gn_apply; the statistics differ from gg_gn_partial + gg_gn_finalize only in summation order. */
 int gg_gn_fused(const void* x1_cl, int32_t C1, const void* x2_cl, int32_t C2, const float* gamma, const float* beta, void* y_cl,
                 int32_t N, int64_t S, int32_t groups, float eps, int32_t silu, gg_stream_t stream);
 /* Cluster size (1..8) gg_gn_fused uses for a sample of S positions x C channels when the sample fits the shared memory of one
