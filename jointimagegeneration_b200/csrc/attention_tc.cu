@@ -29,7 +29,19 @@
 
 namespace gg {
 
-constexpr int AT_BM = 128, AT_BN = 128, AT_ST = 3, AT_THREADS = 320;
+// GG_ATTN_RS = 1 (tuning builds; OFF): every score row shared by TWO softmax threads (64 keys each; 16 softmax warps, four per
+// scheduler, instead of 8; the halves exchange their maxima / row sums through shared memory and a 64-thread named barrier per
+// key tile).  The idea was to hide the per-tile chain  TMEM load -> row maximum -> exponentials -> P store -> fence  behind more
+// warps; measured SLOWER on every site (tools/run_al.sh: T = 16384 0.856 -> 1.126 ms, T = 4096 0.238 -> 0.307, T = 1024
+// 0.103 -> 0.126): the kernel is bound by MUFU / FMA issue, not by latency, and the extra barrier + exchange per tile (and 96
+// registers per thread at 576 threads) cost more than the added warps hide.
+#ifndef GG_ATTN_RS
+#define GG_ATTN_RS 0
+#endif
+constexpr int AT_HS = GG_ATTN_RS ? 2 : 1;          // threads per score row
+constexpr int AT_NC = 128 / AT_HS;                 // score columns per thread
+constexpr int AT_BM = 128, AT_BN = 128, AT_ST = 3, AT_THREADS = 64 + 256 * AT_HS;
+constexpr int AT_XCH_BYTES = 2 * 2 * 2 * 128 * 4 + 2 * 2 * 128 * 4;      // maxima [parity][tile][half][row] + row sums [tile][half][row]
 constexpr int AT_TILE = 16384;              // 128 rows x 128 B
 
 struct alignas(64) AttnTcParams {
@@ -162,6 +174,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     uint64_t* pv_done = p_full + 2;                      // [2]
     uint64_t* s_free = pv_done + 2;                      // [2]  the softmax warps hold S_g(j) in registers: its TMEM columns may be rewritten
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+    float* xch_max = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(q_full) + 256);      // [2][2][2][128]
+    float* xch_sum = xch_max + 2 * 2 * 2 * 128;                                                // [2][2][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool two = p.two != 0;
@@ -173,7 +187,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         if (lane == 0) {
             mbar_init(q_full, 1);
             for (int i = 0; i < AT_ST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&s_free[i], 4); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4 * AT_HS); mbar_init(&pv_done[i], 1); mbar_init(&s_free[i], 4 * AT_HS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -270,48 +284,59 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             }
         }
     } else {
-        // ================================================================ softmax + output: warps 2..5 tile A, 6..9 tile B
-        const int g = warp >= 6 ? 1 : 0;
+        // ================================================================ softmax + output: 4 AT_HS warps per query tile (tile A first);
+        // within a tile, warps [0, 4) take the first AT_NC keys of every row, warps [4, 8) the rest (AT_HS = 2)
+        const int sw = warp - 2;
+        const int g = sw / (4 * AT_HS);
+        const int hf = (sw >> 2) % AT_HS;
         const int qd4 = warp & 3;
         const int row = qd4 * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(qd4 * 32) << 16);
-        const uint32_t s_addr = lane_base + COL_S + (uint32_t)g * AT_BN, o_addr = lane_base + COL_O + (uint32_t)g * O_STRIDE;
+        const uint32_t s_addr = lane_base + COL_S + (uint32_t)g * AT_BN + (uint32_t)(hf * AT_NC);
+        const uint32_t o_addr = lane_base + COL_O + (uint32_t)g * O_STRIDE;
         uint8_t* prow = smem_p + (size_t)(2 * g) * AT_TILE + row * 128;
         const int swz = row & 7;
         const float sl2 = p.scale_log2;
+        const int pair_bar = 1 + g * 4 + qd4;                      // named barrier of the two warps that share these 32 rows
         float m_used = -INFINITY, l = 0.f;
         const int n_mine = (g == 1 && !two) ? 0 : n_kt;          // one-tile CTAs: the warps of tile B have nothing to do
         for (int j = 0; j < n_mine; ++j) {
             const uint32_t ph = (uint32_t)j & 1u;
             mbar_wait(&s_full[g], ph);
             tc_fence_after();
-            const int key0 = j * AT_BN;
-            const bool tail = key0 + AT_BN > p.Tk;
-            // ---- the whole score row into registers (one TMEM round trip per tile), then hand the S columns back
-            uint32_t r[128];
+            const int key0 = j * AT_BN + hf * AT_NC;
+            const bool tail = key0 + AT_NC > p.Tk;
+            // ---- this thread's part of the score row into registers (one TMEM round trip per tile), then hand the S columns back
+            uint32_t r[AT_NC];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) tmem_ld16_nowait(s_addr + 16 * c, r + 16 * c);
+            for (int c = 0; c < AT_NC / 16; ++c) tmem_ld16_nowait(s_addr + 16 * c, r + 16 * c);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[g]);
             if (tail) {
 #pragma unroll
-                for (int i = 0; i < 128; ++i)
+                for (int i = 0; i < AT_NC; ++i)
                     if (key0 + i >= p.Tk) r[i] = 0xff800000u;       // -inf: never the maximum, exp2 = 0
             }
             // ---- row maximum (the scale is positive: maximum of the raw scores, scaled once; four independent three-input chains)
             float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int i = 0; i < 64; ++i) mx4[i & 3] = max3(mx4[i & 3], __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+            for (int i = 0; i < AT_NC / 2; ++i) mx4[i & 3] = max3(mx4[i & 3], __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+            if constexpr (AT_HS == 2) {         // the other half of the row: slots alternate with the tile parity, one barrier per tile
+                float* slot = xch_max + (((j & 1) * 2 + g) * 2) * 128;
+                slot[hf * 128 + row] = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                mx = fmaxf(mx, slot[(hf ^ 1) * 128 + row]);
+            }
             const float m_new = fmaxf(m_used, mx);
             const bool need = m_new > m_used + 8.0f;           // first tile: m_used = -inf
             bool waited = false;
             if (__any_sync(0xffffffffu, need)) {
                 const float alpha = need ? ex2_fast(m_used - m_new) : 1.0f;
                 if (need) { m_used = m_new; l *= alpha; }
-                if (j > 0) {        // O_g += ... of tile j - 1 must have landed before it is rescaled (j = 0: PV overwrites)
+                if (j > 0 && hf == 0) {        // O_g += ... of tile j - 1 must have landed before it is rescaled (j = 0: PV overwrites)
                     mbar_wait(&pv_done[g], ph ^ 1u);
                     tc_fence_after();
                     waited = true;
@@ -327,12 +352,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
             }
-            // ---- P = exp2(s c - m_used) as bf16.  Packed f32x2 arithmetic: per PAIR of scores one FMA, two MUFU.EX2, one pack and
-            // one add (the row sum, kept in independent partial sums); the packed P words replace the scores in place
+            // ---- P = exp2(s c - m_used) as bf16.  Packed f32x2 arithmetic: per PAIR of scores one FMA, two MUFU.EX2 (or the FMA-pipe
+            // polynomial), one pack and one add (the row sum, kept in independent partial sums); the packed P words replace the scores
             const uint64_t sl2x2 = pack_f32x2(sl2, sl2), negm = pack_f32x2(-m_used, -m_used);
             uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
+            for (int i = 0; i < AT_NC / 2; ++i) {
                 const uint64_t x = fma_f32x2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sl2x2, negm);
                 float x0, x1;
                 asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
@@ -348,9 +373,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             }
             // keys 8 q .. 8 q + 7 of this row = 16-byte piece q & 7 of chunk tile q >> 3 (64 keys per tile), swizzled by the row
 #pragma unroll
-            for (int q16 = 0; q16 < 16; ++q16) {
-                uint8_t* base = prow + (size_t)(q16 >> 3) * AT_TILE;
-                *reinterpret_cast<uint4*>(base + (((q16 & 7) ^ swz) << 4)) = make_uint4(r[4 * q16], r[4 * q16 + 1], r[4 * q16 + 2], r[4 * q16 + 3]);
+            for (int q16 = 0; q16 < AT_NC / 8; ++q16) {
+                const int qa = q16 + hf * (AT_NC / 8);             // piece index within the 128-key row
+                uint8_t* base = prow + (size_t)(qa >> 3) * AT_TILE;
+                *reinterpret_cast<uint4*>(base + (((qa & 7) ^ swz) << 4)) = make_uint4(r[4 * q16], r[4 * q16 + 1], r[4 * q16 + 2], r[4 * q16 + 3]);
             }
             float lsum;
             {
@@ -367,17 +393,24 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g]);
         }
-        // ---- output: O / l
+        // ---- output: O / l  (AT_HS = 2: the halves add their row sums, first half first, and take half of the channels each)
         if (n_mine > 0) {
         mbar_wait(&pv_done[g], ((uint32_t)(n_kt - 1)) & 1u);
         tc_fence_after();
+        if constexpr (AT_HS == 2) {
+            float* slot = xch_sum + (g * 2) * 128;
+            slot[hf * 128 + row] = l;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            l = slot[row] + slot[128 + row];
+        }
         const int t = q0 + g * AT_BM + row;
         const float inv = 1.0f / l;
-        __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)t * p.o_rs + (long long)h * p.o_hs;
+        constexpr int DC = D / AT_HS;           // output channels per thread
+        __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)t * p.o_rs + (long long)h * p.o_hs + hf * DC;
 #pragma unroll
-        for (int c = 0; c < D / 16; ++c) {
+        for (int c = 0; c < DC / 16; ++c) {
             uint32_t r[16];
-            tmem_ld16(o_addr + 16 * c, r);
+            tmem_ld16(o_addr + (uint32_t)(hf * DC) + 16 * c, r);
             tmem_ld_wait();
             if (t < p.Tq) {
                 uint32_t w[8];
@@ -454,7 +487,7 @@ static int launch_attention_tc(const gg_attn_args* a, cudaStream_t stream) {
         const int st = launch_result();
         if (st != GG_OK) return st;
     }
-    constexpr size_t smem = 1024 + 2 * AT_TILE + AT_ST * (AT_TILE + 2 * D * 128) + 4 * AT_TILE + 256;
+    constexpr size_t smem = 1024 + 2 * AT_TILE + AT_ST * (AT_TILE + 2 * D * 128) + 4 * AT_TILE + 256 + AT_XCH_BYTES;
     auto* fn = attention_tc_kernel<D>;
     static bool attr_set = false;
     if (!attr_set) {
