@@ -328,9 +328,9 @@ def run_ours(args, workload=None, K=None, W=None, sub=False):
         # captured on (config 2, 8 volumes per GPU, no text conditioning, one rank's full volume); not measured in-run
         traffic, traffic_src = None, None
         if workload == "ccdm_cfg2" and B == 8 and not slab:
-            traffic = 55.87e9 / 114
-            traffic_src = {"constant_from": "profiles/r1_conv_dram_ccdm_cfg2.md",
-                           "what": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the 114 conv launches of one forward = 55.87 GB; "
+            traffic = 55.36e9 / 114
+            traffic_src = {"constant_from": "profiles/r2_conv_dram_ccdm_cfg2.md",
+                           "what": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the 114 conv launches of one forward = 55.36 GB (final code of round 2); "
                                    "algorithmic conv input + output bytes: 56 GB (SURVEY.md 8d)"}
         line["roofline"] = {"bound": "tensor", "kernel": "conv_roll_kernel + conv_halo_kernel + conv_tcgen05_kernel (all %d conv launches of one step)" % n_conv,
                             "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
