@@ -94,6 +94,19 @@ __device__ __forceinline__ void stg_na_u4(void* p, uint4 v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 256-bit global accesses (sm_100: STG / LDG .256): one full 32-byte sector per lane instead of two half-filled ones.  The
+// epilogues of the conv kernels write (and read residuals) row by row -- a lane owns an output position, lanes of a warp are
+// 256+ bytes apart -- so every 128-bit access touches 32 separate sectors; ncu's source page of the folded-upsample conv had the
+// epilogue warps waiting on their own stores.  p must be 32-byte aligned.
+__device__ __forceinline__ void stg_u8(void* p, uint4 a, uint4 b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ldg_nc_u8(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 __device__ __forceinline__ void stg_na_f4(void* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

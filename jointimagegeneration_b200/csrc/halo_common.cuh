@@ -22,11 +22,19 @@ __device__ __forceinline__ void epilogue_row_stats(uint32_t t_addr, int BN, int 
         tmem_ld16_nowait(t_addr + c0, r);
         if (c0 + 16 < BN) tmem_ld16_nowait(t_addr + c0 + 16, r + 16);
         uint4 rr[4];
+        const bool res32 = res_row != nullptr && aligned32(res_row), y32 = aligned32(y_row);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-            rr[g] = (res_row != nullptr && valid && c0 + 8 * g < ncols) ? ldg_nc_u4(res_row + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+        for (int g = 0; g < 4; g += 2) {
+            if (res32 && valid && c0 + 8 * g + 8 < ncols) {
+                ldg_nc_u8(res_row + c0 + 8 * g, rr[g], rr[g + 1]);
+            } else {
+                rr[g] = (res_row != nullptr && valid && c0 + 8 * g < ncols) ? ldg_nc_u4(res_row + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+                rr[g + 1] = (res_row != nullptr && valid && c0 + 8 * g + 8 < ncols) ? ldg_nc_u4(res_row + c0 + 8 * g + 8) : make_uint4(0, 0, 0, 0);
+            }
+        }
         tmem_ld_wait();
         float a[32];
+        uint4 pk_even = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int c = c0 + 8 * g;
@@ -39,7 +47,10 @@ __device__ __forceinline__ void epilogue_row_stats(uint32_t t_addr, int BN, int 
             v[4] = __uint_as_float(r[8 * g + 4]) + b1.x + bf16_lo(rr[g].z); v[5] = __uint_as_float(r[8 * g + 5]) + b1.y + bf16_hi(rr[g].z);
             v[6] = __uint_as_float(r[8 * g + 6]) + b1.z + bf16_lo(rr[g].w); v[7] = __uint_as_float(r[8 * g + 7]) + b1.w + bf16_hi(rr[g].w);
             const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            if (on) *reinterpret_cast<uint4*>(y_row + c) = pk;
+            // pairs of 8-channel pieces leave as one 256-bit store when the row allows it
+            if (on && y32 && (g & 1) == 0 && c + 8 < ncols) pk_even = pk;
+            else if (on && y32 && (g & 1) == 1) stg_u8(y_row + c - 8, pk_even, pk);
+            else if (on) *reinterpret_cast<uint4*>(y_row + c) = pk;
             const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {

@@ -117,11 +117,19 @@ __device__ __forceinline__ void epilogue_row(uint32_t t_addr, int BN, int ncols,
                                              const __nv_bfloat16* __restrict__ res_row, void* y_row, int y_is_f32, bool valid,
                                              const float* __restrict__ emb_row = nullptr) {
     uint4 rn[4];
+    const bool res32 = res_row != nullptr && aligned32(res_row);      // c0 is a multiple of 32 elements: every 16-channel piece is 32-byte aligned
     auto load_res = [&](int c0) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-            rn[g] = (res_row != nullptr && valid && c0 + 8 * g < ncols) ? ldg_nc_u4(res_row + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+        for (int g = 0; g < 4; g += 2) {
+            if (res32 && valid && c0 + 8 * g + 8 < ncols) {
+                ldg_nc_u8(res_row + c0 + 8 * g, rn[g], rn[g + 1]);
+            } else {
+                rn[g] = (res_row != nullptr && valid && c0 + 8 * g < ncols) ? ldg_nc_u4(res_row + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+                rn[g + 1] = (res_row != nullptr && valid && c0 + 8 * g + 8 < ncols) ? ldg_nc_u4(res_row + c0 + 8 * g + 8) : make_uint4(0, 0, 0, 0);
+            }
+        }
     };
+    const bool y32 = !y_is_f32 && aligned32(y_row);
     load_res(0);
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -133,6 +141,7 @@ __device__ __forceinline__ void epilogue_row(uint32_t t_addr, int BN, int ncols,
         if (c0 + 32 < BN) load_res(c0 + 32);
         tmem_ld_wait();
         if (!valid) continue;
+        uint4 pk_even = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int c = c0 + 8 * g;
@@ -158,8 +167,11 @@ __device__ __forceinline__ void epilogue_row(uint32_t t_addr, int BN, int ncols,
                 *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
             } else {
                 __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y_row) + c;
-                *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                                                           pack_bf16(v[6], v[7]));
+                const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                // pairs of 8-channel pieces leave as one 256-bit store when the row allows it (g even: keep, g odd: store both)
+                if (y32 && (g & 1) == 0 && c + 8 < ncols) { pk_even = pk; }
+                else if (y32 && (g & 1) == 1) { stg_u8(yp - 8, pk_even, pk); }
+                else { *reinterpret_cast<uint4*>(yp) = pk; }
             }
         }
     }
