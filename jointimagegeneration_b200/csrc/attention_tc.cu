@@ -416,8 +416,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 uint32_t w[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) w[i] = pack_bf16(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
-                *reinterpret_cast<uint4*>(orow + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4*>(orow + 16 * c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                if (aligned32(orow)) {          // 16 channels = one 32-byte sector per lane
+                    stg_u8(orow + 16 * c, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+                } else {
+                    *reinterpret_cast<uint4*>(orow + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(orow + 16 * c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                }
             }
         }
         }

@@ -129,7 +129,7 @@ __device__ __forceinline__ void epilogue_row(uint32_t t_addr, int BN, int ncols,
             }
         }
     };
-    const bool y32 = !y_is_f32 && aligned32(y_row);
+    const bool y32 = !y_is_f32 && aligned32(y_row), yf32 = y_is_f32 && aligned32(y_row);
     load_res(0);
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -163,8 +163,13 @@ __device__ __forceinline__ void epilogue_row(uint32_t t_addr, int BN, int ncols,
             }
             if (y_is_f32) {
                 float* yp = reinterpret_cast<float*>(y_row) + c;
-                *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                if (yf32) {         // eight floats = one 32-byte sector (split-K partial tiles, fp32 head logits)
+                    stg_u8(yp, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                           make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+                } else {
+                    *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(yp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
             } else {
                 __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y_row) + c;
                 const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
