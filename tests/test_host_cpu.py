@@ -289,3 +289,51 @@ def test_bench_reference_arm_prints_one_json_line():
     r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                         capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_round2_host_planning_logic(monkeypatch):
+    """Host-side decisions added in round 2, none of which needs a GPU: the cluster plan of the one-launch GroupNorm
+    (gg_gn_fused_resident), the sample lanes of a plan (Plan.lanes / UNetEngine.pick_lanes) and the SASS of the remote
+    mbarrier arrive (no GPU-scope fence in front of the accumulator hand-backs of the pair kernels)."""
+    from jointimagegeneration_b200 import _C
+    from jointimagegeneration_b200.unet_engine import Plan, UNetEngine
+    lib = _C.lib()
+    # ---- gg_gn_fused_resident: smallest power-of-two cluster with >= one CTA per 48 KB that holds the sample; 0 = does not fit
+    assert lib.gg_gn_fused_resident(16, 800) == 1              # 25 KB
+    assert lib.gg_gn_fused_resident(64, 640) == 2              # 80 KB
+    assert lib.gg_gn_fused_resident(64, 1440) == 4             # 180 KB
+    assert lib.gg_gn_fused_resident(4096, 160) == 8            # 1.3 MB: 164 KB per CTA
+    assert lib.gg_gn_fused_resident(4096, 320) == 0            # 2.6 MB: more than eight CTAs hold
+    assert lib.gg_gn_fused_resident(256, 12) == 0              # channels not a multiple of 8
+    # ---- Plan.lanes bookkeeping
+    p = Plan()
+    f = lambda *a: 0
+    p.add(f, 1), p.add(f, 2)
+    assert len(p.lanes) == 1 and p.num_launches == 2 and p.steps is p.lanes[0]
+    p.begin_lane(1)
+    p.add(f, 3), p.add(f, 4), p.add(f, 5)
+    assert len(p.lanes) == 2 and p.num_launches == 5
+    assert [a for _, a in p.steps] == [(1,), (2,), (3,), (4,), (5,)]
+    assert [a for _, a in p.body_steps] == [(1,), (3,), (4,)]          # everything but each lane's head conv
+    # ---- pick_lanes: pinned by GG_LANES (reduced until it divides the batch), one lane in depth-slab mode, two for mid-sized 2-D batches
+    import torch
+    eng = UNetEngine(torch.nn.Linear(1, 1), dims=2, num_heads=1, num_head_channels=-1)
+    monkeypatch.delenv("GG_LANES", raising=False)
+    assert eng.pick_lanes(16, (64, 64)) == 1 and eng.pick_lanes(2, (512, 512)) == 2 and eng.pick_lanes(8, (512, 512)) == 1
+    eng3 = UNetEngine(torch.nn.Linear(1, 1), dims=3, num_heads=1, num_head_channels=-1)
+    assert eng3.pick_lanes(8, (64, 128, 128)) == 1 and eng3.pick_lanes(2, (32, 64, 64)) == 1
+    monkeypatch.setenv("GG_LANES", "4")
+    assert eng.pick_lanes(16, (64, 64)) == 4 and eng.pick_lanes(6, (64, 64)) == 3 and eng.pick_lanes(1, (64, 64)) == 1
+    eng.slab = object()
+    assert eng.pick_lanes(16, (64, 64)) == 1
+    # ---- SASS: the pair kernels keep exactly the two cluster-wide barriers of their prologue / exit (MEMBAR.ALL.GPU twice),
+    # none in front of the per-tile / per-plane remote arrives
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if os.path.exists(cuobjdump):
+        for fn in ("_ZN2gg16conv_halo_kernelILi3ELb1ELb1ELi0EEEvNS_10HaloParamsE", "_ZN2gg16conv_roll_kernelILi3ELb1ELi64ELi4EEEvNS_10RollParamsE"):
+            sass = subprocess.run([cuobjdump, "-sass", "-fun", fn, _C.LIB_PATH], capture_output=True, text=True).stdout
+            assert "UTCHMMA.2CTA" in sass, fn
+            assert sass.count("MEMBAR.ALL.GPU") == 2, (fn, sass.count("MEMBAR.ALL.GPU"))
+        sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN2gg16conv_halo_kernelILi2ELb1ELb1ELi0EEEvNS_10HaloParamsE", _C.LIB_PATH],
+                              capture_output=True, text=True).stdout
+        assert "STG.E.ENL2.256" in sass, "no 256-bit epilogue stores in the halo-brick conv"
