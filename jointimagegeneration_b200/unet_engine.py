@@ -269,6 +269,9 @@ class UNetEngine:
         self.num_sms = torch.cuda.get_device_properties(next(model.parameters()).device).multi_processor_count \
             if next(model.parameters()).is_cuda else 148
         self.halo_gn_stats = os.environ.get("GG_HALO_STATS", "1") != "0"    # ... except in the halo / roll kernels (shuffle-reduced per tile)
+        # per sample; below it the separate gg_gn_partial pass stays (re-measured at the end of round 2, tools/run_aq.sh: config 3
+        # 4.08 ms with 8192, 4.21 with 4096, 4.44 with 1024; config 4 9.93 / 10.04 / 10.11)
+        self.halo_stats_min_positions = int(os.environ.get("GG_HALO_STATS_MIN", "8192"))
         self.fused_gn_stats = False     # GroupNorm statistics from the conv epilogue: correct, but the extra epilogue
                                         # work costs more than the separate (cached) statistics pass saves on B200
         self.slab = None            # sharding.SlabComm: depth-slab decomposition of ONE volume over ranks
@@ -511,7 +514,7 @@ class UNetEngine:
         # the halo kernels reduce GroupNorm column sums in their epilogue (bf16 outputs): one partial row per (CTA, warp),
         # i.e. up to 592 rows of C (sum, sum sq) pairs per sample -- less traffic than re-reading the tensor only when
         # a sample has well over 8 x 592 positions (the 64 x 64 latents of the LDM configs do not)
-        halo_stats = halo and stats and self.halo_gn_stats and not f32_out and int(math.prod(out_spatial)) >= 8192
+        halo_stats = halo and stats and self.halo_gn_stats and not f32_out and int(math.prod(out_spatial)) >= self.halo_stats_min_positions
         algo = 1 if halo and (halo_stats or not (stats and self.fused_gn_stats)) else 0
         if algo == 1 and self._roll_ok(dims, stride, taps, offsets, cout, out_spatial, y_strides):
             algo = 4        # narrow outputs: depth-rolling kernel (three depth taps stacked along N)
